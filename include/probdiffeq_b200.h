@@ -1,0 +1,174 @@
+/*
+ * probdiffeq_b200 -- C ABI of the B200-native adaptive probabilistic IVP step loop.
+ *
+ * The reference (pnkraemer/probdiffeq) has no FFI: its seam is the Python `Solver` protocol
+ * (probdiffeq/_ivpsolve/solver_protocols.py:33-57) plus the injected `error` and `control`
+ * collaborators of `solve_adaptive_save_at` (probdiffeq/_ivpsolve/solvers_via_adaptive_steps.py:46-54).
+ * This header is the boundary a `jax.ffi` / ctypes binding for that path would target: the object
+ * graph (prior x strategy x constraint x solver x error x control) is lowered to the POD
+ * `pdeq_config`, and the three loop entry points of the reference become three calls.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless stated otherwise; all floating point is float64.
+ *  - The caller owns every buffer. The library allocates nothing that outlives a call.
+ *  - Calls enqueue work on `stream` (a cudaStream_t passed as void*) and return immediately.
+ *  - Return value: 0 ok; <0 invalid argument / unsupported configuration; >0 CUDA error code.
+ *    `pdeq_last_error()` returns a thread-local message for the last non-zero return.
+ *  - Batched layout ("ensemble of B independent IVPs", the reference's `jax.vmap` axis leads):
+ *      tcoeffs      [B][n][d]        Taylor coefficients u, u', ..., u^(nu) at t0 (unnormalised)
+ *      mean out     [B][T][n][d]
+ *      chol out     isotropic [B][T][n][n]; blockdiag [B][T][d][n][n]; dense [B][T][nd][nd]
+ *                   (left square roots, cov = L L^T, exactly the reference's `cholesky_flat`)
+ *      output_scale isotropic/dense [B][T]; blockdiag [B][T][d]
+ *    n = num_derivatives + 1.
+ */
+#ifndef PROBDIFFEQ_B200_H
+#define PROBDIFFEQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDEQ_VERSION 100
+
+/* state_space_model_{isotropic,blockdiag,dense}: probdiffeq/_probdiffeq/ssm_impl_*.py */
+enum { PDEQ_FACT_ISOTROPIC = 0, PDEQ_FACT_BLOCKDIAG = 1, PDEQ_FACT_DENSE = 2 };
+/* constraint_ode_ts0 / constraint_ode_ts1: probdiffeq/_probdiffeq/ssm_impl_api.py:520-558 */
+enum { PDEQ_CONSTRAINT_TS0 = 0, PDEQ_CONSTRAINT_TS1 = 1 };
+/* solver / solver_mle / solver_dynamic: probdiffeq/_probdiffeq/solvers.py:636,318,483 */
+enum { PDEQ_SOLVER_PLAIN = 0, PDEQ_SOLVER_MLE = 1, PDEQ_SOLVER_DYNAMIC = 2 };
+/* strategy_filter / strategy_smoother_fixedpoint: probdiffeq/_probdiffeq/estimators_and_losses.py:347,473 */
+enum { PDEQ_STRATEGY_FILTER = 0, PDEQ_STRATEGY_FIXEDPOINT = 1 };
+/* error_residual_std / error_state_std: probdiffeq/_probdiffeq/solvers.py:850,999 */
+enum { PDEQ_ERROR_RESIDUAL_STD = 0, PDEQ_ERROR_STATE_STD = 1 };
+/* error_norm_scale_then_rms / error_norm_rms_then_scale: probdiffeq/_probdiffeq/solvers.py:770,794 */
+enum { PDEQ_NORM_SCALE_THEN_RMS = 0, PDEQ_NORM_RMS_THEN_SCALE = 1 };
+/* control_integral / control_proportional_integral: probdiffeq/_ivpsolve/controllers.py:66,24 */
+enum { PDEQ_CONTROL_INTEGRAL = 0, PDEQ_CONTROL_PI = 1 };
+
+/* per-instance status written by the loops (the reference has no runtime failure channel) */
+enum { PDEQ_STATUS_OK = 0, PDEQ_STATUS_NONFINITE = 1, PDEQ_STATUS_MAX_ATTEMPTS = 2 };
+
+#define PDEQ_MAX_COEFFS 8 /* n = num_derivatives + 1 <= 8 */
+
+typedef struct pdeq_config {
+  int32_t factorisation;   /* PDEQ_FACT_*        */
+  int32_t num_derivatives; /* nu; n = nu + 1     */
+  int32_t ode_dim;         /* d                  */
+  int32_t vf_id;           /* pdeq_vf_id(name)   */
+  int32_t constraint;      /* PDEQ_CONSTRAINT_*  */
+  int32_t solver;          /* PDEQ_SOLVER_*      */
+  int32_t strategy;        /* PDEQ_STRATEGY_*    */
+  int32_t error;           /* PDEQ_ERROR_*       */
+  int32_t error_norm;      /* PDEQ_NORM_*        */
+  int32_t control;         /* PDEQ_CONTROL_*     */
+  int32_t clip_dt;         /* solvers_via_adaptive_steps.py:20,51 */
+  int32_t derivative_idx;  /* error_state_std(derivative_idx=)  solvers.py:1022 */
+  int32_t error_per_unit_step;               /* solvers.py:912,1023 */
+  int32_t re_linearize_after_calibration;    /* solver_dynamic    solvers.py:496 */
+  int32_t correct_asymptotic_underconfidence; /* solver_mle        solvers.py:332 */
+  int32_t max_attempts;    /* guard the reference lacks; <=0 means 2^31-1 */
+  double safety, factor_min, factor_max;            /* controllers.py:30-33 */
+  double exponent_integral, exponent_proportional;  /* controllers.py:34-35 */
+  /* IWP system matrices, computed by the host exactly like the reference does
+     (probdiffeq/_probdiffeq/utilities.py:57-84: flipped Pascal A, Cholesky of flipped Hilbert Q,
+     factorials via exp(lgamma)); row-major, leading dimension PDEQ_MAX_COEFFS. */
+  double sys_a[PDEQ_MAX_COEFFS][PDEQ_MAX_COEFFS];
+  double sys_q[PDEQ_MAX_COEFFS][PDEQ_MAX_COEFFS];
+  double factorials[PDEQ_MAX_COEFFS + 1]; /* factorials[k] = k! as the reference evaluates it */
+} pdeq_config;
+
+/* Inputs shared by the loop entry points. A `*_stride` of 0 broadcasts one row to all instances. */
+typedef struct pdeq_problem {
+  int64_t num_instances;        /* B */
+  const double* tcoeffs;        /* [B][n][d] */
+  const double* init_std;       /* NULL = exact initial condition; isotropic [.][n], else [.][n][d] */
+  int64_t init_std_stride;      /* in doubles */
+  const double* prior_scale;    /* NULL = ones; isotropic [.][1], blockdiag/dense [.][d] */
+  int64_t prior_scale_stride;
+  const double* params;         /* [.][pdeq_vf_num_params(vf_id)] */
+  int64_t params_stride;
+} pdeq_problem;
+
+/* Outputs of the loop entry points (T checkpoints per instance). Optional pointers may be NULL. */
+typedef struct pdeq_solution {
+  double* t;             /* [B][T] */
+  double* mean;          /* [B][T][n][d] */
+  double* chol;          /* see layout note above; may be NULL */
+  double* output_scale;  /* may be NULL */
+  int32_t* num_steps;    /* [B][T] accepted steps up to each checkpoint (entry 0 is 0) */
+  int32_t* num_attempts; /* [B] attempted steps (accepted + rejected); may be NULL */
+  int32_t* status;       /* [B] PDEQ_STATUS_* */
+  /* fixed-point smoother only (may be NULL): backward conditionals checkpoint k -> k-1, k = 1..T-1,
+     with the preconditioner folded in: x_{k-1} | x_k ~ N(G x_k + xi, Xi Xi^T). */
+  double* bw_gain;       /* blockdiag [B][T][d][n][n] (entry 0 unused) */
+  double* bw_mean;       /* [B][T][n][d] */
+  double* bw_chol;       /* like chol */
+} pdeq_solution;
+
+int pdeq_version(void);
+const char* pdeq_last_error(void);
+
+/* Registry of vector-field device functors (the benchmark problems of the reference:
+   benchmarks/A0..A5). Returns -1 for unknown names. */
+int pdeq_vf_id(const char* name);
+int pdeq_vf_num_params(int vf_id);
+int pdeq_vf_ode_order(int vf_id);
+/* fixed dimension of the problem, or 0 if the functor accepts any d (linear, burgers) */
+int pdeq_vf_dim(int vf_id);
+
+/* 0 if (cfg) is a combination the library has a kernel for, negative otherwise (see pdeq_last_error). */
+int pdeq_config_supported(const pdeq_config* cfg);
+
+/* Bytes of device scratch `workspace` the loop entry points need for (cfg, B, T). */
+size_t pdeq_workspace_bytes(const pdeq_config* cfg, int64_t num_instances, int32_t num_checkpoints);
+
+/* jetexpand_ode_padded_scan / jetexpand_ode_unroll (probdiffeq/_probdiffeq/jet_expansion_algorithms.py:49,110):
+   u0 [B][ode_order][d] -> tcoeffs [B][n][d], n = num_derivatives + 1 (unnormalised derivatives at t0). */
+int pdeq_taylor_init(const pdeq_config* cfg, int64_t num_instances, const double* u0,
+                     const double* params, int64_t params_stride, double t0, double* tcoeffs,
+                     void* stream);
+
+/* ivpsolve.dt0 (probdiffeq/_ivpsolve/stepsize_initialisers.py:7-21): out[B]. */
+int pdeq_dt0(const pdeq_config* cfg, int64_t num_instances, const double* u0, const double* params,
+             int64_t params_stride, double t0, double scale, double nugget, double* out,
+             void* stream);
+
+/* ivpsolve.solve_adaptive_save_at (probdiffeq/_ivpsolve/solvers_via_adaptive_steps.py:46-148);
+   solve_adaptive_terminal_values (:16-43) is the T == 2 case with save_at = {t0, t1}.
+   save_at [T] is shared by all instances. dt0 [.] with stride 0 or 1. */
+int pdeq_solve_adaptive_save_at(const pdeq_config* cfg, const pdeq_problem* problem,
+                                const double* save_at, int32_t num_checkpoints, double atol,
+                                double rtol, const double* dt0, int64_t dt0_stride, double eps,
+                                double damp, const pdeq_solution* solution, void* workspace,
+                                size_t workspace_bytes, void* stream);
+
+/* ivpsolve.solve_fixed_grid (probdiffeq/_ivpsolve/solvers_via_fixed_steps.py:11-34): one step per
+   grid interval, every grid point is stored. grid [T] shared by all instances. */
+int pdeq_solve_fixed_grid(const pdeq_config* cfg, const pdeq_problem* problem, const double* grid,
+                          int32_t num_gridpoints, double damp, const pdeq_solution* solution,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* loss_lml_terminal_values (probdiffeq/_probdiffeq/estimators_and_losses.py:20-50): observe Taylor
+   coefficient `tcoeff_index` of N(mean, chol chol^T) through noise `std` and evaluate the log-pdf of
+   `data`. mean [B][n][d], chol as above with T == 1, data [.][d], std [.][1|d], out [B]. */
+int pdeq_lml_terminal_values(const pdeq_config* cfg, int64_t num_instances, int32_t tcoeff_index,
+                             const double* mean, const double* chol, const double* data,
+                             int64_t data_stride, const double* std, int64_t std_stride,
+                             double* out, void* stream);
+
+/* Sum `n` doubles in place across the ranks of an NCCL communicator (ncclComm_t passed as void*):
+   the ensemble log-marginal-likelihood reduction. The only collective on this path. */
+int pdeq_allreduce_sum_f64(void* nccl_comm, double* buf, int64_t n, void* stream);
+
+/* Device-side FP64 FMA throughput probe used for the roofline denominator: runs `iters` dependent
+   FMA chains on every SM and returns the elapsed milliseconds in *ms and the FLOP count in *flops. */
+int pdeq_fp64_peak_probe(int32_t iters, double* ms, double* flops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROBDIFFEQ_B200_H */

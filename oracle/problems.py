@@ -310,6 +310,19 @@ def ode(name, params=None):
     return Ode(name, params)
 
 
+def taylor_coefficients_batched(name, params, inits, t, num):
+    """Taylor coefficients for an ensemble at once: params (B, P), inits = sequence of (B, d) -> (B, q+num, d).
+
+    Same recursion as `Ode.taylor_coefficients`, with the ensemble as a trailing array axis (works for the
+    right-hand sides that only index components: lotka_volterra, hires, vanderpol, linear).
+    """
+    vf = Ode(name, None if _REGISTRY[name][2] == 0 else np.zeros(_REGISTRY[name][2]))
+    params = np.asarray(params, dtype=np.float64)
+    vf.params = tuple(params[:, k] for k in range(params.shape[1])) if params.size else ()
+    out = vf.taylor_coefficients([np.asarray(u, dtype=np.float64).T for u in inits], t, num)  # (n, d, B)
+    return np.ascontiguousarray(np.transpose(out, (2, 0, 1)))
+
+
 # Initial values of the benchmark problems ---------------------------------------------------------
 
 

@@ -1,0 +1,79 @@
+"""In-tree build of libprobdiffeq_b200.so (hand-written CUDA for sm_100a) with plain nvcc.
+
+The translation units under ``csrc/`` and ``csrc/inst/`` are compiled in parallel and linked into
+``probdiffeq_b200/lib/libprobdiffeq_b200.so``.  The shared object is git-ignored but travels to the
+GPU box with the repository snapshot.  No GPU is needed to build.
+"""
+
+from __future__ import annotations
+
+import concurrent.futures
+import os
+import pathlib
+import shutil
+import subprocess
+import sys
+
+ROOT = pathlib.Path(__file__).resolve().parent
+CSRC = ROOT / "csrc"
+OBJ = ROOT / "build"
+LIB = ROOT / "lib" / "libprobdiffeq_b200.so"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+]  # fmt: skip
+
+
+def _nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found; cannot build libprobdiffeq_b200.so")
+    return exe
+
+
+def sources() -> list[pathlib.Path]:
+    return sorted(CSRC.glob("*.cu")) + sorted((CSRC / "inst").glob("*.cu"))
+
+
+def _headers_mtime() -> float:
+    hdrs = list(CSRC.glob("*.cuh")) + [ROOT.parent / "include" / "probdiffeq_b200.h"]
+    return max(h.stat().st_mtime for h in hdrs)
+
+
+def _compile(src: pathlib.Path, force: bool, verbose: bool) -> pathlib.Path:
+    obj = OBJ / (src.stem + ".o")
+    newest = max(src.stat().st_mtime, _headers_mtime())
+    if not force and obj.exists() and obj.stat().st_mtime >= newest:
+        return obj
+    cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src.name}:\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        sys.stderr.write(res.stderr)
+    return obj
+
+
+def build(force: bool = False, verbose: bool = False, jobs: int | None = None) -> pathlib.Path:
+    OBJ.mkdir(exist_ok=True)
+    LIB.parent.mkdir(exist_ok=True)
+    srcs = sources()
+    jobs = jobs or min(len(srcs), os.cpu_count() or 4)
+    with concurrent.futures.ThreadPoolExecutor(max_workers=jobs) as pool:
+        objs = list(pool.map(lambda s: _compile(s, force, verbose), srcs))
+    if force or not LIB.exists() or any(o.stat().st_mtime > LIB.stat().st_mtime for o in objs):
+        cmd = [_nvcc(), "-shared", "-o", str(LIB), *map(str, objs), "-ldl"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(path)

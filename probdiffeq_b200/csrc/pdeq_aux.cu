@@ -1,0 +1,230 @@
+// Once-per-solve device routines around the step loop: Taylor-coefficient initialisation, initial
+// step size, terminal-value log-marginal-likelihood. All are generic in the ODE dimension d.
+#include <cuda_runtime.h>
+
+#include "pdeq_dispatch.cuh"
+
+namespace pdeq {
+
+int api_fail(int code, const char* fmt, ...);       // pdeq_api.cu
+int api_cuda_fail(cudaError_t e, const char* where);  // pdeq_api.cu
+int api_validate(const pdeq_config* c);              // pdeq_api.cu
+
+// ---------------------------------------------------------------------------------------------------
+// Taylor-mode initialisation (probdiffeq/_probdiffeq/jet_expansion_algorithms.py:49-177).
+// One launch per new coefficient ("pass"); thread (b, i) evaluates component i of the vector field on the
+// truncated series built from the coefficients known so far and writes u^(pass+q)_i.
+// `out` [B][n][d] holds unnormalised derivatives and doubles as the workspace.
+// ---------------------------------------------------------------------------------------------------
+template <int KS>
+struct GlobalSeriesAcc {
+  const double* __restrict__ U;  // [n][d] of one instance, unnormalised derivatives
+  int d, known;                  // coefficients 0..known-1 are valid
+  PDEQ_DI Series<KS> operator()(int j, int i) const {
+    Series<KS> s;
+    double kfact = 1.0;  // k!
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      if (k > 0) kfact *= double(k);
+      s.c[k] = (k + j < known) ? U[(k + j) * d + i] / kfact : 0.0;  // (u^(j))_k = u^(k+j) / k!
+    }
+    return s;
+  }
+};
+
+template <class VF, int KS>
+__global__ void taylor_pass_kernel(int64_t B, int n, int d, int pass, const double* __restrict__ params,
+                                   int64_t params_stride, double t0, double* __restrict__ out) {
+  constexpr int q = VF::order, P = VF::num_params > 0 ? VF::num_params : 1;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= B * d) return;
+  const int64_t b = gid / d;
+  const int i = (int)(gid % d);
+  double par[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) par[k] = VF::num_params > 0 ? params[b * params_stride + k] : 0.0;
+  GlobalSeriesAcc<KS> acc{out + b * (int64_t)n * d, d, pass + q};
+  const Series<KS> F = VF::template component<Series<KS>>(i, d, acc, par, t0);
+  double fk = 0.0, pf = 1.0;  // F.c[pass] * pass!  == u^(pass+q)
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    if (k > 0) pf *= double(k);
+    if (k == pass) fk = F.c[k] * pf;
+  }
+  out[(b * n + pass + q) * d + i] = fk;
+}
+
+template <class VF, int KS>
+static cudaError_t taylor_run(int64_t B, int n, int d, const double* u0, const double* params,
+                              int64_t params_stride, double t0, double* out, cudaStream_t s) {
+  constexpr int q = VF::order;
+  // copy the initial values into the first q coefficient slots
+  cudaError_t e = cudaMemcpy2DAsync(out, sizeof(double) * n * d, u0, sizeof(double) * q * d,
+                                    sizeof(double) * q * d, B, cudaMemcpyDeviceToDevice, s);
+  if (e != cudaSuccess) return e;
+  const int threads = 128;
+  const int64_t total = B * d;
+  const int grid = (int)((total + threads - 1) / threads);
+  for (int pass = 0; pass < n - q; ++pass) {
+    taylor_pass_kernel<VF, KS><<<grid, threads, 0, s>>>(B, n, d, pass, params, params_stride, t0, out);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+template <class VF>
+static cudaError_t taylor_dispatch_ks(int ks, int64_t B, int n, int d, const double* u0, const double* params,
+                                      int64_t ps, double t0, double* out, cudaStream_t s) {
+  switch (ks) {
+    case 1: return taylor_run<VF, 1>(B, n, d, u0, params, ps, t0, out, s);
+    case 2: return taylor_run<VF, 2>(B, n, d, u0, params, ps, t0, out, s);
+    case 3: return taylor_run<VF, 3>(B, n, d, u0, params, ps, t0, out, s);
+    case 4: return taylor_run<VF, 4>(B, n, d, u0, params, ps, t0, out, s);
+    case 5: return taylor_run<VF, 5>(B, n, d, u0, params, ps, t0, out, s);
+    case 6: return taylor_run<VF, 6>(B, n, d, u0, params, ps, t0, out, s);
+    case 7: return taylor_run<VF, 7>(B, n, d, u0, params, ps, t0, out, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ivpsolve.dt0 (probdiffeq/_ivpsolve/stepsize_initialisers.py:7-21): scale * ||u0|| / (||f(u0)|| + nugget).
+// One warp per instance; lanes stride over the components.
+// ---------------------------------------------------------------------------------------------------
+struct GlobalAcc {
+  const double* __restrict__ u;  // [order][d]
+  int d;
+  PDEQ_DI double operator()(int k, int i) const { return u[k * d + i]; }
+};
+
+template <class VF>
+__global__ void dt0_kernel(int64_t B, int d, const double* __restrict__ u0, const double* __restrict__ params,
+                           int64_t params_stride, double t0, double scale, double nugget,
+                           double* __restrict__ out) {
+  constexpr int q = VF::order, P = VF::num_params > 0 ? VF::num_params : 1;
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  const int lane = threadIdx.x % 32;
+  if (b >= B) return;
+  double par[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) par[k] = VF::num_params > 0 ? params[b * params_stride + k] : 0.0;
+  GlobalAcc acc{u0 + b * (int64_t)q * d, d};
+  double su = 0.0, sf = 0.0;
+  for (int i = lane; i < d; i += 32) {
+    const double ui = acc(0, i);
+    const double fi = VF::template component<double>(i, d, acc, par, t0);
+    su = fma(ui, ui, su);
+    sf = fma(fi, fi, sf);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    su += __shfl_xor_sync(0xffffffffu, su, o);
+    sf += __shfl_xor_sync(0xffffffffu, sf, o);
+  }
+  if (lane == 0) out[b] = scale * sqrt(su) / (sqrt(sf) + nugget);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// loss_lml_terminal_values for the isotropic and block-diagonal factorisations
+// (probdiffeq/_probdiffeq/estimators_and_losses.py:20-50 with IsotropicNormal.logpdf_scalar_flat,
+// ssm_impl_isotropic.py:225-236, and BlockDiagNormal.logpdf_scalar_flat, ssm_impl_blockdiag.py:305-316).
+// Observing one coefficient through scalar noise gives a 1x1 factor per dimension:
+//   s_i = sqrt(sum_j L[idx][j]^2 + std_i^2),  logpdf = sum_i -0.5 (2 log s_i + ((u_i - m_i)/s_i)^2 + log 2pi).
+// One warp per instance; lanes stride over dimensions.
+// ---------------------------------------------------------------------------------------------------
+__global__ void lml_terminal_kernel(int64_t B, int n, int d, int blockdiag, int idx, const double* __restrict__ mean,
+                                    const double* __restrict__ chol, const double* __restrict__ data,
+                                    int64_t data_stride, const double* __restrict__ std_, int64_t std_stride,
+                                    int std_per_dim, double* __restrict__ out) {
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  const int lane = threadIdx.x % 32;
+  if (b >= B) return;
+  const double* m = mean + b * (int64_t)n * d + (int64_t)idx * d;
+  const double log2pi = 1.8378770664093453;
+  double acc = 0.0;
+  for (int i = lane; i < d; i += 32) {
+    const double* Lrow = blockdiag ? chol + ((b * d + i) * (int64_t)n + idx) * n : chol + (b * (int64_t)n + idx) * n;
+    double ss = 0.0;
+    for (int j = 0; j <= idx; ++j) ss = fma(Lrow[j], Lrow[j], ss);
+    const double sd = std_[b * std_stride + (std_per_dim ? i : 0)];
+    const double s = sqrt(fma(sd, sd, ss));
+    const double w = (data[b * data_stride + i] - m[i]) / s;
+    acc += -0.5 * (2.0 * log(s) + w * w + log2pi);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[b] = acc;
+}
+
+}  // namespace pdeq
+
+using namespace pdeq;
+
+#define PDEQ_VF_SWITCH(vf_id, CALL)                                 \
+  switch (vf_id) {                                                  \
+    case VF_LOTKA_VOLTERRA: { using VF = LotkaVolterra; CALL; } break; \
+    case VF_PLEIADES: { using VF = Pleiades; CALL; } break;         \
+    case VF_HIRES: { using VF = Hires; CALL; } break;               \
+    case VF_VANDERPOL: { using VF = VanDerPol; CALL; } break;       \
+    case VF_LINEAR: { using VF = Linear; CALL; } break;             \
+    case VF_BURGERS: { using VF = Burgers; CALL; } break;           \
+    default: break;                                                 \
+  }
+
+extern "C" {
+
+int pdeq_taylor_init(const pdeq_config* cfg, int64_t num_instances, const double* u0, const double* params,
+                     int64_t params_stride, double t0, double* tcoeffs, void* stream) {
+  int rc = api_validate(cfg);
+  if (rc != 0) return rc;
+  if (u0 == nullptr || tcoeffs == nullptr) return api_fail(-22, "u0/tcoeffs is NULL");
+  if (pdeq_vf_num_params(cfg->vf_id) > 0 && params == nullptr) return api_fail(-22, "params is NULL");
+  if (num_instances == 0) return 0;
+  const int n = cfg->num_derivatives + 1, d = cfg->ode_dim, q = pdeq_vf_ode_order(cfg->vf_id);
+  cudaError_t e = cudaErrorInvalidValue;
+  PDEQ_VF_SWITCH(cfg->vf_id, e = taylor_dispatch_ks<VF>(n - q, num_instances, n, d, u0, params, params_stride, t0,
+                                                        tcoeffs, (cudaStream_t)stream));
+  if (e != cudaSuccess) return api_cuda_fail(e, "taylor_init");
+  return 0;
+}
+
+int pdeq_dt0(const pdeq_config* cfg, int64_t num_instances, const double* u0, const double* params,
+             int64_t params_stride, double t0, double scale, double nugget, double* out, void* stream) {
+  int rc = api_validate(cfg);
+  if (rc != 0) return rc;
+  if (u0 == nullptr || out == nullptr) return api_fail(-22, "u0/out is NULL");
+  if (pdeq_vf_num_params(cfg->vf_id) > 0 && params == nullptr) return api_fail(-22, "params is NULL");
+  if (num_instances == 0) return 0;
+  const int threads = 128;
+  const int grid = (int)((num_instances * 32 + threads - 1) / threads);
+  PDEQ_VF_SWITCH(cfg->vf_id, (dt0_kernel<VF><<<grid, threads, 0, (cudaStream_t)stream>>>(
+                                 num_instances, cfg->ode_dim, u0, params, params_stride, t0, scale, nugget, out)));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return api_cuda_fail(e, "dt0");
+  return 0;
+}
+
+int pdeq_lml_terminal_values(const pdeq_config* cfg, int64_t num_instances, int32_t tcoeff_index,
+                             const double* mean, const double* chol, const double* data, int64_t data_stride,
+                             const double* std, int64_t std_stride, double* out, void* stream) {
+  int rc = api_validate(cfg);
+  if (rc != 0) return rc;
+  if (mean == nullptr || chol == nullptr || data == nullptr || std == nullptr || out == nullptr)
+    return api_fail(-22, "NULL argument");
+  if (tcoeff_index < 0 || tcoeff_index > cfg->num_derivatives) return api_fail(-5, "bad tcoeff_index");
+  int fact = cfg->factorisation;
+  if (fact == PDEQ_FACT_DENSE && cfg->ode_dim == 1) fact = PDEQ_FACT_ISOTROPIC;
+  if (fact == PDEQ_FACT_DENSE) return api_fail(-10, "lml_terminal_values: dense factorisation with d > 1 not built");
+  if (num_instances == 0) return 0;
+  const int threads = 128;
+  const int grid = (int)((num_instances * 32 + threads - 1) / threads);
+  lml_terminal_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
+      num_instances, cfg->num_derivatives + 1, cfg->ode_dim, fact == PDEQ_FACT_BLOCKDIAG, tcoeff_index, mean, chol,
+      data, data_stride, std, std_stride, fact == PDEQ_FACT_BLOCKDIAG, out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return api_cuda_fail(e, "lml_terminal_values");
+  return 0;
+}
+
+}  // extern "C"

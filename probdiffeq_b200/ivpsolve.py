@@ -1,0 +1,265 @@
+"""IVP loops, mirroring ``probdiffeq.ivpsolve`` of the reference (probdiffeq/ivpsolve.py:10-14).
+
+``solve_adaptive_terminal_values`` / ``solve_adaptive_save_at`` / ``solve_fixed_grid`` keep the
+reference's signatures (probdiffeq/_ivpsolve/solvers_via_adaptive_steps.py:16-22,34-36,46-54,100-102;
+probdiffeq/_ivpsolve/solvers_via_fixed_steps.py:11-13,21) but run the whole loop -- for the whole
+ensemble -- inside one persistent CUDA kernel.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+
+import numpy as np
+import torch
+
+from probdiffeq_b200 import _lib
+from probdiffeq_b200 import probdiffeq as _pdq
+
+__all__ = [
+    "control_integral",
+    "control_proportional_integral",
+    "dt0",
+    "solve_adaptive_save_at",
+    "solve_adaptive_terminal_values",
+    "solve_fixed_grid",
+]
+
+
+class control_proportional_integral:
+    """reference: _ivpsolve/controllers.py:24-63."""
+
+    kind = "proportional_integral"
+
+    def __init__(self, *, safety=0.95, factor_min=0.2, factor_max=10.0, exponent_integral=0.3, exponent_proportional=0.4):
+        self.safety = float(safety)
+        self.factor_min = float(factor_min)
+        self.factor_max = float(factor_max)
+        self.exponent_integral = float(exponent_integral)
+        self.exponent_proportional = float(exponent_proportional)
+
+
+class control_integral:
+    """reference: _ivpsolve/controllers.py:66-84."""
+
+    kind = "integral"
+
+    def __init__(self, *, safety=0.95, factor_min=0.2, factor_max=10.0):
+        self.safety = float(safety)
+        self.factor_min = float(factor_min)
+        self.factor_max = float(factor_max)
+        self.exponent_integral = 1.0
+        self.exponent_proportional = 0.0
+
+
+def _lower(prior, solver, error, control, clip_dt, max_attempts=0) -> _lib.Config:
+    """Object graph -> pdeq_config."""
+    constraint = solver.constraint
+    if error is not None and error.constraint is not constraint:
+        c2 = error.constraint
+        if (c2.kind, c2.ode.vf_id, c2.factorisation) != (constraint.kind, constraint.ode.vf_id, constraint.factorisation):
+            raise ValueError("solver and error estimator must share the constraint on the accelerated path.")
+    if constraint.factorisation != prior.factorisation:
+        raise ValueError(
+            f"constraint was built for the {constraint.factorisation} model, prior for {prior.factorisation}."
+        )
+    kw = dict(
+        constraint=_lib.CONSTRAINT[constraint.kind],
+        solver=_lib.SOLVER[solver.kind],
+        strategy=_lib.STRATEGY[solver.strategy.kind],
+        clip_dt=int(bool(clip_dt)),
+        max_attempts=int(max_attempts),
+    )
+    for k, v in solver.options.items():
+        kw[k] = v
+    if error is not None:
+        kw.update(
+            error=_lib.ERROR[error.kind],
+            error_norm=_lib.NORM[error.error_norm],
+            derivative_idx=error.derivative_idx,
+            error_per_unit_step=int(error.error_per_unit_step),
+        )
+    if control is not None:
+        kw.update(
+            control=_lib.CONTROL[control.kind],
+            safety=control.safety,
+            factor_min=control.factor_min,
+            factor_max=control.factor_max,
+            exponent_integral=control.exponent_integral,
+            exponent_proportional=control.exponent_proportional,
+        )
+    cfg = _pdq._make_config(
+        fact=prior.factorisation, nu=prior.num_derivatives, d=prior.ode_dim, vf=constraint.ode, **kw
+    )
+    rc = _lib.load().pdeq_config_supported(C.byref(cfg))
+    _lib.check(rc, "pdeq_config_supported")
+    return cfg
+
+
+def _problem(prior, vf):
+    B = prior.tcoeffs.shape[0]
+    params, pstride = vf.params_on_device(B)
+    pr = _lib.Problem()
+    pr.num_instances = B
+    pr.tcoeffs = _pdq._ptr(prior.tcoeffs)
+    pr.init_std = _pdq._ptr(prior.init_std)
+    pr.init_std_stride = 0 if prior.init_std is None or prior.init_std.shape[0] == 1 else prior.init_std[0].numel()
+    pr.prior_scale = _pdq._ptr(prior.output_scale)
+    pr.prior_scale_stride = (
+        0 if prior.output_scale is None or prior.output_scale.shape[0] == 1 else prior.output_scale.shape[1]
+    )
+    pr.params = _pdq._ptr(params)
+    pr.params_stride = pstride
+    return pr, (params,)
+
+
+def _alloc_solution(prior, T, want_chol=True):
+    B, n, d = prior.tcoeffs.shape
+    dev = prior.tcoeffs.device
+    fact = prior.factorisation
+    f64 = dict(dtype=torch.float64, device=dev)
+    chol_shape = {"isotropic": (B, T, n, n), "blockdiag": (B, T, d, n, n), "dense": (B, T, n * d, n * d)}[fact]
+    if fact == "dense" and d == 1:
+        chol_shape = (B, T, n, n)
+    scale_shape = (B, T, d) if fact == "blockdiag" else (B, T)
+    bufs = dict(
+        t=torch.empty((B, T), **f64),
+        mean=torch.empty((B, T, n, d), **f64),
+        chol=torch.empty(chol_shape, **f64) if want_chol else None,
+        output_scale=torch.empty(scale_shape, **f64),
+        num_steps=torch.empty((B, T), dtype=torch.int32, device=dev),
+        num_attempts=torch.empty((B,), dtype=torch.int32, device=dev),
+        status=torch.empty((B,), dtype=torch.int32, device=dev),
+    )
+    so = _lib.Solution()
+    for k, v in bufs.items():
+        setattr(so, k, _pdq._ptr(v))
+    return so, bufs
+
+
+def _wrap(prior, bufs, *, terminal: bool):
+    sol = _pdq.ProbabilisticSolution(
+        t=bufs["t"],
+        u=_pdq.Normal(prior.factorisation if not (prior.factorisation == "dense" and prior.ode_dim == 1) else "isotropic",
+                      bufs["mean"], bufs["chol"]),
+        output_scale=bufs["output_scale"],
+        num_steps=bufs["num_steps"],
+        num_attempts=bufs["num_attempts"],
+        status=bufs["status"],
+    )  # fmt: skip
+    if terminal:
+        sol = sol._index(lambda x: x[:, -1])
+    if prior.unbatched:
+        sol = sol._index(lambda x: x[0])
+        sol.num_attempts = sol.num_attempts[0]
+        sol.status = sol.status[0]
+    return sol
+
+
+def _workspace(cfg, B, T, device):
+    nbytes = _lib.load().pdeq_workspace_bytes(C.byref(cfg), B, T)
+    return torch.empty((max(int(nbytes), 8),), dtype=torch.uint8, device=device), int(nbytes)
+
+
+def _run_adaptive(prior, solver, error, control, clip_dt, save_at, atol, rtol, dt0, eps, damp, *, terminal,
+                  want_chol=True, max_attempts=0):  # fmt: skip
+    if control is None:
+        control = control_integral()  # solvers_via_adaptive_steps.py:87-90
+    cfg = _lower(prior, solver, error, control, clip_dt, max_attempts)
+    B = prior.tcoeffs.shape[0]
+    grid = _pdq._as_device_f64(np.asarray(save_at, dtype=np.float64) if not isinstance(save_at, torch.Tensor) else save_at)
+    if grid.ndim != 1:
+        raise ValueError("save_at must be one-dimensional (shared by the ensemble).")
+    T = grid.shape[0]
+    dt0_t = _pdq._as_device_f64(dt0).reshape(-1)
+    if dt0_t.shape[0] not in (1, B):
+        raise ValueError("dt0 must be a scalar or have one entry per ensemble member.")
+    pr, keep = _problem(prior, solver.constraint.ode)
+    so, bufs = _alloc_solution(prior, T, want_chol)
+    ws, nbytes = _workspace(cfg, B, T, prior.tcoeffs.device)
+    rc = _lib.load().pdeq_solve_adaptive_save_at(
+        C.byref(cfg), C.byref(pr), _pdq._ptr(grid), T, float(atol), float(rtol), _pdq._ptr(dt0_t),
+        0 if dt0_t.shape[0] == 1 else 1, float(eps), float(damp), C.byref(so), _pdq._ptr(ws), nbytes,
+        _pdq._stream(),
+    )  # fmt: skip
+    _lib.check(rc, "pdeq_solve_adaptive_save_at")
+    del keep
+    return _wrap(prior, bufs, terminal=terminal)
+
+
+def solve_adaptive_terminal_values(solver, error, control=None, clip_dt: bool = True, *, max_attempts: int = 0):
+    """reference: _ivpsolve/solvers_via_adaptive_steps.py:16-43."""
+
+    def solve(u, /, *, t0, t1, atol, rtol, dt0=0.1, eps=1e-8, damp=0.0, want_cholesky=True):
+        save_at = np.asarray([t0, t1], dtype=np.float64)
+        return _run_adaptive(u, solver, error, control, clip_dt, save_at, atol, rtol, dt0, eps, damp,
+                             terminal=True, want_chol=want_cholesky, max_attempts=max_attempts)  # fmt: skip
+
+    return solve
+
+
+def solve_adaptive_save_at(*, solver, error, control=None, clip_dt: bool = False, warn: bool = True,
+                           max_attempts: int = 0):  # fmt: skip
+    """reference: _ivpsolve/solvers_via_adaptive_steps.py:46-148."""
+    if not solver.is_suitable_for_save_at and warn:
+        msg = f"Solver {solver} should not be used in solve_adaptive_save_at."
+        msg += " This is typically caused by the wrong strategy selection."
+        msg += " Try using filters or fixed-point smoothers."
+        warnings.warn(msg, stacklevel=1)
+
+    def solve(u, save_at, atol, rtol, dt0=0.1, eps=1e-8, damp=0.0, want_cholesky=True):
+        return _run_adaptive(u, solver, error, control, clip_dt, save_at, atol, rtol, dt0, eps, damp,
+                             terminal=False, want_chol=want_cholesky, max_attempts=max_attempts)  # fmt: skip
+
+    return solve
+
+
+def solve_fixed_grid(*, solver):
+    """reference: _ivpsolve/solvers_via_fixed_steps.py:11-34."""
+    if not solver.is_suitable_for_save_every_step:
+        msg = f"Solver {solver} should not be used in solve_adaptive_save_every_step/solve_fixed_grid."
+        msg += " This is typically caused by using a fixed-point smoother."
+        msg += " Try using filters or fixed-interval smoothers instead."
+        warnings.warn(msg, stacklevel=1)
+
+    def solve(u, /, *, grid, damp: float = 0.0, want_cholesky=True):
+        prior = u
+        cfg = _lower(prior, solver, None, None, False)
+        B = prior.tcoeffs.shape[0]
+        g = _pdq._as_device_f64(np.asarray(grid, dtype=np.float64) if not isinstance(grid, torch.Tensor) else grid)
+        if g.ndim != 1:
+            raise ValueError("grid must be one-dimensional (shared by the ensemble).")
+        T = g.shape[0]
+        pr, keep = _problem(prior, solver.constraint.ode)
+        so, bufs = _alloc_solution(prior, T, want_cholesky)
+        ws, nbytes = _workspace(cfg, B, T, prior.tcoeffs.device)
+        rc = _lib.load().pdeq_solve_fixed_grid(
+            C.byref(cfg), C.byref(pr), _pdq._ptr(g), T, float(damp), C.byref(so), _pdq._ptr(ws), nbytes,
+            _pdq._stream(),
+        )  # fmt: skip
+        _lib.check(rc, "pdeq_solve_fixed_grid")
+        del keep
+        return _wrap(prior, bufs, terminal=False)
+
+    return solve
+
+
+def dt0(vf, initial_values, /, *, t=0.0, scale=0.01, nugget=1e-5):
+    """Initial step size per ensemble member (reference: _ivpsolve/stepsize_initialisers.py:7-21)."""
+    inits = [_pdq._as_device_f64(u) for u in initial_values]
+    if len(inits) != vf.order:
+        raise ValueError(f"{vf.name} is an order-{vf.order} ODE; got {len(inits)} initial values.")
+    unbatched = inits[0].ndim == 1
+    inits = [u.reshape(1, -1) if u.ndim == 1 else u for u in inits]
+    u0 = torch.stack(inits, dim=1).contiguous()
+    B, _q, d = u0.shape
+    cfg = _pdq._make_config(fact="isotropic", nu=vf.order, d=d, vf=vf)
+    params, stride = vf.params_on_device(B)
+    out = torch.empty((B,), dtype=torch.float64, device=u0.device)
+    rc = _lib.load().pdeq_dt0(
+        C.byref(cfg), B, _pdq._ptr(u0), _pdq._ptr(params), stride, float(t), float(scale), float(nugget),
+        _pdq._ptr(out), _pdq._stream(),
+    )  # fmt: skip
+    _lib.check(rc, "pdeq_dt0")
+    return out[0] if unbatched else out

@@ -1,0 +1,551 @@
+"""Solver-construction API, mirroring ``probdiffeq.probdiffeq`` of the reference for the hot path.
+
+The reference composes Python objects (prior x strategy x constraint x solver x error) and traces
+them with JAX.  Here the same constructors return light-weight descriptors; ``ivpsolve.solve_*``
+lowers the object graph to the POD ``pdeq_config`` and calls the CUDA kernels through the C ABI.
+
+Differences a reference user will notice:
+
+* vector fields are *registered device functors* -- ``ode("lotka_volterra", params=...)`` instead of a
+  decorated Python function (reference: probdiffeq/_probdiffeq/problems.py:283-312);
+* every array carries a leading ensemble axis ``B`` (the reference's ``jax.vmap`` axis); unbatched
+  inputs are treated as ``B = 1`` and squeezed on return;
+* arrays are ``torch`` CUDA tensors (float64).
+
+Reference files mirrored: probdiffeq/probdiffeq.py:6-17 (namespace),
+_probdiffeq/ssm_impl_{isotropic,blockdiag,dense}.py (`state_space_model_*`, priors, constraints),
+_probdiffeq/solvers.py:318,483,636,770,794,850,999, _probdiffeq/estimators_and_losses.py:20,347,473,
+_probdiffeq/jet_expansion_algorithms.py:49,110.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Any
+
+import numpy as np
+import torch
+
+from probdiffeq_b200 import _iwp, _lib
+
+__all__ = [
+    "ProbabilisticSolution",
+    "error_norm_rms_then_scale",
+    "error_norm_scale_then_rms",
+    "error_residual_std",
+    "error_state_std",
+    "jetexpand_ode_padded_scan",
+    "jetexpand_ode_unroll",
+    "loss_lml_terminal_values",
+    "ode",
+    "registered_vector_fields",
+    "solver",
+    "solver_dynamic",
+    "solver_mle",
+    "state_space_model_blockdiag",
+    "state_space_model_dense",
+    "state_space_model_isotropic",
+    "strategy_filter",
+    "strategy_smoother_fixedpoint",
+]
+
+
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.NativeLibraryError("probdiffeq_b200 needs a CUDA device (B200, sm_100a); there is no CPU path.")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _as_device_f64(x, *, allow_none=False):
+    """Host (numpy / pinned torch) or device array -> contiguous float64 CUDA tensor."""
+    if x is None:
+        if allow_none:
+            return None
+        raise ValueError("array expected")
+    if not isinstance(x, torch.Tensor):
+        x = torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64)))
+    if x.dtype != torch.float64:
+        x = x.to(torch.float64)
+    if not x.is_cuda:
+        x = x.to(_device(), non_blocking=True)
+    return x.contiguous()
+
+
+def _ptr(x) -> int | None:
+    return None if x is None else x.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ------------------------------------------------------------------------------------------------------
+# Vector fields
+# ------------------------------------------------------------------------------------------------------
+
+registered_vector_fields = ("lotka_volterra", "pleiades", "hires", "vanderpol", "linear", "burgers")
+
+
+class VectorField:
+    """A registered right-hand side u^(order) = f(u, ..., u^(order-1), t) (reference: `JetOde`)."""
+
+    def __init__(self, name: str, params=None):
+        lib = _lib.load()
+        vf_id = lib.pdeq_vf_id(name.encode())
+        if vf_id < 0:
+            raise ValueError(f"Unknown vector field {name!r}. Registered: {registered_vector_fields}.")
+        self.name = name
+        self.vf_id = vf_id
+        self.num_tcoeffs_in_args = lib.pdeq_vf_ode_order(vf_id)
+        self.order = self.num_tcoeffs_in_args
+        self.num_params = lib.pdeq_vf_num_params(vf_id)
+        self.fixed_dim = lib.pdeq_vf_dim(vf_id)
+        self.tcoeff_indices_output = [self.order]
+        self.is_jet_lifted = False
+        if self.num_params == 0:
+            if params is not None and np.size(params) != 0:
+                raise ValueError(f"{name} takes no parameters.")
+            self.params = None
+        else:
+            if params is None:
+                raise ValueError(f"{name} needs {self.num_params} parameter(s).")
+            p = params if isinstance(params, torch.Tensor) else np.asarray(params, dtype=np.float64)
+            if p.shape[-1] != self.num_params or p.ndim > 2:
+                raise ValueError(f"params must have shape ({self.num_params},) or (B, {self.num_params}).")
+            self.params = p
+
+    def __repr__(self):
+        return f"VectorField({self.name!r}, num_tcoeffs_in_args={self.order})"
+
+    def params_on_device(self, B: int):
+        """-> (tensor or None, stride in doubles)."""
+        if self.params is None:
+            return None, 0
+        p = _as_device_f64(self.params)
+        if p.ndim == 1:
+            return p, 0
+        if p.shape[0] != B:
+            raise ValueError(f"params has {p.shape[0]} rows for an ensemble of {B}.")
+        return p, self.num_params
+
+
+def ode(name: str, /, *, params=None) -> VectorField:
+    """Select a registered vector field (reference: `probdiffeq.ode` / `ode_order_two`)."""
+    return VectorField(name, params)
+
+
+def _make_config(*, fact: str, nu: int, d: int, vf: VectorField, **kw) -> _lib.Config:
+    cfg = _lib.Config()
+    cfg.factorisation = _lib.FACT[fact]
+    cfg.num_derivatives = nu
+    cfg.ode_dim = d
+    cfg.vf_id = vf.vf_id
+    cfg.safety, cfg.factor_min, cfg.factor_max = 0.95, 0.2, 10.0
+    cfg.exponent_integral, cfg.exponent_proportional = 0.3, 0.4
+    cfg.correct_asymptotic_underconfidence = 1
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    a, q, facts = _iwp.system_matrices(nu)
+    n = nu + 1
+    for i in range(n):
+        for j in range(n):
+            cfg.sys_a[i][j] = a[i, j]
+            cfg.sys_q[i][j] = q[i, j]
+    for k in range(n + 1):
+        cfg.factorials[k] = facts[k]
+    return cfg
+
+
+def jetexpand_ode_padded_scan(*, num: int):
+    """Taylor-mode initialisation on the device (reference: jet_expansion_algorithms.py:49-103).
+
+    ``expand(vf, inits, t=t0)`` with ``inits`` a tuple of ``order`` arrays of shape (B, d) or (d,)
+    returns ``(tcoeffs, {})`` with ``tcoeffs`` of shape (B, order + num, d).
+    """
+
+    def expand(vf: VectorField, inits, /, *, t: float = 0.0):
+        if not isinstance(vf, VectorField):
+            raise TypeError(vf)
+        inits = [_as_device_f64(u) for u in inits]
+        if len(inits) != vf.order:
+            raise ValueError(f"{vf.name} is an order-{vf.order} ODE; got {len(inits)} initial values.")
+        unbatched = inits[0].ndim == 1
+        inits = [u.reshape(1, -1) if u.ndim == 1 else u for u in inits]
+        u0 = torch.stack(inits, dim=1).contiguous()  # (B, order, d)
+        B, q, d = u0.shape
+        if num == 0:
+            out = u0
+        else:
+            n = q + num
+            cfg = _make_config(fact="isotropic", nu=n - 1, d=d, vf=vf)
+            out = torch.empty((B, n, d), dtype=torch.float64, device=u0.device)
+            params, stride = vf.params_on_device(B)
+            rc = _lib.load().pdeq_taylor_init(
+                C.byref(cfg), B, _ptr(u0), _ptr(params), stride, float(t), _ptr(out), _stream()
+            )
+            _lib.check(rc, "pdeq_taylor_init")
+        return (out[0] if unbatched else out), {}
+
+    return expand
+
+
+jetexpand_ode_unroll = jetexpand_ode_padded_scan  # same output (jet_expansion_algorithms.py:110-152)
+
+
+# ------------------------------------------------------------------------------------------------------
+# State-space models, priors, constraints
+# ------------------------------------------------------------------------------------------------------
+
+
+@dataclasses.dataclass
+class WienerIntegratedPrior:
+    """Integrated Wiener process prior over an ensemble (reference: `*WienerIntegrated`)."""
+
+    factorisation: str
+    tcoeffs: torch.Tensor  # (B, n, d)
+    init_std: torch.Tensor | None  # isotropic (B|1, n); else (B|1, n, d); None = exact
+    output_scale: torch.Tensor | None  # isotropic (B|1, 1); else (B|1, d); None = ones
+    unbatched: bool
+
+    @property
+    def num_derivatives(self) -> int:
+        return self.tcoeffs.shape[1] - 1
+
+    @property
+    def ode_dim(self) -> int:
+        return self.tcoeffs.shape[2]
+
+
+class _Constraint:
+    def __init__(self, kind: str, vf: VectorField, factorisation: str):
+        if not isinstance(vf, VectorField):
+            raise TypeError(vf)
+        self.kind = kind
+        self.ode = vf
+        self.factorisation = factorisation
+        self.residual_order = vf.order + 1
+
+    def __repr__(self):
+        return f"Constraint({self.kind}, {self.ode!r}, {self.factorisation})"
+
+
+class _StateSpaceModel:
+    def __init__(self, factorisation: str):
+        self.factorisation = factorisation
+
+    def __repr__(self):
+        return f"state_space_model_{self.factorisation}()"
+
+    def prior_wiener_integrated(
+        self, tcoeffs, /, *, is_exact=True, inexact_eps: float = 1e-6, output_scale=None
+    ) -> WienerIntegratedPrior:
+        """reference: ssm_impl_isotropic.py:409-482, ssm_impl_blockdiag.py:463-547, ssm_impl_dense.py:458-514."""
+        tc = _as_device_f64(tcoeffs)
+        unbatched = tc.ndim == 2
+        if unbatched:
+            tc = tc[None]
+        if tc.ndim != 3:
+            raise ValueError("tcoeffs must have shape (B, n, d) or (n, d).")
+        B, n, d = tc.shape
+        std_shape = (n,) if self.factorisation == "isotropic" else (n, d)
+        if isinstance(is_exact, bool):
+            std = None if is_exact else torch.full((1, *std_shape), inexact_eps, dtype=torch.float64, device=tc.device)
+        else:
+            mask = np.broadcast_to(np.asarray(is_exact, dtype=bool), std_shape)
+            std = _as_device_f64(np.where(mask, 0.0, inexact_eps)[None])
+        return self._prior(tc, std, output_scale, unbatched)
+
+    def prior_wiener_integrated_diffuse(self, tcoeffs, tcoeffs_std, /, *, output_scale=None):
+        tc = _as_device_f64(tcoeffs)
+        unbatched = tc.ndim == 2
+        if unbatched:
+            tc = tc[None]
+        B, n, d = tc.shape
+        std_shape = (n,) if self.factorisation == "isotropic" else (n, d)
+        std = _as_device_f64(tcoeffs_std)
+        if tuple(std.shape) == std_shape:
+            std = std[None]
+        if tuple(std.shape[1:]) != std_shape or std.shape[0] not in (1, B):
+            raise ValueError(f"tcoeffs_std must have shape {std_shape} or (B, {std_shape}).")
+        return self._prior(tc, std, output_scale, unbatched)
+
+    def _prior(self, tc, std, output_scale, unbatched):
+        B, n, d = tc.shape
+        k = 1 if self.factorisation == "isotropic" else d
+        if output_scale is not None:
+            os_ = _as_device_f64(output_scale)
+            if self.factorisation == "isotropic":
+                if os_.ndim not in (0, 1):
+                    raise ValueError("The base-scale has the wrong shape. Expected: ().")
+                os_ = os_.reshape(-1, 1)
+            else:
+                if os_.shape[-1] != d or os_.ndim > 2:
+                    raise ValueError(f"The output-scale has the wrong shape. Expected: ({d},).")
+                os_ = os_.reshape(-1, d)
+            if os_.shape[0] not in (1, B):
+                raise ValueError("output_scale batch axis does not match the ensemble.")
+            output_scale = os_.contiguous()
+        del k
+        return WienerIntegratedPrior(self.factorisation, tc, std, output_scale, unbatched)
+
+    def constraint_ode_ts0(self, vf: VectorField, /) -> _Constraint:
+        return _Constraint("ts0", vf, self.factorisation)
+
+    def constraint_ode_ts1(self, vf: VectorField, /) -> _Constraint:
+        return _Constraint("ts1", vf, self.factorisation)
+
+
+def state_space_model_isotropic() -> _StateSpaceModel:
+    return _StateSpaceModel("isotropic")
+
+
+def state_space_model_blockdiag() -> _StateSpaceModel:
+    return _StateSpaceModel("blockdiag")
+
+
+def state_space_model_dense() -> _StateSpaceModel:
+    return _StateSpaceModel("dense")
+
+
+# ------------------------------------------------------------------------------------------------------
+# Strategies, solvers, error estimators (descriptors)
+# ------------------------------------------------------------------------------------------------------
+
+
+class strategy_filter:
+    """reference: estimators_and_losses.py:347-421."""
+
+    kind = "filter"
+    is_suitable_for_save_at = True
+    is_suitable_for_save_every_step = True
+
+    def __repr__(self):
+        return "strategy_filter()"
+
+
+class strategy_smoother_fixedpoint:
+    """reference: estimators_and_losses.py:473-591."""
+
+    kind = "fixedpoint"
+    is_suitable_for_save_at = True
+    is_suitable_for_save_every_step = False
+
+    def __repr__(self):
+        return "strategy_smoother_fixedpoint()"
+
+
+class _Solver:
+    kind = ""
+
+    def __init__(self, *, strategy, constraint, constraint_init=None, **options):
+        if constraint_init is not None:
+            raise NotImplementedError("constraint_init is outside the accelerated path.")
+        if not isinstance(constraint, _Constraint):
+            raise TypeError(constraint)
+        self.strategy = strategy
+        self.constraint = constraint
+        self.options = options
+
+    @property
+    def is_suitable_for_save_at(self):
+        return self.strategy.is_suitable_for_save_at
+
+    @property
+    def is_suitable_for_save_every_step(self):
+        return self.strategy.is_suitable_for_save_every_step
+
+    def __repr__(self):
+        return f"{self.kind}(strategy={self.strategy!r}, constraint={self.constraint!r})"
+
+
+class solver(_Solver):
+    """Uncalibrated solver (reference: solvers.py:636-767)."""
+
+    kind = "solver"
+
+    def __init__(self, *, strategy, constraint, constraint_init=None):
+        super().__init__(strategy=strategy, constraint=constraint, constraint_init=constraint_init)
+
+
+class solver_mle(_Solver):
+    """Running maximum-likelihood calibration (reference: solvers.py:318-480)."""
+
+    kind = "solver_mle"
+
+    def __init__(self, *, strategy, constraint, constraint_init=None, correct_asymptotic_underconfidence=True):
+        super().__init__(
+            strategy=strategy,
+            constraint=constraint,
+            constraint_init=constraint_init,
+            correct_asymptotic_underconfidence=int(bool(correct_asymptotic_underconfidence)),
+        )
+
+
+class solver_dynamic(_Solver):
+    """Per-step calibration (reference: solvers.py:483-633)."""
+
+    kind = "solver_dynamic"
+
+    def __init__(self, *, strategy, constraint, constraint_init=None, re_linearize_after_calibration=False):
+        if re_linearize_after_calibration:
+            raise NotImplementedError("re_linearize_after_calibration=True is outside the accelerated path.")
+        super().__init__(strategy=strategy, constraint=constraint, constraint_init=constraint_init)
+
+
+def error_norm_scale_then_rms(*, norm_order=None):
+    if norm_order is not None:
+        raise NotImplementedError("only the 2-norm is accelerated")
+    return "scale_then_rms"
+
+
+def error_norm_rms_then_scale(norm_order=None):
+    if norm_order is not None:
+        raise NotImplementedError("only the 2-norm is accelerated")
+    return "rms_then_scale"
+
+
+class _ErrorEstimator:
+    kind = ""
+
+    def __init__(self, *, constraint, error_norm=None, re_linearize_before_error=False, derivative_idx=0,
+                 error_per_unit_step=False):  # fmt: skip
+        if re_linearize_before_error:
+            raise NotImplementedError("re_linearize_before_error=True is outside the accelerated path.")
+        self.constraint = constraint
+        self.error_norm = "scale_then_rms" if error_norm is None else error_norm
+        if self.error_norm not in _lib.NORM:
+            raise ValueError(f"unknown error norm {error_norm!r}")
+        self.derivative_idx = int(derivative_idx)
+        self.error_per_unit_step = bool(error_per_unit_step)
+
+
+class error_residual_std(_ErrorEstimator):
+    """reference: solvers.py:850-996."""
+
+    kind = "residual_std"
+
+    def __init__(self, *, constraint, error_norm=None, re_linearize_before_error=False, error_per_unit_step=False):
+        super().__init__(constraint=constraint, error_norm=error_norm,
+                         re_linearize_before_error=re_linearize_before_error,
+                         error_per_unit_step=error_per_unit_step)  # fmt: skip
+
+
+class error_state_std(_ErrorEstimator):
+    """reference: solvers.py:999-1098."""
+
+    kind = "state_std"
+
+
+# ------------------------------------------------------------------------------------------------------
+# Solutions
+# ------------------------------------------------------------------------------------------------------
+
+
+class _CoefficientList:
+    """`rv.mean` / `rv.std` of the reference: a list over Taylor coefficients."""
+
+    def __init__(self, flat: torch.Tensor, axis: int):
+        self.flat = flat
+        self.axis = axis
+
+    def __len__(self):
+        return self.flat.shape[self.axis]
+
+    def __getitem__(self, k):
+        return self.flat.select(self.axis, k)
+
+    def __iter__(self):
+        return (self[k] for k in range(len(self)))
+
+
+@dataclasses.dataclass
+class Normal:
+    """Marginal normal distributions (reference: `IsotropicNormal` / `BlockDiagNormal` / `DenseNormal`)."""
+
+    factorisation: str
+    mean_flat: torch.Tensor  # (..., n, d)
+    cholesky_flat: torch.Tensor | None  # isotropic (..., n, n); blockdiag (..., d, n, n)
+
+    @property
+    def mean(self):
+        return _CoefficientList(self.mean_flat, self.mean_flat.ndim - 2)
+
+    @property
+    def std_flat(self):
+        """isotropic (..., n); blockdiag (..., n, d)."""
+        if self.cholesky_flat is None:
+            raise ValueError("Cholesky factors were not requested.")
+        s = torch.linalg.vector_norm(self.cholesky_flat, dim=-1)
+        return s if self.factorisation == "isotropic" else s.transpose(-1, -2)
+
+    @property
+    def std(self):
+        s = self.std_flat
+        return _CoefficientList(s, s.ndim - 1 if self.factorisation == "isotropic" else s.ndim - 2)
+
+    def covariance(self):
+        L = self.cholesky_flat
+        return L @ L.transpose(-1, -2)
+
+
+@dataclasses.dataclass
+class ProbabilisticSolution:
+    """reference: `ProbabilisticSolution` (solvers.py:33-69), with a leading ensemble axis."""
+
+    t: torch.Tensor
+    u: Normal
+    output_scale: torch.Tensor
+    num_steps: torch.Tensor
+    num_attempts: torch.Tensor
+    status: torch.Tensor
+    solution_full: Any = None
+
+    def _index(self, fn):
+        return ProbabilisticSolution(
+            t=fn(self.t),
+            u=Normal(self.u.factorisation, fn(self.u.mean_flat),
+                     None if self.u.cholesky_flat is None else fn(self.u.cholesky_flat)),
+            output_scale=fn(self.output_scale),
+            num_steps=fn(self.num_steps),
+            num_attempts=self.num_attempts,
+            status=self.status,
+            solution_full=self.solution_full,
+        )  # fmt: skip
+
+
+# ------------------------------------------------------------------------------------------------------
+# Log-marginal likelihood of terminal values
+# ------------------------------------------------------------------------------------------------------
+
+
+def loss_lml_terminal_values(*, tcoeff_index: int = 0):
+    """reference: estimators_and_losses.py:20-50. Returns one log-pdf per ensemble member, shape (B,)."""
+
+    def loss(u, /, *, marginals: Normal, std, vf: VectorField | None = None):
+        mean = marginals.mean_flat
+        chol = marginals.cholesky_flat
+        if chol is None:
+            raise ValueError("marginals carry no Cholesky factors")
+        unbatched = mean.ndim == 2
+        if unbatched:
+            mean, chol = mean[None], chol[None]
+        B, n, d = mean.shape
+        data = _as_device_f64(u).reshape(-1, d)
+        k = 1 if marginals.factorisation == "isotropic" else d
+        sd = _as_device_f64(std).reshape(-1, k)
+        for name, arr in (("data", data), ("std", sd)):
+            if arr.shape[0] not in (1, B):
+                raise ValueError(f"{name} batch axis does not match the ensemble.")
+        vf_ = vf if vf is not None else VectorField("linear", params=[1.0])
+        cfg = _make_config(fact=marginals.factorisation, nu=n - 1, d=d, vf=vf_)
+        out = torch.empty((B,), dtype=torch.float64, device=mean.device)
+        rc = _lib.load().pdeq_lml_terminal_values(
+            C.byref(cfg), B, int(tcoeff_index), _ptr(mean.contiguous()), _ptr(chol.contiguous()),
+            _ptr(data), 0 if data.shape[0] == 1 else d, _ptr(sd), 0 if sd.shape[0] == 1 else k,
+            _ptr(out), _stream(),
+        )  # fmt: skip
+        _lib.check(rc, "pdeq_lml_terminal_values")
+        return out[0] if unbatched else out
+
+    return loss

