@@ -79,6 +79,7 @@ typedef struct pdeq_config {
   double sys_a[PDEQ_MAX_COEFFS][PDEQ_MAX_COEFFS];
   double sys_q[PDEQ_MAX_COEFFS][PDEQ_MAX_COEFFS];
   double factorials[PDEQ_MAX_COEFFS + 1]; /* factorials[k] = k! as the reference evaluates it */
+  double inv_factorials[PDEQ_MAX_COEFFS + 1]; /* 1 / factorials[k], so the kernels multiply instead of divide */
 } pdeq_config;
 
 /* Inputs shared by the loop entry points. A `*_stride` of 0 broadcasts one row to all instances. */
@@ -107,6 +108,11 @@ typedef struct pdeq_solution {
   double* bw_gain;       /* blockdiag [B][T][d][n][n] (entry 0 unused) */
   double* bw_mean;       /* [B][T][n][d] */
   double* bw_chol;       /* like chol */
+  /* optional attempt log (NULL = off): for attempt a < trace_capacity of instance b,
+     trace[(b * trace_capacity + a) * 4 + {0,1,2,3}] = {t_from, dt_used, error_power, accepted ? 1 : 0}.
+     Lets a caller check the accepted-step sequence against the reference attempt by attempt. */
+  double* trace;
+  int64_t trace_capacity;
 } pdeq_solution;
 
 int pdeq_version(void);

@@ -46,6 +46,7 @@ class Config(C.Structure):
         ("sys_a", (C.c_double * MAX_COEFFS) * MAX_COEFFS),
         ("sys_q", (C.c_double * MAX_COEFFS) * MAX_COEFFS),
         ("factorials", C.c_double * (MAX_COEFFS + 1)),
+        ("inv_factorials", C.c_double * (MAX_COEFFS + 1)),
     ]
 
 
@@ -74,6 +75,8 @@ class Solution(C.Structure):
         ("bw_gain", C.c_void_p),
         ("bw_mean", C.c_void_p),
         ("bw_chol", C.c_void_p),
+        ("trace", C.c_void_p),
+        ("trace_capacity", C.c_int64),
     ]
 
 

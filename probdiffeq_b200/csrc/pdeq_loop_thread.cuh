@@ -13,6 +13,11 @@
 // Why one flat loop: under `jax.vmap` the reference's nested while-loops run until the slowest lane is
 // done.  Here a lane that finishes its instance immediately pulls the next instance index from a global
 // counter, so all 32 lanes of a warp keep executing the same attempt body on different instances.
+//
+// Scalar arithmetic: divisions and square roots use branch-free MUFU + Newton sequences (pdeq_blockops.cuh),
+// and the controller works on log2(error_power) -- error_power = norm^(-1/n) is never formed: accept iff
+// log2(norm) <= 0, and the PI gain e^0.3 (e/e_prev)^0.4 is one exp2 of a linear combination of logs. These
+// differ from the reference's pow() chain by rounding only (1e-16 relative in dt).
 #pragma once
 
 #include "pdeq_blockops.cuh"
@@ -44,6 +49,8 @@ PDEQ_DI double ipow_small(double x, int k) {
   }
   return r;
 }
+
+PDEQ_DI double safe_sqrt(double x) { return x > 0.0 ? fast_sqrt(x) : 0.0; }
 
 template <class VF, int NU, int FACT, int D, bool TS0>
 struct ThreadLoop {
@@ -100,11 +107,67 @@ struct ThreadLoop {
     }
   }
 
+  // interp_from lives in shared memory (one column per thread): it is written on every accepted step but read
+  // only when a checkpoint is overstepped, so it should not occupy registers.
+  PDEQ_DI static void if_store(double* __restrict__ sm, int nthreads, int tid, const double (&m)[n][D],
+                               const double (&L)[NB][n][n], double t) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) sm[(i * D + j) * nthreads + tid] = m[i][j];
+    }
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+#pragma unroll
+        for (int j = 0; j <= i; ++j) sm[(n * D + (k * n + i) * n + j) * nthreads + tid] = L[k][i][j];
+      }
+    }
+    sm[(IF_SLOTS - 1) * nthreads + tid] = t;
+  }
+  PDEQ_DI static void if_load(const double* __restrict__ sm, int nthreads, int tid, double (&m)[n][D],
+                              double (&L)[NB][n][n], double& t) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) m[i][j] = sm[(i * D + j) * nthreads + tid];
+    }
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+#pragma unroll
+        for (int j = 0; j <= i; ++j) L[k][i][j] = sm[(n * D + (k * n + i) * n + j) * nthreads + tid];
+      }
+    }
+    t = sm[(IF_SLOTS - 1) * nthreads + tid];
+  }
+
+  // Whitened RMS of the observation residual per block (IsotropicNormal.residual_whitened_rms_flat,
+  // ssm_impl_isotropic.py:203-207; BlockDiagNormal..., ssm_impl_blockdiag.py:285-292) for 1x1 factors r[k].
+  PDEQ_DI static void whitened_rms(const double (&mobs)[D], const double (&r)[NB], double (&out)[NB]) {
+    if (FACT == PDEQ_FACT_BLOCKDIAG) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) out[blk(j)] = fabs(mobs[j] * fast_rcp(r[blk(j)]));
+    } else {
+      const double inv = fast_rcp(r[0]);
+      double ss = 0.0;
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        const double w = mobs[j] * inv;
+        ss = fma(w, w, ss);
+      }
+      out[0] = safe_sqrt(ss) * rsqrt((double)D);
+    }
+  }
+
   PDEQ_DI static void run(const LoopArgs& a, double* __restrict__ smem_if) {
     const pdeq_config& cfg = a.cfg;
     const double(*__restrict__ A)[PDEQ_MAX_COEFFS] = cfg.sys_a;
     const double(*__restrict__ Q)[PDEQ_MAX_COEFFS] = cfg.sys_q;
     const double* __restrict__ fact = cfg.factorials;
+    const double* __restrict__ ifact = cfg.inv_factorials;
     const bool adaptive = a.fixed_grid == 0;
     const bool clip = cfg.clip_dt != 0;
     const bool needs_interp = adaptive && !clip;
@@ -113,11 +176,12 @@ struct ThreadLoop {
     const int max_attempts = cfg.max_attempts > 0 ? cfg.max_attempts : 0x7fffffff;
     const int tid = threadIdx.x;
     const int nthreads = blockDim.x;
-#define PDEQ_IF(slot) smem_if[(slot) * nthreads + tid]
+    const double inv_sqrt_d = rsqrt((double)D);
+    const double neg_inv_n = -1.0 / (double)n;
 
     // ---- per-instance state (registers) ----
     double m[n][D], L[NB][n][n], prior[NB], sig[NB], run_scale[NB], params[P];
-    double t = 0.0, dt = 0.0, ctrl_prev = 1.0, ndata = 0.0, t_next = 0.0;
+    double t = 0.0, dt = 0.0, ctrl_lprev = 0.0, ndata = 0.0, t_next = 0.0;
     int nsteps = 0, nattempts = 0, ck = 0, status = 0;
     long b = -1;
     bool need_load = true;
@@ -161,7 +225,7 @@ struct ThreadLoop {
           params[k] = (VF::num_params > 0) ? a.prob.params[b * a.prob.params_stride + k] : 0.0;
         t = a.grid[0];
         dt = adaptive ? a.dt0[b * a.dt0_stride] : 0.0;
-        ctrl_prev = 1.0;
+        ctrl_lprev = 0.0;  // log2 of the PI controller's initial state 1.0 (controllers.py:42-44)
         ndata = 0.0;
         nsteps = 0;
         nattempts = 0;
@@ -169,22 +233,7 @@ struct ThreadLoop {
         emit(a, b, 0, t, m, L, sig, 0);
         ck = 1;
         t_next = (T > 1) ? a.grid[1] : t;
-        if (needs_interp) {
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-#pragma unroll
-            for (int j = 0; j < D; ++j) PDEQ_IF(i * D + j) = m[i][j];
-          }
-#pragma unroll
-          for (int k = 0; k < NB; ++k) {
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-#pragma unroll
-              for (int j = 0; j <= i; ++j) PDEQ_IF(n * D + (k * n + i) * n + j) = L[k][i][j];
-            }
-          }
-          PDEQ_IF(IF_SLOTS - 1) = t;
-        }
+        if (needs_interp) if_store(smem_if, nthreads, tid, m, L, t);
       }
 
       // ------------------------------------------------------------------ checkpoint reached?
@@ -194,24 +243,11 @@ struct ThreadLoop {
         if (ck < T) {
           if (needs_interp && t > t_next + a.eps) {
             // interp_beyond_t1 -> strategy_filter.interpolate_fwd: predict from interp_from to t_next
-            double mi[n][D], Li[NB][n][n], mo[n][D], Lo[NB][n][n], p[n], pinv[n];
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-#pragma unroll
-              for (int j = 0; j < D; ++j) mi[i][j] = PDEQ_IF(i * D + j);
-            }
-#pragma unroll
-            for (int k = 0; k < NB; ++k) {
-#pragma unroll
-              for (int i = 0; i < n; ++i) {
-#pragma unroll
-                for (int j = 0; j <= i; ++j) Li[k][i][j] = PDEQ_IF(n * D + (k * n + i) * n + j);
-              }
-            }
-            const double t_if = PDEQ_IF(IF_SLOTS - 1);
+            double mi[n][D], Li[NB][n][n], mo[n][D], Lo[NB][n][n], p[n], pinv[n], t_if;
+            if_load(smem_if, nthreads, tid, mi, Li, t_if);
             const double dti = t_next - t_if;
-            preconditioner<n>(dti, fact, p, pinv);
-            const double sq = sqrt(fabs(dti));
+            preconditioner<n>(dti, ifact, fact, p, pinv);
+            const double sq = safe_sqrt(fabs(dti));
 #pragma unroll
             for (int j = 0; j < D; ++j) {
               double col[n], out[n];
@@ -224,39 +260,11 @@ struct ThreadLoop {
 #pragma unroll
             for (int k = 0; k < NB; ++k) predict_chol<n>(Li[k], p, pinv, sq * prior[k] * sig[k], A, Q, Lo[k]);
             emit(a, b, ck, t_next, mo, Lo, sig, nsteps);
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-#pragma unroll
-              for (int j = 0; j < D; ++j) PDEQ_IF(i * D + j) = mo[i][j];
-            }
-#pragma unroll
-            for (int k = 0; k < NB; ++k) {
-#pragma unroll
-              for (int i = 0; i < n; ++i) {
-#pragma unroll
-                for (int j = 0; j <= i; ++j) PDEQ_IF(n * D + (k * n + i) * n + j) = Lo[k][i][j];
-              }
-            }
-            PDEQ_IF(IF_SLOTS - 1) = t_next;
+            if_store(smem_if, nthreads, tid, mo, Lo, t_next);
           } else {
             // interp_at_t1: the state itself is the solution; interpolation restarts from it
             emit(a, b, ck, t, m, L, sig, nsteps);
-            if (needs_interp) {
-#pragma unroll
-              for (int i = 0; i < n; ++i) {
-#pragma unroll
-                for (int j = 0; j < D; ++j) PDEQ_IF(i * D + j) = m[i][j];
-              }
-#pragma unroll
-              for (int k = 0; k < NB; ++k) {
-#pragma unroll
-                for (int i = 0; i < n; ++i) {
-#pragma unroll
-                  for (int j = 0; j <= i; ++j) PDEQ_IF(n * D + (k * n + i) * n + j) = L[k][i][j];
-                }
-              }
-              PDEQ_IF(IF_SLOTS - 1) = t;
-            }
+            if (needs_interp) if_store(smem_if, nthreads, tid, m, L, t);
           }
           ck += 1;
           if (ck < T) t_next = a.grid[ck];
@@ -309,8 +317,8 @@ struct ThreadLoop {
         dtc = a.grid[ck] - a.grid[ck - 1];  // np.diff(grid), solvers_via_fixed_steps.py:28
       }
       double p[n], pinv[n];
-      preconditioner<n>(dtc, fact, p, pinv);
-      const double sq = sqrt(fabs(dtc));
+      preconditioner<n>(dtc, ifact, fact, p, pinv);
+      const double sq = safe_sqrt(fabs(dtc));
 
       // mean extrapolation (identical for transition.apply_flat and transition.marginalise)
       double mp[n][D];
@@ -386,20 +394,7 @@ struct ThreadLoop {
       double sig_new[NB];
 #pragma unroll
       for (int k = 0; k < NB; ++k) sig_new[k] = 1.0;
-      if (cfg.solver == PDEQ_SOLVER_DYNAMIC) {
-        if (FACT == PDEQ_FACT_BLOCKDIAG) {
-#pragma unroll
-          for (int j = 0; j < D; ++j) sig_new[blk(j)] = fabs(mobs[j] / robs[blk(j)]);
-        } else {
-          double ss = 0.0;
-#pragma unroll
-          for (int j = 0; j < D; ++j) {
-            const double w = mobs[j] / robs[0];
-            ss = fma(w, w, ss);
-          }
-          sig_new[0] = sqrt(ss) / sqrt((double)D);
-        }
-      }
+      if (cfg.solver == PDEQ_SOLVER_DYNAMIC) whitened_rms(mobs, robs, sig_new);
 
       // extrapolate the Cholesky factor and correct (strategy_filter.predict + bayes_rule)
       double Ln[NB][n][n], gain[NB][n], ry[NB];
@@ -413,7 +408,7 @@ struct ThreadLoop {
 #pragma unroll
       for (int j = 0; j < D; ++j) {
 #pragma unroll
-        for (int i = 0; i < n; ++i) mn[i][j] = mp[i][j] - gain[blk(j)][i] * mobs[j];
+        for (int i = 0; i < n; ++i) mn[i][j] = fma(-gain[blk(j)][i], mobs[j], mp[i][j]);
       }
 
       // solver_mle: running RMS of the whitened residuals (solvers.py:412-424)
@@ -422,20 +417,12 @@ struct ThreadLoop {
       for (int k = 0; k < NB; ++k) run_new[k] = run_scale[k];
       if (cfg.solver == PDEQ_SOLVER_MLE) {
         const double w1 = sqrt(ndata / (ndata + 1.0)), w2 = sqrt(1.0 / (ndata + 1.0));
-        if (FACT == PDEQ_FACT_BLOCKDIAG) {
+        double term[NB];
+        whitened_rms(mobs, ry, term);
 #pragma unroll
-          for (int j = 0; j < D; ++j) {
-            const double term = fabs(mobs[j] / ry[blk(j)]);
-            run_new[blk(j)] = hypot(w1 * run_scale[blk(j)], w2 * term);
-          }
-        } else {
-          double ss = 0.0;
-#pragma unroll
-          for (int j = 0; j < D; ++j) {
-            const double w = mobs[j] / ry[0];
-            ss = fma(w, w, ss);
-          }
-          run_new[0] = hypot(w1 * run_scale[0], w2 * (sqrt(ss) / sqrt((double)D)));
+        for (int k = 0; k < NB; ++k) {
+          const double x1 = w1 * run_scale[k], x2 = w2 * term[k];
+          run_new[k] = safe_sqrt(fma(x1, x1, x2 * x2));  // hypot
         }
       }
 
@@ -447,53 +434,44 @@ struct ThreadLoop {
         int kpow;
         if (cfg.error == PDEQ_ERROR_RESIDUAL_STD) {
           // solvers.py:955-968,978-991
-          if (FACT == PDEQ_FACT_BLOCKDIAG) {
+          double se[NB];
+          whitened_rms(mobs, robs, se);
 #pragma unroll
-            for (int j = 0; j < D; ++j) err[j] = fabs(mobs[j] / robs[blk(j)]) * fabs(robs[blk(j)]);
-          } else {
-            double ss = 0.0;
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-              const double w = mobs[j] / robs[0];
-              ss = fma(w, w, ss);
-            }
-            const double e = (sqrt(ss) / sqrt((double)D)) * fabs(robs[0]);
-#pragma unroll
-            for (int j = 0; j < D; ++j) err[j] = e;
-          }
+          for (int j = 0; j < D; ++j) err[j] = se[blk(j)] * fabs(robs[blk(j)]);
 #pragma unroll
           for (int j = 0; j < D; ++j) ref[j] = fmax(fabs(m[0][j]), fabs(mn[0][j]));
           kpow = q;
         } else {
           // solvers.py:1070-1086: Bayes rule on the zero-error extrapolation, std of one coefficient
           const int idx = cfg.derivative_idx;
-          double se[NB], sd[NB];
+          double rye[NB], sd[NB];
+          if (idx == 0) {
+            // common case: only R_Y and the first row of the corrected factor are needed, which lets the
+            // compiler drop all but the first two reflectors of the (n+1)x(n+1) triangularisation
 #pragma unroll
-          for (int k = 0; k < NB; ++k) {
-            double Lc[n][n], g_unused[n], rye;
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-#pragma unroll
-              for (int j = 0; j <= i; ++j) Lc[i][j] = 0.0;
+            for (int k = 0; k < NB; ++k) {
+              double Lc[n][n], g_unused[n];
+              Lc[0][0] = 0.0;
+              revert_obs<n, q, TS0, 0>(Lq[k], h[k], a.damp, rye[k], g_unused, Lc);
+              sd[k] = fabs(Lc[0][0]);
             }
-            revert_obs<n, q, TS0>(Lq[k], h[k], a.damp, rye, g_unused, Lc);
-            sd[k] = row_norm<n>(Lc, idx);
-            se[k] = rye;
-          }
-          if (FACT == PDEQ_FACT_BLOCKDIAG) {
-#pragma unroll
-            for (int j = 0; j < D; ++j) err[j] = fabs(mobs[j] / se[blk(j)]) * sd[blk(j)];
           } else {
-            double ss = 0.0;
 #pragma unroll
-            for (int j = 0; j < D; ++j) {
-              const double w = mobs[j] / se[0];
-              ss = fma(w, w, ss);
+            for (int k = 0; k < NB; ++k) {
+              double Lc[n][n], g_unused[n];
+#pragma unroll
+              for (int i = 0; i < n; ++i) {
+#pragma unroll
+                for (int j = 0; j <= i; ++j) Lc[i][j] = 0.0;
+              }
+              revert_obs<n, q, TS0>(Lq[k], h[k], a.damp, rye[k], g_unused, Lc);
+              sd[k] = row_norm<n>(Lc, idx);
             }
-            const double e = (sqrt(ss) / sqrt((double)D)) * sd[0];
-#pragma unroll
-            for (int j = 0; j < D; ++j) err[j] = e;
           }
+          double se[NB];
+          whitened_rms(mobs, rye, se);
+#pragma unroll
+          for (int j = 0; j < D; ++j) err[j] = se[blk(j)] * sd[blk(j)];
 #pragma unroll
           for (int j = 0; j < D; ++j) {
             double a0 = 0.0, a1 = 0.0;
@@ -509,74 +487,64 @@ struct ThreadLoop {
           kpow = idx;
         }
         if (cfg.error_per_unit_step) kpow += 1;
-        const double dtk = ipow_small<n>(dtc, kpow);
-        double fk = 1.0;
+        double escale = ipow_small<n>(dtc, kpow);  // dt^k / k!
 #pragma unroll
         for (int e = 0; e <= n; ++e) {
-          if (e == kpow) fk = fact[e];
+          if (e == kpow) escale *= ifact[e];
         }
         double norm;
         if (cfg.error_norm == PDEQ_NORM_SCALE_THEN_RMS) {
           double ss = 0.0;
 #pragma unroll
           for (int j = 0; j < D; ++j) {
-            const double w = (err[j] * dtk / fk) / (a.atol + a.rtol * ref[j]);
+            const double w = (err[j] * escale) * fast_rcp(fma(a.rtol, ref[j], a.atol));
             ss = fma(w, w, ss);
           }
-          norm = sqrt(ss) / sqrt((double)D);
+          norm = safe_sqrt(ss) * inv_sqrt_d;
         } else {
           // rms(error_abs) / (atol + rtol * rms(reference)); the isotropic error has size 1
           double se2 = 0.0, sr2 = 0.0;
-          const int ne = (FACT == PDEQ_FACT_BLOCKDIAG) ? D : 1;
+          constexpr int ne = (FACT == PDEQ_FACT_BLOCKDIAG) ? D : 1;
 #pragma unroll
           for (int j = 0; j < D; ++j) {
-            const double ea = err[j] * dtk / fk;
+            const double ea = err[j] * escale;
             if (j < ne) se2 = fma(ea, ea, se2);
             sr2 = fma(ref[j], ref[j], sr2);
           }
-          norm = (sqrt(se2) / sqrt((double)ne)) / (a.atol + a.rtol * (sqrt(sr2) / sqrt((double)D)));
+          norm = (safe_sqrt(se2) * rsqrt((double)ne)) * fast_rcp(fma(a.rtol, safe_sqrt(sr2) * inv_sqrt_d, a.atol));
         }
-        const double ep = pow(norm, -1.0 / (double)n);  // solvers.py:995
-        accept = !(ep < 1.0);                            // solvers_via_adaptive_steps.py:256-258
+        // error_power = norm^(-1/n) (solvers.py:995); accept iff !(error_power < 1) (solvers_via_adaptive_steps.py:256-258)
+        const double lep = neg_inv_n * log2(norm);
+        accept = !(lep < 0.0);
 
-        double ratio;
+        double lratio;  // log2 of the unclipped step ratio / safety
         if (cfg.control == PDEQ_CONTROL_PI) {
-          const double gi = pow(ep, cfg.exponent_integral);
-          const double gp = pow(ep / ctrl_prev, cfg.exponent_proportional);
-          ratio = cfg.safety * gi * gp;
-          if (ep >= 1.0) ctrl_prev = ep;
+          lratio = fma(cfg.exponent_integral, lep, cfg.exponent_proportional * (lep - ctrl_lprev));
+          if (lep >= 0.0) ctrl_lprev = lep;
         } else {
-          ratio = cfg.safety * ep;
+          lratio = lep;
         }
+        const double ratio = cfg.safety * exp2(lratio);
         const double sc = fmax(cfg.factor_min, fmin(ratio, cfg.factor_max));
         dt_next = sc * dtc;
+        if (a.sol.trace != nullptr && nattempts <= a.sol.trace_capacity) {
+          double* tr = a.sol.trace + (b * a.sol.trace_capacity + (nattempts - 1)) * 4;
+          tr[0] = t;
+          tr[1] = dtc;
+          tr[2] = exp2(lep);
+          tr[3] = accept ? 1.0 : 0.0;
+        }
         if (nattempts >= max_attempts) {
           status = PDEQ_STATUS_MAX_ATTEMPTS;
           accept = true;
-          // give up on this instance: jump beyond every remaining checkpoint
-          ck = T;
+          ck = T;  // give up on this instance
         }
       }
 
       // ------------------------------------------------------------------ commit
       dt = dt_next;
       if (accept) {
-        if (needs_interp) {  // interp_from <- step_from (solvers_via_adaptive_steps.py:330-338)
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-#pragma unroll
-            for (int j = 0; j < D; ++j) PDEQ_IF(i * D + j) = m[i][j];
-          }
-#pragma unroll
-          for (int k = 0; k < NB; ++k) {
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-#pragma unroll
-              for (int j = 0; j <= i; ++j) PDEQ_IF(n * D + (k * n + i) * n + j) = L[k][i][j];
-            }
-          }
-          PDEQ_IF(IF_SLOTS - 1) = t;
-        }
+        if (needs_interp) if_store(smem_if, nthreads, tid, m, L, t);  // interp_from <- step_from (:330-338)
 #pragma unroll
         for (int i = 0; i < n; ++i) {
 #pragma unroll
@@ -601,7 +569,6 @@ struct ThreadLoop {
         }
       }
     }
-#undef PDEQ_IF
   }
 };
 

@@ -114,7 +114,7 @@ def _problem(prior, vf):
     return pr, (params,)
 
 
-def _alloc_solution(prior, T, want_chol=True):
+def _alloc_solution(prior, T, want_chol=True, trace_capacity=0):
     B, n, d = prior.tcoeffs.shape
     dev = prior.tcoeffs.device
     fact = prior.factorisation
@@ -132,9 +132,12 @@ def _alloc_solution(prior, T, want_chol=True):
         num_attempts=torch.empty((B,), dtype=torch.int32, device=dev),
         status=torch.empty((B,), dtype=torch.int32, device=dev),
     )
+    if trace_capacity > 0:
+        bufs["trace"] = torch.full((B, trace_capacity, 4), float("nan"), **f64)
     so = _lib.Solution()
     for k, v in bufs.items():
         setattr(so, k, _pdq._ptr(v))
+    so.trace_capacity = int(trace_capacity)
     return so, bufs
 
 
@@ -148,12 +151,15 @@ def _wrap(prior, bufs, *, terminal: bool):
         num_attempts=bufs["num_attempts"],
         status=bufs["status"],
     )  # fmt: skip
+    trace = bufs.get("trace")
     if terminal:
         sol = sol._index(lambda x: x[:, -1])
     if prior.unbatched:
         sol = sol._index(lambda x: x[0])
         sol.num_attempts = sol.num_attempts[0]
         sol.status = sol.status[0]
+        trace = None if trace is None else trace[0]
+    sol.trace = trace  # (B, capacity, 4): t_from, dt, error_power, accepted -- only if trace_capacity > 0
     return sol
 
 
@@ -163,7 +169,7 @@ def _workspace(cfg, B, T, device):
 
 
 def _run_adaptive(prior, solver, error, control, clip_dt, save_at, atol, rtol, dt0, eps, damp, *, terminal,
-                  want_chol=True, max_attempts=0):  # fmt: skip
+                  want_chol=True, max_attempts=0, trace_capacity=0):  # fmt: skip
     if control is None:
         control = control_integral()  # solvers_via_adaptive_steps.py:87-90
     cfg = _lower(prior, solver, error, control, clip_dt, max_attempts)
@@ -176,7 +182,7 @@ def _run_adaptive(prior, solver, error, control, clip_dt, save_at, atol, rtol, d
     if dt0_t.shape[0] not in (1, B):
         raise ValueError("dt0 must be a scalar or have one entry per ensemble member.")
     pr, keep = _problem(prior, solver.constraint.ode)
-    so, bufs = _alloc_solution(prior, T, want_chol)
+    so, bufs = _alloc_solution(prior, T, want_chol, trace_capacity)
     ws, nbytes = _workspace(cfg, B, T, prior.tcoeffs.device)
     rc = _lib.load().pdeq_solve_adaptive_save_at(
         C.byref(cfg), C.byref(pr), _pdq._ptr(grid), T, float(atol), float(rtol), _pdq._ptr(dt0_t),
@@ -191,10 +197,11 @@ def _run_adaptive(prior, solver, error, control, clip_dt, save_at, atol, rtol, d
 def solve_adaptive_terminal_values(solver, error, control=None, clip_dt: bool = True, *, max_attempts: int = 0):
     """reference: _ivpsolve/solvers_via_adaptive_steps.py:16-43."""
 
-    def solve(u, /, *, t0, t1, atol, rtol, dt0=0.1, eps=1e-8, damp=0.0, want_cholesky=True):
+    def solve(u, /, *, t0, t1, atol, rtol, dt0=0.1, eps=1e-8, damp=0.0, want_cholesky=True, trace_capacity=0):
         save_at = np.asarray([t0, t1], dtype=np.float64)
         return _run_adaptive(u, solver, error, control, clip_dt, save_at, atol, rtol, dt0, eps, damp,
-                             terminal=True, want_chol=want_cholesky, max_attempts=max_attempts)  # fmt: skip
+                             terminal=True, want_chol=want_cholesky, max_attempts=max_attempts,
+                             trace_capacity=trace_capacity)  # fmt: skip
 
     return solve
 
@@ -208,9 +215,10 @@ def solve_adaptive_save_at(*, solver, error, control=None, clip_dt: bool = False
         msg += " Try using filters or fixed-point smoothers."
         warnings.warn(msg, stacklevel=1)
 
-    def solve(u, save_at, atol, rtol, dt0=0.1, eps=1e-8, damp=0.0, want_cholesky=True):
+    def solve(u, save_at, atol, rtol, dt0=0.1, eps=1e-8, damp=0.0, want_cholesky=True, trace_capacity=0):
         return _run_adaptive(u, solver, error, control, clip_dt, save_at, atol, rtol, dt0, eps, damp,
-                             terminal=False, want_chol=want_cholesky, max_attempts=max_attempts)  # fmt: skip
+                             terminal=False, want_chol=want_cholesky, max_attempts=max_attempts,
+                             trace_capacity=trace_capacity)  # fmt: skip
 
     return solve
 

@@ -154,6 +154,7 @@ def _make_config(*, fact: str, nu: int, d: int, vf: VectorField, **kw) -> _lib.C
             cfg.sys_q[i][j] = q[i, j]
     for k in range(n + 1):
         cfg.factorials[k] = facts[k]
+        cfg.inv_factorials[k] = 1.0 / facts[k]
     return cfg
 
 
@@ -500,6 +501,7 @@ class ProbabilisticSolution:
     num_attempts: torch.Tensor
     status: torch.Tensor
     solution_full: Any = None
+    trace: Any = None
 
     def _index(self, fn):
         return ProbabilisticSolution(

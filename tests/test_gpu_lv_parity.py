@@ -55,17 +55,31 @@ COMBOS = [
 ]
 
 
-def _tolerances(s, tc, params, save_at, atol, rtol, osol):
-    """Tolerance for an adaptive comparison = max(stated tolerance, 100 x the oracle's own sensitivity).
+def _tolerances(s, tc, params, save_at, atol, rtol, osol, otrace):
+    """Tolerances for an adaptive comparison, relative to the oracle's own conditioning.
 
     The adaptive loop amplifies rounding: re-running the ORACLE with dt0 changed by one ulp moves later step
-    sizes by ~1e-10 relative and terminal values by up to ~1e-7 ("conditioning of the adaptive loop").
-    No independent implementation can agree more closely than that, so the comparison is made relative to it.
+    sizes by ~1e-10 relative (much more when clip_dt cancels t_next - t) and terminal values by up to ~1e-7
+    ("conditioning of the adaptive loop"). No independent implementation can agree more closely than
+    that, so values are compared at max(stated tolerance, 100 x that sensitivity), and the accept/reject sequence
+    is required to be identical whenever the perturbed oracle reproduces its own sequence.
     """
-    pert, _ = H.oracle_solve_save_at(s, tc, params, save_at, atol, rtol, dt0=0.1 * (1 + 2.3e-16))
+    ptrace = []
+    pert, ptrace = H.oracle_solve_save_at(s, tc, params, save_at, atol, rtol, dt0=0.1 * (1 + 2.3e-16))
     sens_mean = _rel(pert.u_mean, osol.u_mean)
     sens_cov = _rel(H.cov_from_chol(pert.u_chol), H.cov_from_chol(osol.u_chol))
-    return max(RTOL_ADAPTIVE, 100 * sens_mean), max(RTOL_ADAPTIVE_COV, 100 * sens_cov)
+    stable = len(ptrace) == len(otrace) and [r[3] for r in ptrace] == [r[3] for r in otrace]
+    return max(RTOL_ADAPTIVE, 100 * sens_mean), max(RTOL_ADAPTIVE_COV, 100 * sens_cov), stable
+
+
+def _check_sequence(sol_trace, otrace, n_attempts):
+    """Identical accept/reject sequence, attempt by attempt, and matching step times."""
+    tr = sol_trace[:n_attempts]
+    otr = np.asarray(otrace)
+    assert n_attempts == len(otr)
+    assert np.array_equal(tr[:, 3] > 0.5, otr[:, 3] > 0.5)
+    assert np.allclose(tr[:, 0], otr[:, 0], rtol=1e-6, atol=1e-9)  # t_from
+    assert np.allclose(tr[:, 1], otr[:, 1], rtol=1e-4)  # dt (drifts with the conditioning of the controller)
 
 
 @pytest.mark.parametrize("combo", COMBOS, ids=lambda c: "-".join(f"{k}={v}" for k, v in c.items()) or "headline")
@@ -79,21 +93,27 @@ def test_adaptive_terminal_values_match_oracle(cuda, combo):
     tcoeffs, _ = p_pdq.jetexpand_ode_padded_scan(num=4)(vf, (u0,), t=0.0)
     prior = ssm.prior_wiener_integrated(tcoeffs)
     solve = p_ivp.solve_adaptive_terminal_values(solver=solver, error=err, control=ctrl, clip_dt=s["clip_dt"])
-    sol = solve(prior, t0=0.0, t1=10.0, atol=1e-8, rtol=1e-6)
+    sol = solve(prior, t0=0.0, t1=10.0, atol=1e-8, rtol=1e-6, trace_capacity=512)
     torch.cuda.synchronize()
     assert int(sol.status.abs().max()) == 0
     tc = tcoeffs.cpu().numpy()
+    gtrace = sol.trace.cpu().numpy()
+    num_stable = 0
     for b in range(B):
-        osol, trace = H.oracle_solve_save_at(s, tc[b], params[b], np.asarray([0.0, 10.0]), 1e-8, 1e-6)
-        assert int(sol.num_steps[b]) == int(osol.num_steps[-1]), (b, int(sol.num_steps[b]), osol.num_steps)
-        assert int(sol.num_attempts[b]) == len(trace)
-        assert abs(float(sol.t[b]) - osol.t[-1]) <= 1e-12 * 10.0
-        tol_mean, tol_cov = _tolerances(s, tc[b], params[b], np.asarray([0.0, 10.0]), 1e-8, 1e-6, osol)
+        save_at = np.asarray([0.0, 10.0])
+        osol, trace = H.oracle_solve_save_at(s, tc[b], params[b], save_at, 1e-8, 1e-6)
+        tol_mean, tol_cov, stable = _tolerances(s, tc[b], params[b], save_at, 1e-8, 1e-6, osol, trace)
+        if stable:
+            num_stable += 1
+            assert int(sol.num_steps[b]) == int(osol.num_steps[-1]), (b, int(sol.num_steps[b]), osol.num_steps)
+            _check_sequence(gtrace[b], trace, int(sol.num_attempts[b]))
+            assert abs(float(sol.t[b]) - osol.t[-1]) <= 1e-12 * 10.0
         assert _rel(sol.u.mean_flat[b].cpu().numpy(), osol.u_mean[-1]) < tol_mean
         L = sol.u.cholesky_flat[b].cpu().numpy()
         Lo = osol.u_chol[-1]
         assert _rel(H.cov_from_chol(L), H.cov_from_chol(Lo)) < tol_cov
         assert _rel(sol.output_scale[b].cpu().numpy(), np.asarray(osol.output_scale[-1])) < tol_cov
+    assert num_stable >= B - 2  # the sequence check must not be vacuous
 
 
 @pytest.mark.parametrize("fact,constraint,solver", list(itertools.product(
@@ -114,12 +134,21 @@ def test_fixed_grid_matches_oracle(cuda, fact, constraint, solver):
     for b in range(B):
         osol = H.oracle_solve_fixed(s, tc[b], params[b], grid)
         assert np.allclose(sol.t[b].cpu().numpy(), osol.t, rtol=0, atol=1e-13)
-        assert _rel(sol.u.mean_flat[b].cpu().numpy(), osol.u_mean) < RTOL_FIXED
+        # solver_dynamic scales the process noise by sigma, the whitened norm of the residual u' - f(u): a
+        # difference of nearly equal numbers (|u'| / |residual| ~ 4e6 here), so one ulp in the extrapolated mean
+        # is ~4e-10 relative in sigma, hence in the covariance and (through the gain) in the mean. The 1e-10 bar
+        # is kept for the solvers whose covariance recursion does not depend on the data.
+        # The tolerance for solver_dynamic is therefore set from the oracle's own response to a 1-ulp change of
+        # its input (same principle as the adaptive tests); everything else is held to 1e-10.
+        tol_cov = RTOL_FIXED
+        if solver == "solver_dynamic":
+            pert = H.oracle_solve_fixed(s, tc[b] * (1.0 + 2.3e-16), params[b], grid)
+            sens = max(_rel(pert.u_mean, osol.u_mean),
+                       max(_rel(H.cov_from_chol(pert.u_chol[k]), H.cov_from_chol(osol.u_chol[k])) for k in range(len(grid))))
+            tol_cov = max(RTOL_FIXED, 100 * sens)
+            assert tol_cov < 1e-3  # guard against a vacuous comparison
+        assert _rel(sol.u.mean_flat[b].cpu().numpy(), osol.u_mean) < tol_cov
         L = sol.u.cholesky_flat[b].cpu().numpy()
-        # solver_dynamic rescales the covariance by sigma^2, and sigma is the whitened norm of the residual
-        # u' - f(u): a difference of nearly equal numbers (|u'| / |residual| ~ 4e6 here), so one ulp in the
-        # extrapolated mean is ~4e-10 relative in sigma. Means are unaffected (the gain does not depend on sigma).
-        tol_cov = 5e-9 if solver == "solver_dynamic" else RTOL_FIXED
         for k in range(len(grid)):
             assert _rel(H.cov_from_chol(L[k]), H.cov_from_chol(osol.u_chol[k])) < tol_cov, k
         # sign-normalised factors agree as well (LAPACK reflector convention)
@@ -132,10 +161,12 @@ def test_fixed_grid_matches_oracle(cuda, fact, constraint, solver):
             assert _rel(sol.output_scale[b, 1:].cpu().numpy(), np.asarray(osol.output_scale)) < RTOL_FIXED
 
 
-@pytest.mark.parametrize("combo", [dict(clip_dt=False), dict(clip_dt=False, solver="solver_dynamic", fact="blockdiag"),
-                                   dict(clip_dt=True, solver="solver_mle")],
-                         ids=["noclip", "noclip-dynamic-bd", "clip-mle"])  # fmt: skip
-def test_adaptive_save_at_matches_oracle(cuda, combo):
+@pytest.mark.parametrize("combo,num_ck", [(dict(clip_dt=False), 41),
+                                          (dict(clip_dt=False, solver="solver_dynamic", fact="blockdiag"), 41),
+                                          (dict(clip_dt=False, solver="solver_mle", constraint="ts1"), 17),
+                                          (dict(clip_dt=True, solver="solver_mle"), 6)],
+                         ids=["noclip", "noclip-dynamic-bd", "noclip-mle-ts1", "clip-mle"])  # fmt: skip
+def test_adaptive_save_at_matches_oracle(cuda, combo, num_ck):
     import torch
 
     s = H.spec(**combo)
@@ -144,21 +175,29 @@ def test_adaptive_save_at_matches_oracle(cuda, combo):
     p_pdq, p_ivp, vf, ssm, solver, err, ctrl = H.product_build(s, params)
     tcoeffs, _ = p_pdq.jetexpand_ode_padded_scan(num=4)(vf, (u0,), t=0.0)
     prior = ssm.prior_wiener_integrated(tcoeffs)
-    save_at = np.linspace(0.0, 5.0, 41)  # dense grid: several checkpoints per step in places
+    # dense grid without clipping: several checkpoints inside one step in places (interpolation branch);
+    # with clipping the grid is coarse, because clip_dt cancels t_next - t and a dense grid makes the
+    # reference algorithm itself ill-conditioned (its own 1-ulp sensitivity reaches 1e-4 after 60 steps)
+    save_at = np.linspace(0.0, 5.0, num_ck)
     solve = p_ivp.solve_adaptive_save_at(solver=solver, error=err, control=ctrl, clip_dt=s["clip_dt"])
-    sol = solve(prior, save_at=save_at, atol=1e-7, rtol=1e-5)
+    sol = solve(prior, save_at=save_at, atol=1e-7, rtol=1e-5, trace_capacity=512)
     torch.cuda.synchronize()
     assert int(sol.status.abs().max()) == 0
     tc = tcoeffs.cpu().numpy()
+    gtrace = sol.trace.cpu().numpy()
+    num_stable = 0
     for b in range(B):
         osol, trace = H.oracle_solve_save_at(s, tc[b], params[b], save_at, 1e-7, 1e-5)
-        assert np.array_equal(sol.num_steps[b, 1:].cpu().numpy(), osol.num_steps)
-        assert int(sol.num_attempts[b]) == len(trace)
-        assert np.allclose(sol.t[b].cpu().numpy(), osol.t, rtol=0, atol=1e-12)
-        tol_mean, tol_cov = _tolerances(s, tc[b], params[b], save_at, 1e-7, 1e-5, osol)
+        tol_mean, tol_cov, stable = _tolerances(s, tc[b], params[b], save_at, 1e-7, 1e-5, osol, trace)
+        if stable:
+            num_stable += 1
+            assert np.array_equal(sol.num_steps[b, 1:].cpu().numpy(), osol.num_steps), b
+            _check_sequence(gtrace[b], trace, int(sol.num_attempts[b]))
+            assert np.allclose(sol.t[b].cpu().numpy(), osol.t, rtol=0, atol=1e-12)
         assert _rel(sol.u.mean_flat[b].cpu().numpy(), osol.u_mean) < tol_mean
         L = sol.u.cholesky_flat[b].cpu().numpy()
         assert _rel(H.cov_from_chol(L), H.cov_from_chol(osol.u_chol)) < tol_cov
+    assert num_stable >= B - 2
 
 
 def test_taylor_init_and_dt0_match_oracle(cuda):
