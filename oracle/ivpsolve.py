@@ -184,7 +184,7 @@ def solve_fixed_grid(*, solver):
     return solve
 
 
-def solve_adaptive_save_every_step(*, solver, error, control=None, clip_dt=True):
+def solve_adaptive_save_every_step(*, solver, error, control=None, clip_dt=False):
     """util/test_util.py:10-80: record every accepted step."""
     if control is None:
         control = control_integral()

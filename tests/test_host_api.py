@@ -1,0 +1,108 @@
+"""CPU-only checks of the product's host side: the C ABI exports, config lowering, argument validation.
+
+No compute call is made here (there is no GPU in the build container); the GPU parity tests do that.
+"""
+
+import ctypes as C
+import pathlib
+import re
+
+import numpy as np
+import pytest
+
+from probdiffeq_b200 import _iwp, _lib
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_symbol_the_header_declares():
+    header = (ROOT / "include" / "probdiffeq_b200.h").read_text()
+    declared = set(re.findall(r"\b(pdeq_[a-z0-9_]+)\s*\(", header))
+    declared -= {"pdeq_config", "pdeq_problem", "pdeq_solution"}
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.pdeq_version() == 100
+
+
+def test_struct_layouts_match_the_header():
+    # sizes computed from the C declarations: 16 int32 + 5 double + 2*64 double + 2*9 double
+    assert C.sizeof(_lib.Config) == 16 * 4 + 5 * 8 + 2 * 64 * 8 + 2 * 9 * 8
+    assert C.sizeof(_lib.Problem) == 8 * 8
+    assert C.sizeof(_lib.Solution) == 12 * 8
+
+
+def test_vector_field_registry():
+    lib = _lib.load()
+    expect = {"lotka_volterra": (1, 4, 2), "pleiades": (1, 0, 28), "hires": (1, 0, 8),
+              "vanderpol": (2, 1, 1), "linear": (1, 1, 0), "burgers": (1, 1, 0)}  # fmt: skip
+    for name, (order, nparams, dim) in expect.items():
+        vid = lib.pdeq_vf_id(name.encode())
+        assert vid >= 0
+        assert (lib.pdeq_vf_ode_order(vid), lib.pdeq_vf_num_params(vid), lib.pdeq_vf_dim(vid)) == (order, nparams, dim)
+    assert lib.pdeq_vf_id(b"no_such_problem") == -1
+
+
+def _cfg(**kw):
+    cfg = _lib.Config()
+    cfg.factorisation, cfg.num_derivatives, cfg.ode_dim = 0, 4, 2
+    cfg.vf_id = _lib.load().pdeq_vf_id(b"lotka_volterra")
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def test_config_validation_reports_errors_without_touching_the_gpu():
+    lib = _lib.load()
+    assert lib.pdeq_config_supported(C.byref(_cfg())) == 0
+    assert lib.pdeq_config_supported(C.byref(_cfg(ode_dim=3))) < 0
+    assert b"dimension" in lib.pdeq_last_error()
+    assert lib.pdeq_config_supported(C.byref(_cfg(num_derivatives=9))) < 0
+    assert lib.pdeq_config_supported(C.byref(_cfg(vf_id=99))) < 0
+    assert lib.pdeq_config_supported(C.byref(_cfg(solver=7))) < 0
+    assert lib.pdeq_config_supported(None) < 0
+    with pytest.raises(ValueError):
+        _lib.check(lib.pdeq_config_supported(C.byref(_cfg(control=5))), "cfg")
+
+
+def test_iwp_system_matrices_match_the_oracle():
+    from oracle import linalg
+
+    for nu in range(1, 8):
+        a, q, f = _iwp.system_matrices(nu)
+        a_ref, q_ref = linalg.system_matrices_1d_iwp(nu)
+        assert np.array_equal(a, a_ref) and np.allclose(q, q_ref, rtol=1e-15, atol=0)
+        assert np.array_equal(f, linalg.factorial(np.arange(nu + 2)))
+        assert np.allclose(q @ q.T, np.flip(1.0 / (np.arange(1, nu + 2)[:, None] + np.arange(1, nu + 2)[None, :] - 1.0)), rtol=1e-8)
+
+
+def test_product_path_fails_loudly_without_a_gpu():
+    import torch
+
+    from probdiffeq_b200 import probdiffeq
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    vf = probdiffeq.ode("lotka_volterra", params=[0.5, 0.05, 0.5, 0.05])
+    with pytest.raises(_lib.NativeLibraryError):
+        probdiffeq.jetexpand_ode_padded_scan(num=4)(vf, (np.asarray([20.0, 20.0]),), t=0.0)
+
+
+def test_constructors_mirror_the_reference_error_behaviour():
+    from probdiffeq_b200 import ivpsolve, probdiffeq
+
+    with pytest.raises(ValueError):
+        probdiffeq.ode("lotka_volterra")  # parameters missing
+    with pytest.raises(ValueError):
+        probdiffeq.ode("not_registered")
+    with pytest.raises(TypeError):
+        probdiffeq.state_space_model_isotropic().constraint_ode_ts0(lambda u, t: u)
+    vf = probdiffeq.ode("hires")
+    ssm = probdiffeq.state_space_model_isotropic()
+    ts0 = ssm.constraint_ode_ts0(vf)
+    fp = probdiffeq.solver(strategy=probdiffeq.strategy_smoother_fixedpoint(), constraint=ts0)
+    with pytest.warns(UserWarning):
+        ivpsolve.solve_fixed_grid(solver=fp)  # reference: solvers_via_fixed_steps.py:14-18
+    assert ivpsolve.control_integral().safety == 0.95
+    assert ivpsolve.control_proportional_integral().exponent_proportional == 0.4

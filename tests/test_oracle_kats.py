@@ -1,0 +1,271 @@
+"""Pin the oracle against the reference's own known-answer tests and cross-implementation identities.
+
+Each test names the reference test it restates (paths relative to /root/reference/tests). The reference
+cannot be imported here (no JAX), so these identities -- which do not depend on JAX-generated data -- are what
+pins the restatement.
+"""
+
+import numpy as np
+import pytest
+import scipy.integrate
+import scipy.stats
+
+from oracle import ivpsolve, linalg, ssm
+from oracle import probdiffeq as pdq
+
+FACTORIES = [pdq.state_space_model_isotropic, pdq.state_space_model_dense, pdq.state_space_model_blockdiag]
+
+
+@pytest.mark.parametrize("factory", FACTORIES)
+@pytest.mark.parametrize("dt", [1.234, -1.234])
+def test_iwp_transitions_are_correct_in_1d(factory, dt):
+    """test_probdiffeq/test_priors/test_wiener_integrated.py:12-43,49-81."""
+    model = factory()
+    iwp = model.prior_wiener_integrated(np.asarray([2.0, 3.0, 4.0, 5.0]))
+    scale = np.ones(1) if model.kind == "blockdiag" else 1.0
+    cond = iwp.transition(dt=dt, output_scale=scale)
+    cond = cond.alg.preconditioner_apply(cond)
+    A = np.asarray([[1.0, dt, dt**2 / 2, dt**3 / 6], [0, 1.0, dt, dt**2 / 2], [0, 0, 1.0, dt], [0, 0, 0, 1.0]])
+    h = abs(dt)
+    Q = np.asarray(
+        [
+            [h**7 / 252, h**6 / 72, h**5 / 30, h**4 / 24],
+            [h**6 / 72, h**5 / 20, h**4 / 8, h**3 / 6],
+            [h**5 / 30, h**4 / 8, h**3 / 3, h**2 / 2],
+            [h**4 / 24, h**3 / 6, h**2 / 2, h],
+        ]
+    )
+    assert np.allclose(np.squeeze(cond.A), A, rtol=1e-14, atol=1e-14)
+    mean, cov = cond.noise.cov_dense()
+    assert np.allclose(mean, 0.0)
+    assert np.allclose(cov, Q, rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("shapes", [[(4, 3), (3, 3), (4, 4)], [(2, 3), (3, 3), (2, 2)]])
+def test_revert_conditional(shapes):
+    """test_util/test_cholesky_util.py:14-33."""
+    rng = np.random.default_rng(1)
+    HC = rng.normal(size=shapes[0]) + 1.0
+    C = rng.normal(size=shapes[1]) + 2.0
+    X = rng.normal(size=shapes[2]) + 3.0 + np.eye(shapes[2][0])
+    S = HC @ HC.T + X @ X.T
+    K = C @ HC.T @ np.linalg.inv(S)
+    C1 = C @ C.T - K @ S @ K.T
+    r_obs, (r_cor, gain) = linalg.revert_conditional(R_X_F=HC.T, R_X=C.T, R_YX=X.T)
+    assert np.allclose(r_obs.T @ r_obs, S)
+    assert np.allclose(gain, K)
+    assert np.allclose(r_cor.T @ r_cor, C1)
+
+
+def test_revert_conditional_zero_covariance_is_finite():
+    """test_util/test_cholesky_util.py:41-55 (values, not gradients): zero prior covariance is admissible."""
+    HC, C = np.zeros((2, 3)), np.zeros((3, 3))
+    X = np.asarray([[4.0, 0.3], [0.1, 3.5]])
+    r_obs, (r_cor, gain) = linalg.revert_conditional(R_X_F=HC.T, R_X=C.T, R_YX=X.T)
+    assert np.all(np.isfinite(r_obs)) and np.all(np.isfinite(gain)) and np.allclose(r_cor, 0.0)
+
+
+@pytest.mark.parametrize("factory", FACTORIES)
+def test_logpdf_matches_dense_mvn(factory):
+    """test_probdiffeq/test_logpdf.py:18-29."""
+    rng = np.random.default_rng(3)
+    n, d = 3, 2
+    model = factory()
+    prior = model.prior_wiener_integrated(rng.normal(size=(n, d)))
+    tr = prior.transition(dt=0.3, output_scale=np.ones(d) if model.kind == "blockdiag" else 1.0)
+    rv = tr.marginalise(prior.init)
+    u_nd = rng.normal(size=(n, d))
+    mean, cov = rv.cov_dense()
+    expected = scipy.stats.multivariate_normal(mean, cov).logpdf(u_nd.reshape(-1))
+    assert np.isclose(rv.alg.logpdf(rv, rv.alg.from_nd(u_nd)), expected, rtol=1e-10)
+
+
+def test_controllers_pi_equals_i_for_trivial_exponents():
+    """test_ivpsolve/test_controllers.py:10-26."""
+    pi = ivpsolve.control_proportional_integral(exponent_integral=1.0, exponent_proportional=0.0)
+    i = ivpsolve.control_integral()
+    dt_pi, x_pi, dt_i, x_i = 0.1428, pi.init(0.1428), 0.1428, i.init(0.1428)
+    for _ in range(4):
+        dt_pi, x_pi = pi.apply(dt_pi, x_pi, error_power=3.142)
+        dt_i, x_i = i.apply(dt_i, x_i, error_power=3.142)
+    assert np.isclose(dt_pi, dt_i, rtol=1e-15)
+
+
+def test_cholesky_hilbert_is_a_cholesky_factor():
+    """util/cholesky_util.py:106-176 against the definition."""
+    for n in (2, 5, 8):
+        L = linalg.cholesky_hilbert(n)
+        H = 1.0 / (np.arange(1, n + 1)[:, None] + np.arange(1, n + 1)[None, :] - 1.0)
+        assert np.allclose(L @ L.T, H, rtol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------------
+# end-to-end: accuracy against an independent integrator + cross-implementation identities
+# ---------------------------------------------------------------------------------------------------
+
+LV = pdq.ode("lotka_volterra")
+U0 = np.asarray([20.0, 20.0])
+
+
+def _setup(kind, constraint, solver_name, strategy, error_name, num=3):
+    model = getattr(pdq, "state_space_model_" + kind)()
+    tcoeffs, _ = pdq.jetexpand_ode_padded_scan(num=num)(LV, (U0,), t=0.0)
+    prior = model.prior_wiener_integrated(tcoeffs)
+    cons = getattr(model, "constraint_ode_" + constraint)(LV)
+    slv = getattr(pdq, solver_name)(strategy=strategy(), constraint=cons)
+    err = getattr(pdq, error_name)(constraint=cons)
+    return prior, slv, err
+
+
+@pytest.fixture(scope="module")
+def truth():
+    sol = scipy.integrate.solve_ivp(
+        lambda t, y: LV.vector_field((y,), t), (0.0, 2.0), U0, rtol=1e-12, atol=1e-12, method="DOP853",
+        t_eval=np.linspace(0.0, 2.0, 5),
+    )  # fmt: skip
+    return sol.y.T
+
+
+@pytest.mark.parametrize("kind", ["isotropic", "blockdiag", "dense"])
+@pytest.mark.parametrize("constraint", ["ts0", "ts1"])
+@pytest.mark.parametrize("solver_name", ["solver", "solver_mle", "solver_dynamic"])
+@pytest.mark.parametrize("strategy", [pdq.strategy_filter, pdq.strategy_smoother_fixedpoint])
+def test_save_at_solution_is_accurate(kind, constraint, solver_name, strategy, truth):
+    """test_ivpsolve/test_solve_adaptive_save_at.py:211-247 with scipy instead of jax's odeint."""
+    prior, slv, err = _setup(kind, constraint, solver_name, strategy, "error_residual_std")
+    solve = ivpsolve.solve_adaptive_save_at(solver=slv, error=err)
+    sol = solve(prior, save_at=np.linspace(0.0, 2.0, 5), atol=1e-6, rtol=1e-4)
+    assert np.allclose(sol.u_mean[:, 0], truth, rtol=2e-3)
+    assert np.allclose(sol.t, np.linspace(0.0, 2.0, 5))
+
+
+@pytest.mark.parametrize("error_name", ["error_residual_std", "error_state_std"])
+def test_terminal_values_equal_last_save_at_entry(error_name):
+    """solve_adaptive_terminal_values is save_at=[t0, t1] (solvers_via_adaptive_steps.py:16-43)."""
+    prior, slv, err = _setup("isotropic", "ts0", "solver", pdq.strategy_filter, error_name)
+    a = ivpsolve.solve_adaptive_terminal_values(solver=slv, error=err)(prior, t0=0.0, t1=2.0, atol=1e-6, rtol=1e-4)
+    b = ivpsolve.solve_adaptive_save_at(solver=slv, error=err, clip_dt=True)(
+        prior, save_at=np.asarray([0.0, 2.0]), atol=1e-6, rtol=1e-4
+    )
+    assert np.array_equal(a.u.tcoeffs, b.u_mean[-1])
+
+
+@pytest.mark.parametrize("solver_name", ["solver", "solver_dynamic"])
+def test_dense_equals_isotropic_for_ts0(solver_name):
+    """test_probdiffeq/test_calibration/test_dynamic_across_factorisations.py:12: for ts0 the dense and
+    isotropic models describe the same process when the dynamics are calibrated with a shared scale."""
+    grid = np.linspace(0.0, 1.0, 11)
+    out = {}
+    for kind in ("isotropic", "dense"):
+        prior, slv, _ = _setup(kind, "ts0", solver_name, pdq.strategy_filter, "error_residual_std")
+        out[kind] = ivpsolve.solve_fixed_grid(solver=slv)(prior, grid=grid)
+    assert np.allclose(out["isotropic"].u_mean, out["dense"].u_mean, rtol=1e-9, atol=1e-12)
+    iso_cov = np.stack([r.cov_dense()[1] for r in out["isotropic"].u])
+    dense_cov = np.stack([r.cov_dense()[1] for r in out["dense"].u])
+    # entries that vanish exactly in the isotropic model are rounding noise in the dense one
+    assert np.allclose(iso_cov, dense_cov, rtol=1e-7, atol=1e-13 * np.abs(dense_cov).max())
+
+
+def test_blockdiag_equals_independent_scalar_dense_models():
+    """test_dynamic_across_factorisations.py:66 (vmap(dense) == blockdiag) on a decoupled problem."""
+    lin = pdq.ode("linear", [1.5])
+    u0 = np.asarray([1.0, -2.0, 0.5])
+    grid = np.linspace(0.0, 1.0, 9)
+    tc, _ = pdq.jetexpand_ode_padded_scan(num=3)(lin, (u0,), t=0.0)
+    bd = pdq.state_space_model_blockdiag()
+    slv = pdq.solver_dynamic(strategy=pdq.strategy_filter(), constraint=bd.constraint_ode_ts0(lin))
+    sol_bd = ivpsolve.solve_fixed_grid(solver=slv)(bd.prior_wiener_integrated(tc), grid=grid)
+    for i in range(3):
+        dn = pdq.state_space_model_dense()
+        slv_i = pdq.solver_dynamic(strategy=pdq.strategy_filter(), constraint=dn.constraint_ode_ts0(lin))
+        sol_i = ivpsolve.solve_fixed_grid(solver=slv_i)(dn.prior_wiener_integrated(tc[:, i : i + 1]), grid=grid)
+        assert np.allclose(sol_bd.u_mean[:, :, i], sol_i.u_mean[:, :, 0], rtol=1e-10, atol=1e-14)
+        assert np.allclose(sol_bd.u_std[:, :, i], sol_i.u_std[:, :, 0], rtol=1e-8, atol=1e-16)
+
+
+def test_fixed_grid_on_the_adaptive_grid_reproduces_the_adaptive_solution():
+    """test_ivpsolve/test_solve_fixed_grid.py:17-54."""
+    prior, slv, err = _setup("isotropic", "ts0", "solver", pdq.strategy_filter, "error_residual_std")
+    adaptive = ivpsolve.solve_adaptive_save_every_step(solver=slv, error=err, clip_dt=True)(
+        prior, t0=0.0, t1=1.0, atol=1e-5, rtol=1e-3
+    )
+    fixed = ivpsolve.solve_fixed_grid(solver=slv)(prior, grid=adaptive.t)
+    assert np.allclose(adaptive.u_mean, fixed.u_mean, rtol=1e-10)
+    assert np.allclose(adaptive.u_std, fixed.u_std, rtol=1e-8, atol=1e-16)
+
+
+def test_fixedpoint_smoother_equals_fixedinterval_smoother_on_the_same_grid():
+    """test_probdiffeq/test_strategies/test_smoother_fixedinterval_vs_fixedpoint.py:50-86."""
+    for kind in ("isotropic", "blockdiag", "dense"):
+        prior, slv_fi, err = _setup(kind, "ts0", "solver", pdq.strategy_smoother_fixedinterval, "error_residual_std", num=2)
+        every = ivpsolve.solve_adaptive_save_every_step(solver=slv_fi, error=err)(
+            prior, t0=0.0, t1=2.0, atol=1e-3, rtol=1e-3
+        )
+        _, slv_fp, err_fp = _setup(kind, "ts0", "solver", pdq.strategy_smoother_fixedpoint, "error_residual_std", num=2)
+        fp = ivpsolve.solve_adaptive_save_at(solver=slv_fp, error=err_fp)(prior, save_at=every.t, atol=1e-3, rtol=1e-3)
+        assert np.allclose(fp.t, every.t)
+        assert np.array_equal(fp.num_steps, every.num_steps)
+        assert np.allclose(fp.u_mean, every.u_mean, rtol=1e-9, atol=1e-12)
+        assert np.allclose(fp.u_std, every.u_std, rtol=1e-7, atol=1e-14)
+
+
+def test_save_at_is_invariant_to_cutting_the_grid():
+    """test_probdiffeq/test_dense_output/test_behaviour_close_to_t1.py:59-94: solving to [t0, t1] equals solving
+    on a grid that contains t1 and reading off t1 (filter, no clipping)."""
+    prior, slv, err = _setup("isotropic", "ts0", "solver", pdq.strategy_filter, "error_residual_std")
+    solve = ivpsolve.solve_adaptive_save_at(solver=slv, error=err)
+    a = solve(prior, save_at=np.asarray([0.0, 0.7, 1.4]), atol=1e-6, rtol=1e-4)
+    b = solve(prior, save_at=np.asarray([0.0, 1.4]), atol=1e-6, rtol=1e-4)
+    assert np.allclose(a.u_mean[-1], b.u_mean[-1], rtol=1e-9)
+
+
+def test_taylor_coefficients_match_hand_derivatives():
+    """jet_expansion_algorithms.py:49-177 against derivatives of u' = f(u) written out by hand."""
+    a, b, c, d = LV.params
+    u = U0
+    f = np.asarray([a * u[0] - b * u[0] * u[1], -c * u[1] + d * u[0] * u[1]])
+    J = np.asarray([[a - b * u[1], -b * u[0]], [d * u[1], -c + d * u[0]]])
+    d2 = J @ f
+    tc, _ = pdq.jetexpand_ode_padded_scan(num=2)(LV, (U0,), t=0.0)
+    assert np.allclose(tc[1], f) and np.allclose(tc[2], d2)
+    vdp = pdq.ode("vanderpol", [1e3])
+    tc2, _ = pdq.jetexpand_ode_padded_scan(num=2)(vdp, (np.asarray([2.0]), np.asarray([0.0])), t=0.0)
+    # u'' = s((1-u^2)u' - u) = -2s ; u''' = s(-2uu'u' + (1-u^2)u'' - u') = s(-3)(-2s) = 6 s^2
+    assert np.allclose(tc2[:, 0], [2.0, 0.0, -2e3, 6e6])
+
+
+def test_jacobians_are_exact():
+    """jacobians.py:93-98: complex-step Jacobians against closed forms."""
+    a, b, c, d = LV.params
+    (J,) = LV.jacobians((U0,), 0.0)
+    assert np.allclose(J, [[a - b * U0[1], -b * U0[0]], [d * U0[1], -c + d * U0[0]]], rtol=1e-15)
+    hires = pdq.ode("hires")
+    from oracle import problems
+
+    u = problems.hires_u0() + 0.1
+    (Jh,) = hires.jacobians((u,), 0.0)
+    assert np.isclose(Jh[5, 5], -280.0 * u[7] - 0.43) and np.isclose(Jh[6, 7], 280.0 * u[5])
+
+
+def test_lml_terminal_values_matches_dense_gaussian():
+    """estimators_and_losses.py:20-50 on all three factorisations."""
+    rng = np.random.default_rng(0)
+    for kind in ("isotropic", "blockdiag", "dense"):
+        prior, slv, err = _setup(kind, "ts0", "solver", pdq.strategy_filter, "error_residual_std")
+        sol = ivpsolve.solve_adaptive_terminal_values(solver=slv, error=err)(prior, t0=0.0, t1=1.0, atol=1e-5, rtol=1e-3)
+        data = sol.u.tcoeffs[0] + 1e-2 * rng.normal(size=2)
+        std = 1e-2 if kind == "isotropic" else 1e-2 * np.ones(2)
+        lml = pdq.loss_lml_terminal_values()(data, marginals=sol.u, std=std)
+        mean, cov = sol.u.cov_dense()
+        if kind == "dense":
+            m0, c0 = mean[:2], cov[:2, :2]
+        else:
+            n = sol.u.tcoeffs.shape[0]
+            m0 = mean.reshape(n, 2)[0]
+            c0 = cov.reshape(n, 2, n, 2)[0, :, 0, :]
+        expected = scipy.stats.multivariate_normal(m0, c0 + 1e-4 * np.eye(2)).logpdf(data)
+        assert np.isclose(lml, expected, rtol=1e-9), kind
+
+
+def test_unused_import_guard():
+    assert ssm.Normal is not None
