@@ -83,8 +83,18 @@ static int validate(const pdeq_config* c) {
 static const LoopEntry* select_loop(const pdeq_config* c) {
   int fact = c->factorisation;
   if (fact == PDEQ_FACT_DENSE && c->ode_dim == 1) fact = PDEQ_FACT_ISOTROPIC;
-  if (c->strategy == PDEQ_STRATEGY_FILTER) {
-    const LoopEntry* e = find_loop({c->vf_id, c->num_derivatives, fact, c->ode_dim, c->constraint == PDEQ_CONSTRAINT_TS0});
+  const int ts0 = c->constraint == PDEQ_CONSTRAINT_TS0;
+  const int fp = c->strategy == PDEQ_STRATEGY_FIXEDPOINT;
+  // K1: thread per instance, compile-time d, filter only
+  if (!fp) {
+    const LoopEntry* e = find_loop({c->vf_id, c->num_derivatives, fact, c->ode_dim, ts0, 0});
+    if (e != nullptr) return e;
+  }
+  // K2: lane per dimension, run-time d <= 1024, filter and fixed-point smoother
+  //     (several dimensions per lane only for the block-diagonal filter; otherwise d <= 256)
+  const int k2_max_d = (fact == PDEQ_FACT_BLOCKDIAG && !fp) ? K2_CTA_THREADS * K2_MAX_DPL : K2_CTA_THREADS;
+  if (fact != PDEQ_FACT_DENSE && c->ode_dim <= k2_max_d) {
+    const LoopEntry* e = find_loop({c->vf_id, c->num_derivatives, fact, 0, ts0, fp});
     if (e != nullptr) return e;
   }
   return nullptr;
@@ -130,7 +140,12 @@ int pdeq_config_supported(const pdeq_config* cfg) {
   return 0;
 }
 
-size_t pdeq_workspace_bytes(const pdeq_config*, int64_t, int32_t) { return 256; }
+size_t pdeq_workspace_bytes(const pdeq_config* cfg, int64_t num_instances, int32_t num_checkpoints) {
+  if (validate(cfg) != 0) return 256;
+  const LoopEntry* e = select_loop(cfg);
+  if (e == nullptr) return 256;
+  return e->workspace_bytes(*cfg, num_instances, num_checkpoints);
+}
 
 static int check_common(const pdeq_config* cfg, const pdeq_problem* pr, const pdeq_solution* so, int32_t T,
                         void* ws, size_t ws_bytes) {
@@ -150,7 +165,7 @@ static int check_common(const pdeq_config* cfg, const pdeq_problem* pr, const pd
 
 static int run_loop(const pdeq_config* cfg, const pdeq_problem* pr, const pdeq_solution* so, const double* grid,
                     int32_t T, int fixed, double atol, double rtol, const double* dt0, int64_t dt0_stride,
-                    double eps, double damp, void* ws, void* stream) {
+                    double eps, double damp, void* ws, size_t ws_bytes, void* stream) {
   if (pr->num_instances == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   LoopArgs a;
@@ -170,7 +185,7 @@ static int run_loop(const pdeq_config* cfg, const pdeq_problem* pr, const pdeq_s
   cudaError_t e = cudaMemsetAsync(ws, 0, 256, s);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
   const LoopEntry* entry = select_loop(cfg);
-  e = entry->launch(a, s);
+  e = entry->launch(a, ws, ws_bytes, s);
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
   return 0;
 }
@@ -183,7 +198,7 @@ int pdeq_solve_adaptive_save_at(const pdeq_config* cfg, const pdeq_problem* prob
   if (rc != 0) return rc;
   if (save_at == nullptr || dt0 == nullptr) return fail(-25, "save_at/dt0 is NULL");
   return run_loop(cfg, problem, solution, save_at, num_checkpoints, 0, atol, rtol, dt0, dt0_stride, eps, damp,
-                  workspace, stream);
+                  workspace, workspace_bytes, stream);
 }
 
 int pdeq_solve_fixed_grid(const pdeq_config* cfg, const pdeq_problem* problem, const double* grid,
@@ -192,8 +207,10 @@ int pdeq_solve_fixed_grid(const pdeq_config* cfg, const pdeq_problem* problem, c
   int rc = check_common(cfg, problem, solution, num_gridpoints, workspace, workspace_bytes);
   if (rc != 0) return rc;
   if (grid == nullptr) return fail(-25, "grid is NULL");
+  if (cfg->strategy == PDEQ_STRATEGY_FIXEDPOINT)
+    return fail(-10, "solve_fixed_grid with a fixed-point smoother is not accelerated (the reference warns against it)");
   return run_loop(cfg, problem, solution, grid, num_gridpoints, 1, 0.0, 0.0, nullptr, 0, 0.0, damp, workspace,
-                  stream);
+                  workspace_bytes, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------

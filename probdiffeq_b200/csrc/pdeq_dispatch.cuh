@@ -8,23 +8,28 @@
 #include <cstdint>
 #include <cstdio>
 
+#include "pdeq_loop_group.cuh"
 #include "pdeq_loop_thread.cuh"
 
 namespace pdeq {
 
 struct KernelKey {
-  int vf, nu, fact, d, ts0;
+  int vf, nu, fact, d, ts0;  // d == 0: the kernel takes the ODE dimension at run time
+  int fixedpoint = 0;
   bool operator==(const KernelKey& o) const {
-    return vf == o.vf && nu == o.nu && fact == o.fact && d == o.d && ts0 == o.ts0;
+    return vf == o.vf && nu == o.nu && fact == o.fact && d == o.d && ts0 == o.ts0 && fixedpoint == o.fixedpoint;
   }
 };
 
-using LoopLauncher = cudaError_t (*)(const LoopArgs&, cudaStream_t);
+// `workspace` points at the caller's scratch: the first 256 bytes hold the work counter, the rest is kernel specific.
+using LoopLauncher = cudaError_t (*)(const LoopArgs&, void* workspace, size_t workspace_bytes, cudaStream_t);
+using WorkspaceFn = size_t (*)(const pdeq_config&, int64_t num_instances, int32_t T);
 
 struct LoopEntry {
   KernelKey key;
   LoopLauncher launch;
-  const char* family;  // "thread" (K1) or "group" (K2) ...
+  WorkspaceFn workspace_bytes;
+  const char* family;  // "thread" (K1), "group" (K2), "dense" (K3)
 };
 
 void register_loop(const LoopEntry& e);
@@ -36,7 +41,7 @@ int device_sm_count();
 // K1 launcher
 // ---------------------------------------------------------------------------------------------------
 template <class VF, int NU, int FACT, int D, bool TS0>
-cudaError_t k1_launch(const LoopArgs& a, cudaStream_t stream) {
+cudaError_t k1_launch(const LoopArgs& a, void*, size_t, cudaStream_t stream) {
   using TL = ThreadLoop<VF, NU, FACT, D, TS0>;
   auto kern = k1_loop_kernel<VF, NU, FACT, D, TS0>;
   const bool needs_interp = a.fixed_grid == 0 && a.cfg.clip_dt == 0;
@@ -59,7 +64,8 @@ cudaError_t k1_launch(const LoopArgs& a, cudaStream_t stream) {
 
 template <class VF, int NU, int FACT, int D, bool TS0>
 struct K1Registrar {
-  K1Registrar() { register_loop({{VF::id, NU, FACT, D, TS0 ? 1 : 0}, &k1_launch<VF, NU, FACT, D, TS0>, "thread"}); }
+  static size_t ws(const pdeq_config&, int64_t, int32_t) { return 256; }
+  K1Registrar() { register_loop({{VF::id, NU, FACT, D, TS0 ? 1 : 0, 0}, &k1_launch<VF, NU, FACT, D, TS0>, &ws, "thread"}); }
 };
 
 #define PDEQ_INSTANTIATE_K1(VF, NU, D)                                              \
@@ -67,5 +73,101 @@ struct K1Registrar {
   static K1Registrar<VF, NU, PDEQ_FACT_ISOTROPIC, D, false> _k1_iso1_##VF##_##NU##_##D; \
   static K1Registrar<VF, NU, PDEQ_FACT_BLOCKDIAG, D, true> _k1_bd0_##VF##_##NU##_##D;  \
   static K1Registrar<VF, NU, PDEQ_FACT_BLOCKDIAG, D, false> _k1_bd1_##VF##_##NU##_##D;
+
+// ---------------------------------------------------------------------------------------------------
+// K2 launcher: warp per instance for d <= 32, CTA per instance otherwise.
+// ---------------------------------------------------------------------------------------------------
+struct K2Plan {
+  bool cta;
+  int threads, groups_per_cta, grid;
+  size_t smem_bytes, ring_bytes_per_group;
+};
+
+template <class VF, int NU, int FACT, bool TS0, bool FP>
+cudaError_t k2_plan(const pdeq_config& cfg, int64_t B, int32_t T, bool needs_interp, K2Plan* plan) {
+  using GL = GroupLoop<VF, NU, FACT, TS0, FP, false>;
+  const int d = cfg.ode_dim;
+  const size_t per_group = ((needs_interp ? 2 : 1) * (size_t)GL::NF * d + (size_t)VF::order * d + 32) * sizeof(double);
+  plan->cta = d > 32;
+  if (plan->cta) {
+    using GC = GroupLoop<VF, NU, FACT, TS0, FP, true>;
+    plan->threads = std::min(K2_CTA_THREADS, ((d + 31) / 32) * 32);
+    if ((d + plan->threads - 1) / plan->threads > GC::MAXR) return cudaErrorInvalidValue;
+    plan->groups_per_cta = 1;
+  } else {
+    plan->groups_per_cta = 4;
+    while (plan->groups_per_cta > 1 && per_group * plan->groups_per_cta > 96 * 1024) plan->groups_per_cta /= 2;
+    plan->threads = 32 * plan->groups_per_cta;
+  }
+  plan->smem_bytes = per_group * plan->groups_per_cta;
+  if (plan->smem_bytes > 227 * 1024) return cudaErrorInvalidValue;
+  plan->ring_bytes_per_group = FP ? (size_t)T * GL::NFC * d * sizeof(double) : 0;
+  int per_sm = 0;
+  cudaError_t err;
+  if (plan->cta) {
+    auto kern = k2_loop_kernel<VF, NU, FACT, TS0, FP, true>;
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
+    if (err != cudaSuccess) return err;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, plan->threads, plan->smem_bytes);
+  } else {
+    auto kern = k2_loop_kernel<VF, NU, FACT, TS0, FP, false>;
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
+    if (err != cudaSuccess) return err;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, plan->threads, plan->smem_bytes);
+  }
+  if (err != cudaSuccess) return err;
+  if (per_sm < 1) per_sm = 1;
+  const long want = (B + plan->groups_per_cta - 1) / plan->groups_per_cta;
+  plan->grid = (int)std::max(1L, std::min(want, (long)per_sm * device_sm_count()));
+  return cudaSuccess;
+}
+
+template <class VF, int NU, int FACT, bool TS0, bool FP>
+size_t k2_workspace(const pdeq_config& cfg, int64_t B, int32_t T) {
+  K2Plan plan;
+  if (k2_plan<VF, NU, FACT, TS0, FP>(cfg, B, T, /*needs_interp=*/true, &plan) != cudaSuccess) return 256;
+  K2Plan plan2;
+  size_t groups = (size_t)plan.grid * plan.groups_per_cta;
+  if (k2_plan<VF, NU, FACT, TS0, FP>(cfg, B, T, /*needs_interp=*/false, &plan2) == cudaSuccess)
+    groups = std::max(groups, (size_t)plan2.grid * plan2.groups_per_cta);
+  return 256 + groups * plan.ring_bytes_per_group;
+}
+
+template <class VF, int NU, int FACT, bool TS0, bool FP>
+cudaError_t k2_launch(const LoopArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  const bool needs_interp = a.fixed_grid == 0 && a.cfg.clip_dt == 0;
+  K2Plan plan;
+  cudaError_t err = k2_plan<VF, NU, FACT, TS0, FP>(a.cfg, a.prob.num_instances, a.T, needs_interp, &plan);
+  if (err != cudaSuccess) return err;
+  GroupLaunchInfo info;
+  info.groups_per_cta = plan.groups_per_cta;
+  info.cond_ring = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
+  if (FP) {  // never launch more groups than the ring has room for
+    const size_t room = (workspace_bytes - 256) / plan.ring_bytes_per_group;
+    const int max_grid = (int)(room / plan.groups_per_cta);
+    if (max_grid < 1) return cudaErrorMemoryAllocation;
+    plan.grid = std::min(plan.grid, max_grid);
+  }
+  if (plan.cta)
+    k2_loop_kernel<VF, NU, FACT, TS0, FP, true><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);
+  else
+    k2_loop_kernel<VF, NU, FACT, TS0, FP, false><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);
+  return cudaGetLastError();
+}
+
+template <class VF, int NU, int FACT, bool TS0, bool FP>
+struct K2Registrar {
+  K2Registrar() {
+    register_loop({{VF::id, NU, FACT, 0, TS0 ? 1 : 0, FP ? 1 : 0}, &k2_launch<VF, NU, FACT, TS0, FP>,
+                   &k2_workspace<VF, NU, FACT, TS0, FP>, "group"});
+  }
+};
+
+// filter + fixed-point smoother, ts0 + ts1, for one factorisation
+#define PDEQ_INSTANTIATE_K2(VF, NU, FACT, TAG)                        \
+  static K2Registrar<VF, NU, FACT, true, false> _k2_f0_##VF##_##NU##_##TAG;  \
+  static K2Registrar<VF, NU, FACT, false, false> _k2_f1_##VF##_##NU##_##TAG; \
+  static K2Registrar<VF, NU, FACT, true, true> _k2_s0_##VF##_##NU##_##TAG;   \
+  static K2Registrar<VF, NU, FACT, false, true> _k2_s1_##VF##_##NU##_##TAG;
 
 }  // namespace pdeq

@@ -1,0 +1,159 @@
+"""GPU parity for the lane-per-dimension kernel (K2) and the fixed-point smoother, and for the remaining
+registered vector fields (Pleiades, Burgers, linear, Van der Pol) including their on-device Taylor initialisation.
+
+Same tolerance policy as test_gpu_lv_parity.py: identical accept/reject sequences wherever the oracle reproduces
+its own sequence under a 1-ulp perturbation of dt0, values within max(1e-8, 100 x the oracle's own sensitivity).
+"""
+
+import numpy as np
+import pytest
+
+import pdeq_test_helpers as H
+from oracle import problems as o_problems
+from oracle import probdiffeq as o_pdq
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+def _cov(L):
+    return L @ np.swapaxes(L, -1, -2)
+
+
+def _run_case(s, params, inits, num, save_at, atol, rtol, *, dt0=0.1, terminal=False, min_stable=None):
+    """Solve an ensemble on the GPU and every instance with the oracle; compare."""
+    import torch
+
+    B = inits[0].shape[0]
+    p_pdq, p_ivp, vf, ssm, solver, err, ctrl = H.product_build(s, params)
+    tcoeffs, _ = p_pdq.jetexpand_ode_padded_scan(num=num)(vf, inits, t=float(save_at[0]))
+    prior = ssm.prior_wiener_integrated(tcoeffs)
+    if terminal:
+        solve = p_ivp.solve_adaptive_terminal_values(solver=solver, error=err, control=ctrl, clip_dt=s["clip_dt"])
+        sol = solve(prior, t0=save_at[0], t1=save_at[-1], atol=atol, rtol=rtol, dt0=dt0, trace_capacity=2048)
+    else:
+        solve = p_ivp.solve_adaptive_save_at(solver=solver, error=err, control=ctrl, clip_dt=s["clip_dt"])
+        sol = solve(prior, save_at=save_at, atol=atol, rtol=rtol, dt0=dt0, trace_capacity=2048)
+    torch.cuda.synchronize()
+    assert int(sol.status.abs().max()) == 0
+    tc = tcoeffs.cpu().numpy()
+    gtrace = sol.trace.cpu().numpy()
+    mean = sol.u.mean_flat.cpu().numpy()
+    chol = sol.u.cholesky_flat.cpu().numpy()
+    num_stable = 0
+    for b in range(B):
+        pb = None if params is None else params[b]
+        # the device Taylor initialisation against the oracle's
+        ovf = o_pdq.ode(s["vf"], pb)
+        ref_tc, _ = o_pdq.jetexpand_ode_padded_scan(num=num)(ovf, [u[b] for u in inits], t=float(save_at[0]))
+        assert _rel(tc[b], ref_tc) < 1e-10  # the Burgers Laplacian cancels ~4 digits at d = 300
+        osol, otrace = H.oracle_solve_save_at(s, tc[b], pb, save_at, atol, rtol, dt0=dt0)
+        pert, ptrace = H.oracle_solve_save_at(s, tc[b], pb, save_at, atol, rtol, dt0=dt0 * (1 + 2.3e-16))
+        stable = len(ptrace) == len(otrace) and [r[3] for r in ptrace] == [r[3] for r in otrace]
+        tol_mean = max(1e-8, 100 * _rel(pert.u_mean, osol.u_mean))
+        tol_cov = max(1e-6, 100 * _rel(_cov(pert.u_chol), _cov(osol.u_chol)))
+        o_mean, o_chol = (osol.u_mean[-1], osol.u_chol[-1]) if terminal else (osol.u_mean, osol.u_chol)
+        if stable:
+            num_stable += 1
+            na = int(sol.num_attempts[b])
+            assert na == len(otrace), (b, na, len(otrace))
+            otr = np.asarray(otrace)
+            assert np.array_equal(gtrace[b, :na, 3] > 0.5, otr[:, 3] > 0.5)
+            drift = np.max(np.abs(np.asarray(ptrace)[:, 0] - otr[:, 0]))  # the oracle's own 1-ulp sensitivity
+            assert np.max(np.abs(gtrace[b, :na, 0] - otr[:, 0])) <= max(1e-9, 100 * drift)
+            steps = sol.num_steps[b].cpu().numpy()
+            assert np.array_equal(np.atleast_1d(steps)[-1:] if terminal else steps[1:], osol.num_steps[-1:] if terminal else osol.num_steps)
+        assert _rel(mean[b], o_mean) < tol_mean, (b, _rel(mean[b], o_mean), tol_mean)
+        assert _rel(_cov(chol[b]), _cov(o_chol)) < tol_cov, (b, _rel(_cov(chol[b]), _cov(o_chol)), tol_cov)
+    if min_stable is None:
+        min_stable = max(B - 2, 1)
+    assert num_stable >= min_stable, num_stable
+    return sol
+
+
+@pytest.mark.parametrize("fact", ["blockdiag", "isotropic"])
+@pytest.mark.parametrize("combo", [dict(solver="solver", error="residual_std", control="i"),
+                                   dict(solver="solver_dynamic", error="residual_std", control="i"),
+                                   dict(solver="solver_mle", error="state_std", control="pi", constraint="ts1")],
+                         ids=["plain", "dynamic", "mle-ts1"])  # fmt: skip
+def test_fixedpoint_smoother_lotka_volterra(cuda, fact, combo):
+    s = H.spec(fact=fact, strategy="fixedpoint", clip_dt=False, **combo)
+    params, u0 = H.lv_ensemble(6, seed=11)
+    _run_case(s, params, (u0,), 4, np.linspace(0.0, 4.0, 13), 1e-7, 1e-5)
+
+
+def test_fixedpoint_smoother_with_clipping(cuda):
+    s = H.spec(fact="blockdiag", strategy="fixedpoint", clip_dt=True, solver="solver_dynamic", error="residual_std",
+               control="i")  # fmt: skip
+    params, u0 = H.lv_ensemble(4, seed=12)
+    _run_case(s, params, (u0,), 4, np.linspace(0.0, 3.0, 4), 1e-7, 1e-5)
+
+
+def _pleiades_ensemble(B, seed=1):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return o_problems.pleiades_u0()[None, :] + 1e-3 * rng.normal(size=(B, 28))
+
+
+def test_pleiades_blockdiag_filter_terminal(cuda):
+    s = H.spec(vf="pleiades", fact="blockdiag", solver="solver_dynamic", error="residual_std", control="i")
+    u0 = _pleiades_ensemble(3)
+    _run_case(s, None, (u0,), 5, np.asarray([0.0, 1.0]), 1e-8, 1e-5, dt0=0.01, terminal=True)
+
+
+def test_pleiades_blockdiag_fixedpoint_save_at(cuda):
+    """BASELINE config 3 wiring (shorter horizon, coarser grid): nu = 5, blockdiag ts0, fixed-point smoother,
+    solver_dynamic + error_residual_std + integral control, save_at grid."""
+    s = H.spec(vf="pleiades", fact="blockdiag", strategy="fixedpoint", solver="solver_dynamic", error="residual_std",
+               control="i", clip_dt=False)  # fmt: skip
+    u0 = _pleiades_ensemble(3)
+    _run_case(s, None, (u0,), 5, np.linspace(0.0, 1.0, 9), 1e-8, 1e-5, dt0=0.01)
+
+
+@pytest.mark.parametrize("d", [48, 300])
+def test_burgers_blockdiag_filter(cuda, d):
+    """BASELINE config 5 wiring at smaller d: blockdiag ts0 filter, solver + error_state_std + PI, clip, terminal.
+    d = 48 runs one dimension per lane, d = 300 two dimensions per lane (CTA of 256 threads)."""
+    s = H.spec(vf="burgers", fact="blockdiag", solver="solver", error="state_std", control="pi", clip_dt=True)
+    rng = np.random.Generator(np.random.PCG64(3))
+    B = 3
+    params = 0.01 * rng.uniform(0.5, 2.0, size=(B, 1))
+    u0 = np.repeat(o_problems.burgers_u0(d)[None, :], B, axis=0)
+    _run_case(s, params, (u0,), 3, np.asarray([0.0, 0.05]), 1e-7, 1e-4, dt0=1e-3, terminal=True)
+
+
+def test_burgers_ts1_blockdiag(cuda):
+    s = H.spec(vf="burgers", fact="blockdiag", constraint="ts1", solver="solver_dynamic", error="residual_std",
+               control="i", clip_dt=True)  # fmt: skip
+    d, B = 40, 2
+    params = np.asarray([[0.01], [0.015]])
+    u0 = np.repeat(o_problems.burgers_u0(d)[None, :], B, axis=0)
+    _run_case(s, params, (u0,), 3, np.asarray([0.0, 0.05]), 1e-7, 1e-4, dt0=1e-3, terminal=True)
+
+
+@pytest.mark.parametrize("fact", ["isotropic", "blockdiag"])
+def test_linear_high_dimensional(cuda, fact):
+    """benchmarks/A4: u' = 1.5 u, d = 100 (CTA mode; the isotropic model exercises the rms reductions)."""
+    s = H.spec(vf="linear", fact=fact, solver="solver_dynamic", error="residual_std", control="pi", clip_dt=True)
+    B, d = 3, 100
+    rng = np.random.Generator(np.random.PCG64(4))
+    params = 1.5 * rng.uniform(0.8, 1.2, size=(B, 1))
+    u0 = 1.0 + 0.1 * rng.normal(size=(B, d))
+    _run_case(s, params, (u0,), 3, np.asarray([0.0, 1.0]), 1e-8, 1e-5, terminal=True)
+
+
+@pytest.mark.parametrize("fact", ["dense", "isotropic"])
+def test_vanderpol_second_order_ts1(cuda, fact):
+    """BASELINE config 4b wiring: second-order Van der Pol (stiffness 1e3), nu = 4, ts1, filter, solver_dynamic +
+    error_state_std + integral control. d = 1, where the dense model coincides with the isotropic one."""
+    s = H.spec(vf="vanderpol", fact=fact, constraint="ts1", solver="solver_dynamic", error="state_std", control="i",
+               clip_dt=True)  # fmt: skip
+    B = 4
+    rng = np.random.Generator(np.random.PCG64(2))
+    u0 = 2.0 * rng.uniform(0.9, 1.1, size=(B, 1))
+    du0 = np.zeros((B, 1))
+    params = np.full((B, 1), 1e3)
+    _run_case(s, params, (u0, du0), 3, np.asarray([0.0, 0.5]), 1e-8, 1e-5, dt0=1e-4, terminal=True)
