@@ -97,6 +97,14 @@ static const LoopEntry* select_loop(const pdeq_config* c) {
     const LoopEntry* e = find_loop({c->vf_id, c->num_derivatives, fact, 0, ts0, fp});
     if (e != nullptr) return e;
   }
+  // K3: dense factorisation, CTA per instance, filter only; the work buffer must fit in shared memory
+  if (fact == PDEQ_FACT_DENSE && !fp) {
+    const DenseSmemLayout lay = DenseSmemLayout::make(c->num_derivatives + 1, c->ode_dim, kVf[c->vf_id].order, true);
+    if (lay.total * sizeof(double) <= 227 * 1024) {
+      const LoopEntry* e = find_loop({c->vf_id, c->num_derivatives, fact, 0, ts0, 0});
+      if (e != nullptr) return e;
+    }
+  }
   return nullptr;
 }
 

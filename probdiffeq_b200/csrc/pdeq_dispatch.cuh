@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cstdio>
 
+#include "pdeq_loop_dense.cuh"
 #include "pdeq_loop_group.cuh"
 #include "pdeq_loop_thread.cuh"
 
@@ -162,6 +163,38 @@ struct K2Registrar {
                    &k2_workspace<VF, NU, FACT, TS0, FP>, "group"});
   }
 };
+
+// ---------------------------------------------------------------------------------------------------
+// K3 launcher: dense factorisation, CTA per instance.
+// ---------------------------------------------------------------------------------------------------
+template <class VF, int NU, bool TS0>
+cudaError_t k3_launch(const LoopArgs& a, void*, size_t, cudaStream_t stream) {
+  const bool needs_interp = a.fixed_grid == 0 && a.cfg.clip_dt == 0;
+  const DenseSmemLayout lay = DenseSmemLayout::make(NU + 1, a.cfg.ode_dim, VF::order, needs_interp);
+  const size_t smem = lay.total * sizeof(double);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  auto kern = k3_loop_kernel<VF, NU, TS0>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  int per_sm = 0;
+  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K3_THREADS, smem);
+  if (err != cudaSuccess) return err;
+  if (per_sm < 1) per_sm = 1;
+  const long cap = (long)per_sm * device_sm_count();
+  const int grid = (int)std::max(1L, std::min((long)a.prob.num_instances, cap));
+  kern<<<grid, K3_THREADS, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+template <class VF, int NU>
+struct K3Registrar {
+  static size_t ws(const pdeq_config&, int64_t, int32_t) { return 256; }
+  K3Registrar() {
+    register_loop({{VF::id, NU, PDEQ_FACT_DENSE, 0, 1, 0}, &k3_launch<VF, NU, true>, &ws, "dense"});
+    register_loop({{VF::id, NU, PDEQ_FACT_DENSE, 0, 0, 0}, &k3_launch<VF, NU, false>, &ws, "dense"});
+  }
+};
+#define PDEQ_INSTANTIATE_K3(VF, NU) static K3Registrar<VF, NU> _k3_##VF##_##NU;
 
 // filter + fixed-point smoother, ts0 + ts1, for one factorisation
 #define PDEQ_INSTANTIATE_K2(VF, NU, FACT, TAG)                        \

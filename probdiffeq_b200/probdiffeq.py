@@ -474,11 +474,15 @@ class Normal:
 
     @property
     def std_flat(self):
-        """isotropic (..., n); blockdiag (..., n, d)."""
+        """isotropic (..., n); blockdiag and dense (..., n, d)."""
         if self.cholesky_flat is None:
             raise ValueError("Cholesky factors were not requested.")
         s = torch.linalg.vector_norm(self.cholesky_flat, dim=-1)
-        return s if self.factorisation == "isotropic" else s.transpose(-1, -2)
+        if self.factorisation == "isotropic":
+            return s
+        if self.factorisation == "dense":  # rows of the (nd, nd) factor, coefficient-major
+            return s.reshape(self.mean_flat.shape)
+        return s.transpose(-1, -2)
 
     @property
     def std(self):

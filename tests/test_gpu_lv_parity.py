@@ -154,7 +154,7 @@ def test_fixed_grid_matches_oracle(cuda, fact, constraint, solver):
         # sign-normalised factors agree as well (LAPACK reflector convention)
         Ln = L[-1] * np.sign(np.diagonal(L[-1], axis1=-1, axis2=-2))[..., None, :]
         Lon = osol.u_chol[-1] * np.sign(np.diagonal(osol.u_chol[-1], axis1=-1, axis2=-2))[..., None, :]
-        assert _rel(Ln, Lon) < 1e-8
+        assert _rel(Ln, Lon) < max(1e-8, 100 * tol_cov)
         if solver == "solver_dynamic":
             assert _rel(sol.output_scale[b].cpu().numpy(), np.asarray(osol.output_scale)) < tol_cov
         if solver == "solver_mle":
