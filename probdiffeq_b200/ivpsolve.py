@@ -17,6 +17,10 @@ import torch
 from probdiffeq_b200 import _lib
 from probdiffeq_b200 import probdiffeq as _pdq
 
+# Guard against runaway adaptive loops (the reference has none: a collapsing step size loops forever inside
+# `lax.while_loop`). Instances that exceed it are reported with status 2 (PDEQ_STATUS_MAX_ATTEMPTS).
+DEFAULT_MAX_ATTEMPTS = 5_000_000
+
 __all__ = [
     "control_integral",
     "control_proportional_integral",
@@ -194,7 +198,8 @@ def _run_adaptive(prior, solver, error, control, clip_dt, save_at, atol, rtol, d
     return _wrap(prior, bufs, terminal=terminal)
 
 
-def solve_adaptive_terminal_values(solver, error, control=None, clip_dt: bool = True, *, max_attempts: int = 0):
+def solve_adaptive_terminal_values(solver, error, control=None, clip_dt: bool = True, *,
+                                   max_attempts: int = DEFAULT_MAX_ATTEMPTS):
     """reference: _ivpsolve/solvers_via_adaptive_steps.py:16-43."""
 
     def solve(u, /, *, t0, t1, atol, rtol, dt0=0.1, eps=1e-8, damp=0.0, want_cholesky=True, trace_capacity=0):
@@ -207,7 +212,7 @@ def solve_adaptive_terminal_values(solver, error, control=None, clip_dt: bool = 
 
 
 def solve_adaptive_save_at(*, solver, error, control=None, clip_dt: bool = False, warn: bool = True,
-                           max_attempts: int = 0):  # fmt: skip
+                           max_attempts: int = DEFAULT_MAX_ATTEMPTS):  # fmt: skip
     """reference: _ivpsolve/solvers_via_adaptive_steps.py:46-148."""
     if not solver.is_suitable_for_save_at and warn:
         msg = f"Solver {solver} should not be used in solve_adaptive_save_at."
