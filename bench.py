@@ -275,7 +275,10 @@ def run_ours(args) -> None:
             evs.append((e0, e1))
         barrier()
         ms = [a.elapsed_time(b) for a, b in evs]
+        per_step.append([round(x, 3) for x in ms])
         return sum(ms) / len(ms), last
+
+    per_step = []
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -339,6 +342,7 @@ def run_ours(args) -> None:
                         "peak_source": "MEASURED_PEAKS.json" if peaks_path.exists() else "fallback 6.65 TB/s"},
             },
             "clocks": clocks,
+            "ms_steps": {"resident": per_step[0], "e2e": per_step[1]},
         }  # fmt: skip
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -119,7 +119,10 @@ SYMBOLS = {
     "pdeq_fp64_peak_probe": (C.c_int, [C.c_int32, _P(C.c_double), _P(C.c_double), C.c_void_p]),
 }
 
-LIB_PATH = pathlib.Path(__file__).resolve().parent / "lib" / "libprobdiffeq_b200.so"
+import os
+
+# PDEQ_B200_LIB lets experiments point at an alternative build of the same library (never a fallback).
+LIB_PATH = pathlib.Path(os.environ.get("PDEQ_B200_LIB") or pathlib.Path(__file__).resolve().parent / "lib" / "libprobdiffeq_b200.so")
 
 _lib = None
 

@@ -39,6 +39,13 @@ struct LoopArgs {
 };
 
 constexpr int K1_THREADS = 128;
+// Resident CTAs per SM the register allocation is sized for. Measured on the headline kernel (2^20 Lotka-Volterra
+// instances): 2 CTAs (254 registers, no spills) 29.9 ms; 3 CTAs (168 registers, 284 B of spills) 26.3 ms;
+// 4 CTAs (128 registers, 892 B of spills) 29.2 ms. One shared factor (isotropic) fits the 168-register budget;
+// per-dimension factors (block-diagonal) keep 255 registers.
+#ifndef PDEQ_K1_MIN_BLOCKS
+#define PDEQ_K1_MIN_BLOCKS(FACT) ((FACT) == PDEQ_FACT_ISOTROPIC ? 3 : 2)
+#endif
 
 template <int n>
 PDEQ_DI double ipow_small(double x, int k) {
@@ -573,7 +580,7 @@ struct ThreadLoop {
 };
 
 template <class VF, int NU, int FACT, int D, bool TS0>
-__global__ void __launch_bounds__(K1_THREADS) k1_loop_kernel(const __grid_constant__ LoopArgs a) {
+__global__ void __launch_bounds__(K1_THREADS, PDEQ_K1_MIN_BLOCKS(FACT)) k1_loop_kernel(const __grid_constant__ LoopArgs a) {
   extern __shared__ double smem_if[];
   ThreadLoop<VF, NU, FACT, D, TS0>::run(a, smem_if);
 }

@@ -81,7 +81,10 @@ def _run_case(s, params, inits, num, save_at, atol, rtol, *, dt0=0.1, terminal=F
         assert _rel(mean[b][..., 0, :], o_mean[..., 0, :]) < tol_u, (b, _rel(mean[b][..., 0, :], o_mean[..., 0, :]), tol_u)
         # the full state: within 100 x the oracle's sensitivity, or -- for the weakly determined high Taylor
         # coefficients of stiff problems -- within 1 % of the posterior standard deviation the solver itself reports
-        o_std = (osol.u_std[-1] if terminal else osol.u_std) + 0.0 * o_mean
+        o_std = np.asarray(osol.u_std[-1] if terminal else osol.u_std)
+        if o_std.ndim == o_mean.ndim - 1:  # isotropic: one standard deviation per Taylor coefficient
+            o_std = o_std[..., None]
+        o_std = o_std + 0.0 * o_mean
         zscore = np.max(np.abs(mean[b] - o_mean) / np.maximum(o_std, 1e-300))
         assert _rel(mean[b], o_mean) < tol_mean or zscore < 1e-2, (b, _rel(mean[b], o_mean), tol_mean, zscore)
         assert _rel(_cov(chol[b]), _cov(o_chol)) < tol_cov, (b, _rel(_cov(chol[b]), _cov(o_chol)), tol_cov)
