@@ -41,7 +41,8 @@ B_DEFAULT = 1 << 20
 NU, D = 4, 2
 T0, T1, RTOL, ATOL = 0.0, 50.0, 1e-6, 1e-8
 BASE_LV = np.asarray([0.5, 0.05, 0.5, 0.05])
-CPU_SAMPLE = 1 << 15
+CPU_SAMPLE = 1 << 19  # cpu_baseline: ~10-30 s of host work
+REF_SAMPLE = 1 << 17  # --impl reference: instances per step
 
 
 def lv_ensemble(B: int, seed: int):
@@ -139,7 +140,8 @@ def cpu_reference_pass(sample: int, seed: int = 0, threads: int = 0):
     params, u0 = params[:sample], u0[:sample]
     tcoeffs = o_problems.taylor_coefficients_batched("lotka_volterra", params, (u0,), T0, NU)
     c_port.load()
-    threads = threads or c_port.max_threads()
+    # all host threads this process may use -- not OMP_NUM_THREADS, which torchrun pins to 1 for N > 1
+    threads = threads or len(os.sched_getaffinity(0))
 
     def run():
         t = time.perf_counter()
@@ -362,9 +364,11 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--instances", type=int, default=B_DEFAULT, help="instances per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=CPU_SAMPLE)
+    ap.add_argument("--cpu-sample", type=int, default=None, help="instances in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.cpu_sample is None:
+        args.cpu_sample = REF_SAMPLE if args.impl == "reference" else CPU_SAMPLE
     if args.impl == "reference":
         run_reference(args)
     else:

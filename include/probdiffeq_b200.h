@@ -143,6 +143,12 @@ int pdeq_dt0(const pdeq_config* cfg, int64_t num_instances, const double* u0, co
              int64_t params_stride, double t0, double scale, double nugget, double* out,
              void* stream);
 
+/* ivpsolve.dt0_adaptive (probdiffeq/_ivpsolve/stepsize_initialisers.py:24-64, Hairer et al. II.4), first-order
+   ODEs: u0 [B][d] -> out[B]. */
+int pdeq_dt0_adaptive(const pdeq_config* cfg, int64_t num_instances, const double* u0, const double* params,
+                      int64_t params_stride, double t0, double error_contraction_rate, double rtol, double atol,
+                      double* out, void* stream);
+
 /* ivpsolve.solve_adaptive_save_at (probdiffeq/_ivpsolve/solvers_via_adaptive_steps.py:46-148);
    solve_adaptive_terminal_values (:16-43) is the T == 2 case with save_at = {t0, t1}.
    save_at [T] is shared by all instances. dt0 [.] with stride 0 or 1. */

@@ -100,6 +100,11 @@ SYMBOLS = {
         [_P(Config), C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double,
          C.c_void_p, C.c_void_p],
     ),  # fmt: skip
+    "pdeq_dt0_adaptive": (
+        C.c_int,
+        [_P(Config), C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
+         C.c_void_p, C.c_void_p],
+    ),  # fmt: skip
     "pdeq_solve_adaptive_save_at": (
         C.c_int,
         [_P(Config), _P(Problem), C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_int64,

@@ -126,6 +126,61 @@ __global__ void dt0_kernel(int64_t B, int d, const double* __restrict__ u0, cons
 }
 
 // ---------------------------------------------------------------------------------------------------
+// ivpsolve.dt0_adaptive (probdiffeq/_ivpsolve/stepsize_initialisers.py:24-64; Hairer et al., Sec. II.4).
+// First-order ODEs only, as in the reference. The Euler point y1 = y0 + h0 f(y0) is evaluated on the fly.
+// ---------------------------------------------------------------------------------------------------
+template <class VF>
+struct EulerAcc {
+  GlobalAcc base;
+  const double* par;
+  double t0, h0;
+  PDEQ_DI double operator()(int k, int i) const {
+    return base(k, i) + h0 * VF::template component<double>(i, base.d, base, par, t0);
+  }
+};
+
+template <class VF>
+__global__ void dt0_adaptive_kernel(int64_t B, int d, const double* __restrict__ u0,
+                                    const double* __restrict__ params, int64_t params_stride, double t0,
+                                    double rate, double rtol, double atol, double* __restrict__ out) {
+  constexpr int P = VF::num_params > 0 ? VF::num_params : 1;
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  const int lane = threadIdx.x % 32;
+  if (b >= B) return;
+  double par[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) par[k] = VF::num_params > 0 ? params[b * params_stride + k] : 0.0;
+  GlobalAcc acc{u0 + b * (int64_t)d, d};
+  double s0 = 0.0, s1 = 0.0;
+  for (int i = lane; i < d; i += 32) {
+    const double yi = acc(0, i);
+    const double fi = VF::template component<double>(i, d, acc, par, t0);
+    s0 = fma(yi, yi, s0);
+    s1 = fma(fi, fi, s1);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  const double d0 = sqrt(s0), d1 = sqrt(s1);
+  const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+  EulerAcc<VF> acc1{acc, par, t0, h0};
+  double s2 = 0.0;
+  for (int i = lane; i < d; i += 32) {
+    const double f0 = VF::template component<double>(i, d, acc, par, t0);
+    const double f1 = VF::template component<double>(i, d, acc1, par, t0 + h0);
+    const double w = (f1 - f0) / (atol + fabs(acc(0, i)) * rtol);
+    s2 = fma(w, w, s2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  const double d2 = sqrt(s2) / h0;
+  const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 1.0 / (rate + 1.0));
+  if (lane == 0) out[b] = fmin(100.0 * h0, h1);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // loss_lml_terminal_values for the isotropic and block-diagonal factorisations
 // (probdiffeq/_probdiffeq/estimators_and_losses.py:20-50 with IsotropicNormal.logpdf_scalar_flat,
 // ssm_impl_isotropic.py:225-236, and BlockDiagNormal.logpdf_scalar_flat, ssm_impl_blockdiag.py:305-316).
@@ -202,6 +257,26 @@ int pdeq_dt0(const pdeq_config* cfg, int64_t num_instances, const double* u0, co
                                  num_instances, cfg->ode_dim, u0, params, params_stride, t0, scale, nugget, out)));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return api_cuda_fail(e, "dt0");
+  return 0;
+}
+
+int pdeq_dt0_adaptive(const pdeq_config* cfg, int64_t num_instances, const double* u0, const double* params,
+                      int64_t params_stride, double t0, double error_contraction_rate, double rtol, double atol,
+                      double* out, void* stream) {
+  int rc = api_validate(cfg);
+  if (rc != 0) return rc;
+  if (u0 == nullptr || out == nullptr) return api_fail(-22, "u0/out is NULL");
+  if (pdeq_vf_ode_order(cfg->vf_id) != 1)
+    return api_fail(-5, "dt0_adaptive is defined for first-order ODEs only (stepsize_initialisers.py:37-38)");
+  if (pdeq_vf_num_params(cfg->vf_id) > 0 && params == nullptr) return api_fail(-22, "params is NULL");
+  if (num_instances == 0) return 0;
+  const int threads = 128;
+  const int grid = (int)((num_instances * 32 + threads - 1) / threads);
+  PDEQ_VF_SWITCH(cfg->vf_id, (dt0_adaptive_kernel<VF><<<grid, threads, 0, (cudaStream_t)stream>>>(
+                                 num_instances, cfg->ode_dim, u0, params, params_stride, t0,
+                                 error_contraction_rate, rtol, atol, out)));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return api_cuda_fail(e, "dt0_adaptive");
   return 0;
 }
 

@@ -25,6 +25,7 @@ __all__ = [
     "control_integral",
     "control_proportional_integral",
     "dt0",
+    "dt0_adaptive",
     "solve_adaptive_save_at",
     "solve_adaptive_terminal_values",
     "solve_fixed_grid",
@@ -187,13 +188,14 @@ def _run_adaptive(prior, solver, error, control, clip_dt, save_at, atol, rtol, d
         raise ValueError("dt0 must be a scalar or have one entry per ensemble member.")
     pr, keep = _problem(prior, solver.constraint.ode)
     so, bufs = _alloc_solution(prior, T, want_chol, trace_capacity)
-    ws, nbytes = _workspace(cfg, B, T, prior.tcoeffs.device)
-    rc = _lib.load().pdeq_solve_adaptive_save_at(
-        C.byref(cfg), C.byref(pr), _pdq._ptr(grid), T, float(atol), float(rtol), _pdq._ptr(dt0_t),
-        0 if dt0_t.shape[0] == 1 else 1, float(eps), float(damp), C.byref(so), _pdq._ptr(ws), nbytes,
-        _pdq._stream(),
-    )  # fmt: skip
-    _lib.check(rc, "pdeq_solve_adaptive_save_at")
+    if B > 0:  # an empty ensemble returns empty arrays (there is nothing to launch)
+        ws, nbytes = _workspace(cfg, B, T, prior.tcoeffs.device)
+        rc = _lib.load().pdeq_solve_adaptive_save_at(
+            C.byref(cfg), C.byref(pr), _pdq._ptr(grid), T, float(atol), float(rtol), _pdq._ptr(dt0_t),
+            0 if dt0_t.shape[0] == 1 else 1, float(eps), float(damp), C.byref(so), _pdq._ptr(ws), nbytes,
+            _pdq._stream(),
+        )  # fmt: skip
+        _lib.check(rc, "pdeq_solve_adaptive_save_at")
     del keep
     return _wrap(prior, bufs, terminal=terminal)
 
@@ -246,12 +248,13 @@ def solve_fixed_grid(*, solver):
         T = g.shape[0]
         pr, keep = _problem(prior, solver.constraint.ode)
         so, bufs = _alloc_solution(prior, T, want_cholesky)
-        ws, nbytes = _workspace(cfg, B, T, prior.tcoeffs.device)
-        rc = _lib.load().pdeq_solve_fixed_grid(
-            C.byref(cfg), C.byref(pr), _pdq._ptr(g), T, float(damp), C.byref(so), _pdq._ptr(ws), nbytes,
-            _pdq._stream(),
-        )  # fmt: skip
-        _lib.check(rc, "pdeq_solve_fixed_grid")
+        if B > 0:
+            ws, nbytes = _workspace(cfg, B, T, prior.tcoeffs.device)
+            rc = _lib.load().pdeq_solve_fixed_grid(
+                C.byref(cfg), C.byref(pr), _pdq._ptr(g), T, float(damp), C.byref(so), _pdq._ptr(ws), nbytes,
+                _pdq._stream(),
+            )  # fmt: skip
+            _lib.check(rc, "pdeq_solve_fixed_grid")
         del keep
         return _wrap(prior, bufs, terminal=False)
 
@@ -275,4 +278,24 @@ def dt0(vf, initial_values, /, *, t=0.0, scale=0.01, nugget=1e-5):
         _pdq._ptr(out), _pdq._stream(),
     )  # fmt: skip
     _lib.check(rc, "pdeq_dt0")
+    return out[0] if unbatched else out
+
+
+def dt0_adaptive(vf, initial_values, /, t0, *, error_contraction_rate, rtol, atol):
+    """Initial step size from the tolerances (reference: _ivpsolve/stepsize_initialisers.py:24-64)."""
+    if len(initial_values) > 1:
+        raise ValueError("dt0_adaptive is defined for first-order ODEs only.")
+    u0 = _pdq._as_device_f64(initial_values[0])
+    unbatched = u0.ndim == 1
+    if unbatched:
+        u0 = u0.reshape(1, -1)
+    B, d = u0.shape
+    cfg = _pdq._make_config(fact="isotropic", nu=vf.order, d=d, vf=vf)
+    params, stride = vf.params_on_device(B)
+    out = torch.empty((B,), dtype=torch.float64, device=u0.device)
+    rc = _lib.load().pdeq_dt0_adaptive(
+        C.byref(cfg), B, _pdq._ptr(u0), _pdq._ptr(params), stride, float(t0), float(error_contraction_rate),
+        float(rtol), float(atol), _pdq._ptr(out), _pdq._stream(),
+    )  # fmt: skip
+    _lib.check(rc, "pdeq_dt0_adaptive")
     return out[0] if unbatched else out

@@ -175,8 +175,8 @@ def jetexpand_ode_padded_scan(*, num: int):
         inits = [u.reshape(1, -1) if u.ndim == 1 else u for u in inits]
         u0 = torch.stack(inits, dim=1).contiguous()  # (B, order, d)
         B, q, d = u0.shape
-        if num == 0:
-            out = u0
+        if num == 0 or B == 0:
+            out = u0 if num == 0 else torch.empty((0, q + num, d), dtype=torch.float64, device=u0.device)
         else:
             n = q + num
             cfg = _make_config(fact="isotropic", nu=n - 1, d=d, vf=vf)
