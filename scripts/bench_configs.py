@@ -15,8 +15,7 @@ sys.path.insert(0, ".")
 from oracle import problems as o_problems  # initial values only (constants of the benchmark problems)
 from probdiffeq_b200 import ivpsolve, probdiffeq
 
-BUDGET = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
-ONLY = sys.argv[2].split(",") if len(sys.argv) > 2 else None
+BUDGET, ONLY = 60.0, None
 
 
 def timed(fn):
@@ -139,6 +138,8 @@ CONFIGS = {
 }
 
 if __name__ == "__main__":
+    BUDGET = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+    ONLY = sys.argv[2].split(",") if len(sys.argv) > 2 else None
     torch.cuda.set_device(0)
     for name, (make, sizes) in CONFIGS.items():
         if ONLY and not any(name.startswith(o) for o in ONLY):

@@ -76,7 +76,7 @@ def product_build(s, params):
     from probdiffeq_b200 import ivpsolve as p_ivp
     from probdiffeq_b200 import probdiffeq as p_pdq
 
-    vf = p_pdq.ode(s["vf"], params=params if params is not None and np.size(params) else None)
+    vf = p_pdq.ode(s["vf"], params=params)
     return (p_pdq, p_ivp, vf, *_build(p_pdq, p_ivp, s, vf))
 
 
