@@ -88,7 +88,7 @@ template <class VF, int NU, int FACT, bool TS0, bool FP>
 cudaError_t k2_plan(const pdeq_config& cfg, int64_t B, int32_t T, bool needs_interp, K2Plan* plan) {
   using GL = GroupLoop<VF, NU, FACT, TS0, FP, false>;
   const int d = cfg.ode_dim;
-  const size_t per_group = ((needs_interp ? 2 : 1) * (size_t)GL::NF * d + (size_t)VF::order * d + 32) * sizeof(double);
+  const size_t per_group = GL::smem_doubles_per_group(d, needs_interp) * sizeof(double);
   plan->cta = d > 32;
   if (plan->cta) {
     using GC = GroupLoop<VF, NU, FACT, TS0, FP, true>;
@@ -102,7 +102,8 @@ cudaError_t k2_plan(const pdeq_config& cfg, int64_t B, int32_t T, bool needs_int
   }
   plan->smem_bytes = per_group * plan->groups_per_cta;
   if (plan->smem_bytes > 227 * 1024) return cudaErrorInvalidValue;
-  plan->ring_bytes_per_group = FP ? (size_t)T * GL::NFC * d * sizeof(double) : 0;
+  // per resident group: the ring of per-checkpoint conditionals plus the interp_from slot (smoother only)
+  plan->ring_bytes_per_group = FP ? ((size_t)T * GL::NFC + GL::NF) * d * sizeof(double) : 0;
   int per_sm = 0;
   cudaError_t err;
   if (plan->cta) {
@@ -143,11 +144,15 @@ cudaError_t k2_launch(const LoopArgs& a, void* workspace, size_t workspace_bytes
   GroupLaunchInfo info;
   info.groups_per_cta = plan.groups_per_cta;
   info.cond_ring = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
-  if (FP) {  // never launch more groups than the ring has room for
+  info.if_scratch = nullptr;
+  if (FP) {  // never launch more groups than the scratch has room for
+    using GL = GroupLoop<VF, NU, FACT, TS0, FP, false>;
     const size_t room = (workspace_bytes - 256) / plan.ring_bytes_per_group;
     const int max_grid = (int)(room / plan.groups_per_cta);
     if (max_grid < 1) return cudaErrorMemoryAllocation;
     plan.grid = std::min(plan.grid, max_grid);
+    const size_t groups = (size_t)plan.grid * plan.groups_per_cta;
+    info.if_scratch = info.cond_ring + groups * (size_t)a.T * GL::NFC * a.cfg.ode_dim;
   }
   if (plan.cta)
     k2_loop_kernel<VF, NU, FACT, TS0, FP, true><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);

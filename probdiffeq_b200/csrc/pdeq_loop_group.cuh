@@ -200,8 +200,16 @@ struct GroupLoop {
     }
   }
 
+  // For the smoother the interp_from copy of the state (written on every accepted step, read only when a checkpoint
+  // is overstepped) lives in an L2-resident global scratch slot instead of shared memory: it halves the shared
+  // memory per instance and doubles the number of resident warps (4 -> 8 per SM for Pleiades).
+  static constexpr bool IF_GLOBAL = FP;
+  PDEQ_HDI static constexpr size_t smem_doubles_per_group(int d, bool needs_interp) {
+    return (size_t)((needs_interp && !IF_GLOBAL) ? 2 : 1) * NF * d + (size_t)q * d + 32;
+  }
+
   PDEQ_DI static void run(const LoopArgs& a, double* __restrict__ smem, double* __restrict__ cond_ring,
-                          int groups_per_cta) {
+                          double* __restrict__ if_scratch, int groups_per_cta) {
     const pdeq_config& cfg = a.cfg;
     const double(*__restrict__ A)[PDEQ_MAX_COEFFS] = cfg.sys_a;
     const double(*__restrict__ Q)[PDEQ_MAX_COEFFS] = cfg.sys_q;
@@ -224,14 +232,15 @@ struct GroupLoop {
     const int nrounds = (d + g.size - 1) / g.size;  // <= MAXR, enforced by the launcher
 
     // shared memory of this group: [state_from | interp_from | exchange u | reduction scratch]
-    const int per_group = (needs_interp ? 2 : 1) * NF * d + q * d + 32;
+    const size_t per_group = smem_doubles_per_group(d, needs_interp);
+    const size_t group_slot = (size_t)blockIdx.x * groups_per_cta + gidx;
     double* base = smem + (size_t)gidx * per_group;
     double* st_from = base;
-    double* st_if = base + NF * d;
-    double* exch = base + (needs_interp ? 2 : 1) * NF * d;
+    double* st_if = IF_GLOBAL ? if_scratch + group_slot * (size_t)NF * d : base + NF * d;
+    double* exch = base + ((needs_interp && !IF_GLOBAL) ? 2 : 1) * NF * d;
     g.red = exch + q * d;
     // global scratch ring for the per-checkpoint conditionals of the instance this group is working on
-    double* ring = FP ? cond_ring + ((size_t)blockIdx.x * groups_per_cta + gidx) * (size_t)T * NFC * d : nullptr;
+    double* ring = FP ? cond_ring + group_slot * (size_t)T * NFC * d : nullptr;
 
     double params[P];
     double t = 0.0, dt = 0.0, ctrl_lprev = 0.0, ndata = 0.0, t_next = 0.0, t_if = 0.0;
@@ -627,6 +636,7 @@ struct GroupLoop {
 
 struct GroupLaunchInfo {
   double* cond_ring;
+  double* if_scratch;
   int groups_per_cta;
 };
 
@@ -634,7 +644,7 @@ template <class VF, int NU, int FACT, bool TS0, bool FP, bool CTA>
 __global__ void __launch_bounds__(CTA ? K2_CTA_THREADS : 128)
     k2_loop_kernel(const __grid_constant__ LoopArgs a, const __grid_constant__ GroupLaunchInfo info) {
   extern __shared__ double smem_k2[];
-  GroupLoop<VF, NU, FACT, TS0, FP, CTA>::run(a, smem_k2, info.cond_ring, info.groups_per_cta);
+  GroupLoop<VF, NU, FACT, TS0, FP, CTA>::run(a, smem_k2, info.cond_ring, info.if_scratch, info.groups_per_cta);
 }
 
 }  // namespace pdeq
