@@ -40,8 +40,10 @@ enum { PDEQ_FACT_ISOTROPIC = 0, PDEQ_FACT_BLOCKDIAG = 1, PDEQ_FACT_DENSE = 2 };
 enum { PDEQ_CONSTRAINT_TS0 = 0, PDEQ_CONSTRAINT_TS1 = 1 };
 /* solver / solver_mle / solver_dynamic: probdiffeq/_probdiffeq/solvers.py:636,318,483 */
 enum { PDEQ_SOLVER_PLAIN = 0, PDEQ_SOLVER_MLE = 1, PDEQ_SOLVER_DYNAMIC = 2 };
-/* strategy_filter / strategy_smoother_fixedpoint: probdiffeq/_probdiffeq/estimators_and_losses.py:347,473 */
-enum { PDEQ_STRATEGY_FILTER = 0, PDEQ_STRATEGY_FIXEDPOINT = 1 };
+/* strategy_filter / strategy_smoother_fixedpoint / strategy_smoother_fixedinterval:
+   probdiffeq/_probdiffeq/estimators_and_losses.py:347,473,594. The fixed-interval smoother is accepted by
+   pdeq_solve_fixed_grid only (the reference: "use this strategy for fixed steps"). */
+enum { PDEQ_STRATEGY_FILTER = 0, PDEQ_STRATEGY_FIXEDPOINT = 1, PDEQ_STRATEGY_FIXEDINTERVAL = 2 };
 /* error_residual_std / error_state_std: probdiffeq/_probdiffeq/solvers.py:850,999 */
 enum { PDEQ_ERROR_RESIDUAL_STD = 0, PDEQ_ERROR_STATE_STD = 1 };
 /* error_norm_scale_then_rms / error_norm_rms_then_scale: probdiffeq/_probdiffeq/solvers.py:770,794 */

@@ -619,7 +619,18 @@ struct GroupLoop {
             if (FP) cond_store(st_if + F_G * d, d, j, pcarried);
           }
           st_store(st_from, d, j, pm[r], pL[r]);
-          if (FP) cond_store(st_from + F_G * d, d, j, pcond);
+          if (FP) {
+            if (!adaptive) {
+              // fixed grid: every grid point is a checkpoint. Store the backward conditional of this step and
+              // restart from the identity -- the fixed-interval smoother (estimators_and_losses.py:612-620).
+              cond_store(ring + (size_t)ck * NFC * d, d, j, pcond);
+              BlockCond<n> ident;
+              cond_identity<n>(ident);
+              cond_store(st_from + F_G * d, d, j, ident);
+            } else {
+              cond_store(st_from + F_G * d, d, j, pcond);
+            }
+          }
           if (cfg.solver == PDEQ_SOLVER_DYNAMIC) st_from[F_SIG * d + j] = psig[r];
           st_from[F_RUN * d + j] = prun[r];
           if (!adaptive) emit(a, b, ck, d, j, t_new, pm[r], pL[r], st_from[F_SIG * d + j], nsteps + 1);

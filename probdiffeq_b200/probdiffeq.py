@@ -47,6 +47,7 @@ __all__ = [
     "state_space_model_dense",
     "state_space_model_isotropic",
     "strategy_filter",
+    "strategy_smoother_fixedinterval",
     "strategy_smoother_fixedpoint",
 ]
 
@@ -334,6 +335,17 @@ class strategy_smoother_fixedpoint:
 
     def __repr__(self):
         return "strategy_smoother_fixedpoint()"
+
+
+class strategy_smoother_fixedinterval:
+    """reference: estimators_and_losses.py:594-717. Accelerated for `solve_fixed_grid` (its intended use)."""
+
+    kind = "fixedinterval"
+    is_suitable_for_save_at = False
+    is_suitable_for_save_every_step = True
+
+    def __repr__(self):
+        return "strategy_smoother_fixedinterval()"
 
 
 class _Solver:

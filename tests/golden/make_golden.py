@@ -1,0 +1,65 @@
+"""Generate tests/golden/oracle_golden.npz from the oracle.
+
+The reference holds no golden outputs of the step loop (its only fixtures are pickled float32 jax.Arrays for
+unrelated problems) and cannot be run here (no JAX), so these vectors are produced by the ORACLE, after it has been
+pinned by the reference's known-answer tests and identities (tests/test_oracle_kats.py). They freeze the oracle:
+a CPU test re-derives them, and a GPU test compares the CUDA path with them.
+
+    python tests/golden/make_golden.py
+"""
+
+import pathlib
+import sys
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import pdeq_test_helpers as H  # noqa: E402
+from oracle import probdiffeq as o_pdq  # noqa: E402
+
+
+def build():
+    out = {}
+    # BASELINE config 1: the reference's own single IVP (benchmarks/A0 wiring with nu = 4)
+    vf = o_pdq.ode("lotka_volterra")
+    tc, _ = o_pdq.jetexpand_ode_padded_scan(num=4)(vf, (np.asarray([20.0, 20.0]),), t=0.0)
+    sol, trace = H.oracle_solve_save_at(H.spec(), tc, H.BASE_LV, np.asarray([0.0, 50.0]), 1e-8, 1e-6)
+    out["config1_tcoeffs"] = tc
+    out["config1_mean"] = sol.u_mean[-1]
+    out["config1_chol"] = sol.u_chol[-1]
+    out["config1_num_steps"] = np.asarray(sol.num_steps[-1])
+    out["config1_num_attempts"] = np.asarray(len(trace))
+    # a fixed-grid solve (1e-10 parity class) for each solver on a small randomised ensemble
+    params, u0 = H.lv_ensemble(3, seed=42)
+    grid = np.linspace(0.0, 1.0, 11)
+    out["fixed_params"], out["fixed_u0"], out["fixed_grid"] = params, u0, grid
+    for fact in ("isotropic", "blockdiag"):
+        for solver in ("solver", "solver_mle"):
+            means, chols = [], []
+            for b in range(3):
+                tcb = o_pdq.ode("lotka_volterra", params[b]).taylor_coefficients((u0[b],), 0.0, 4)
+                s = H.oracle_solve_fixed(H.spec(fact=fact, solver=solver), tcb, params[b], grid)
+                means.append(s.u_mean)
+                chols.append(s.u_chol)
+            out[f"fixed_{fact}_{solver}_mean"] = np.stack(means)
+            out[f"fixed_{fact}_{solver}_chol"] = np.stack(chols)
+    # fixed-point smoother on a save_at grid (smoothed marginals)
+    save_at = np.linspace(0.0, 2.0, 6)
+    s = H.spec(fact="blockdiag", strategy="fixedpoint", solver="solver", error="residual_std", control="i", clip_dt=False)
+    tcb = o_pdq.ode("lotka_volterra", params[0]).taylor_coefficients((u0[0],), 0.0, 4)
+    sol, trace = H.oracle_solve_save_at(s, tcb, params[0], save_at, 1e-6, 1e-4)
+    out["smoother_save_at"] = save_at
+    out["smoother_mean"] = sol.u_mean
+    out["smoother_chol"] = sol.u_chol
+    out["smoother_num_steps"] = np.asarray(sol.num_steps)
+    return out
+
+
+if __name__ == "__main__":
+    data = build()
+    path = pathlib.Path(__file__).with_name("oracle_golden.npz")
+    np.savez_compressed(path, **data)
+    print(path, {k: v.shape for k, v in data.items()})

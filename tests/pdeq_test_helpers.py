@@ -30,7 +30,8 @@ def spec(**kw):
 def _build(mod_pdq, mod_ivp, s, vf):
     ssm = getattr(mod_pdq, "state_space_model_" + s["fact"])()
     cons = getattr(ssm, "constraint_ode_" + s["constraint"])(vf)
-    strat = mod_pdq.strategy_filter() if s["strategy"] == "filter" else mod_pdq.strategy_smoother_fixedpoint()
+    strat = {"filter": mod_pdq.strategy_filter, "fixedpoint": mod_pdq.strategy_smoother_fixedpoint,
+             "fixedinterval": mod_pdq.strategy_smoother_fixedinterval}[s["strategy"]]()
     solver = getattr(mod_pdq, s["solver"])(strategy=strat, constraint=cons)
     norm = getattr(mod_pdq, "error_norm_" + s["error_norm"])()
     if s["error"] == "state_std":

@@ -212,3 +212,39 @@ def test_vanderpol_second_order_ts1(cuda, fact):
     du0 = np.zeros((B, 1))
     params = np.full((B, 1), 1e3)
     _run_case(s, params, (u0, du0), 3, np.asarray([0.0, 0.5]), 1e-8, 1e-5, dt0=1e-4, terminal=True)
+
+
+@pytest.mark.parametrize("fact", ["blockdiag", "isotropic"])
+@pytest.mark.parametrize("solver", ["solver", "solver_mle"])
+def test_fixedinterval_smoother_on_a_fixed_grid(cuda, fact, solver):
+    """solve_fixed_grid + strategy_smoother_fixedinterval (the reference's recommendation for parameter estimation,
+    README.md:200): smoothed marginals at every grid point, 1e-10 class (data-independent covariances)."""
+    import torch
+
+    s = H.spec(fact=fact, strategy="fixedinterval", solver=solver)
+    B = 4
+    params, u0 = H.lv_ensemble(B, seed=31)
+    p_pdq, p_ivp, vf, ssm, slv, _e, _c = H.product_build(s, params)
+    tcoeffs, _ = p_pdq.jetexpand_ode_padded_scan(num=4)(vf, (u0,), t=0.0)
+    grid = np.linspace(0.0, 1.0, 26)
+    sol = p_ivp.solve_fixed_grid(solver=slv)(ssm.prior_wiener_integrated(tcoeffs), grid=grid)
+    torch.cuda.synchronize()
+    assert int(sol.status.abs().max()) == 0
+    tc = tcoeffs.cpu().numpy()
+    for b in range(B):
+        osol = H.oracle_solve_fixed(s, tc[b], params[b], grid)
+        assert _rel(sol.u.mean_flat[b].cpu().numpy(), osol.u_mean) < 1e-9
+        L = sol.u.cholesky_flat[b].cpu().numpy()
+        for k in range(len(grid)):
+            assert _rel(_cov(L[k]), _cov(osol.u_chol[k])) < 1e-8, k
+
+
+def test_fixedinterval_smoother_is_rejected_for_save_at(cuda):
+    s = H.spec(fact="blockdiag", strategy="fixedinterval", clip_dt=False)
+    params, u0 = H.lv_ensemble(2, seed=32)
+    p_pdq, p_ivp, vf, ssm, solver, err, ctrl = H.product_build(s, params)
+    tcoeffs, _ = p_pdq.jetexpand_ode_padded_scan(num=4)(vf, (u0,), t=0.0)
+    with pytest.warns(UserWarning):
+        solve = p_ivp.solve_adaptive_save_at(solver=solver, error=err, control=ctrl)
+    with pytest.raises(ValueError, match="fixed-interval"):
+        solve(ssm.prior_wiener_integrated(tcoeffs), save_at=np.linspace(0, 1, 3), atol=1e-4, rtol=1e-4)
