@@ -42,8 +42,19 @@ enum { PDEQ_CONSTRAINT_TS0 = 0, PDEQ_CONSTRAINT_TS1 = 1 };
 enum { PDEQ_SOLVER_PLAIN = 0, PDEQ_SOLVER_MLE = 1, PDEQ_SOLVER_DYNAMIC = 2 };
 /* strategy_filter / strategy_smoother_fixedpoint / strategy_smoother_fixedinterval:
    probdiffeq/_probdiffeq/estimators_and_losses.py:347,473,594. The fixed-interval smoother is accepted by
-   pdeq_solve_fixed_grid only (the reference: "use this strategy for fixed steps"). */
-enum { PDEQ_STRATEGY_FILTER = 0, PDEQ_STRATEGY_FIXEDPOINT = 1, PDEQ_STRATEGY_FIXEDINTERVAL = 2 };
+   pdeq_solve_fixed_grid only (the reference: "use this strategy for fixed steps").
+   PDEQ_STRATEGY_FIXEDINTERVAL reproduces the reference literally: Smoother.finalize (:437-470) marginalises the
+   last grid state through its own backward conditional before the backward recursion, because solve_fixed_grid
+   (_ivpsolve/solvers_via_fixed_steps.py:30-32) hands it the last grid state as the "overstepped" state; the
+   returned marginals are therefore one interval late at the terminal grid point.
+   PDEQ_STRATEGY_FIXEDINTERVAL_ALIGNED starts the recursion from the filtering marginal at the last grid point
+   (the textbook Rauch-Tung-Striebel pass; what the reference's save-every-step flow yields when it oversteps). */
+enum {
+  PDEQ_STRATEGY_FILTER = 0,
+  PDEQ_STRATEGY_FIXEDPOINT = 1,
+  PDEQ_STRATEGY_FIXEDINTERVAL = 2,
+  PDEQ_STRATEGY_FIXEDINTERVAL_ALIGNED = 3
+};
 /* error_residual_std / error_state_std: probdiffeq/_probdiffeq/solvers.py:850,999 */
 enum { PDEQ_ERROR_RESIDUAL_STD = 0, PDEQ_ERROR_STATE_STD = 1 };
 /* error_norm_scale_then_rms / error_norm_rms_then_scale: probdiffeq/_probdiffeq/solvers.py:770,794 */

@@ -166,8 +166,15 @@ def solve_adaptive_terminal_values(solver, error, control=None, clip_dt=True, tr
     return solve
 
 
-def solve_fixed_grid(*, solver):
-    """_ivpsolve/solvers_via_fixed_steps.py:11-34."""
+def solve_fixed_grid(*, solver, terminal="reference"):
+    """_ivpsolve/solvers_via_fixed_steps.py:11-34.
+
+    `terminal="reference"` is the literal restatement: the last grid state is passed on as `solution1`, which
+    `Smoother.finalize` (estimators_and_losses.py:453-454) treats as an overstepped state and marginalises through
+    its own backward conditional -- for smoothers the marginals then come out one interval late at the terminal
+    grid point. `terminal="aligned"` passes the last state with an identity conditional instead (what the
+    overstepping save-every-step flow of util/test_util.py:10-66 amounts to), giving the Rauch-Tung-Striebel pass.
+    """
     if not solver.is_suitable_for_save_every_step:
         warnings.warn(f"Solver {solver} should not be used in solve_fixed_grid.", stacklevel=1)
 
@@ -179,7 +186,15 @@ def solve_fixed_grid(*, solver):
         for dt in np.diff(grid):
             state = solver.step(state=state, dt=dt, damp=damp)
             result.append(state)
-        return solver.userfriendly_output(solution0=state0, solution=result, solution1=state)
+        last = state
+        if terminal == "aligned" and hasattr(state.solution_full, "conditional"):
+            import copy
+
+            full = state.solution_full
+            ident = full.marginal.alg.identity_conditional(full.marginal)
+            last = copy.copy(state)
+            last.solution_full = type(full)(full.marginal, ident, full.reverse)
+        return solver.userfriendly_output(solution0=state0, solution=result, solution1=last)
 
     return solve
 

@@ -14,7 +14,7 @@ MAX_COEFFS = 8
 FACT = {"isotropic": 0, "blockdiag": 1, "dense": 2}
 CONSTRAINT = {"ts0": 0, "ts1": 1}
 SOLVER = {"solver": 0, "solver_mle": 1, "solver_dynamic": 2}
-STRATEGY = {"filter": 0, "fixedpoint": 1, "fixedinterval": 2}
+STRATEGY = {"filter": 0, "fixedpoint": 1, "fixedinterval": 2, "fixedinterval_aligned": 3}
 ERROR = {"residual_std": 0, "state_std": 1}
 NORM = {"scale_then_rms": 0, "rms_then_scale": 1}
 CONTROL = {"integral": 0, "proportional_integral": 1}

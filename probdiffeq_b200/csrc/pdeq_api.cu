@@ -69,7 +69,7 @@ static int validate(const pdeq_config* c) {
   if (c->factorisation < 0 || c->factorisation > 2) return fail(-5, "bad factorisation %d", c->factorisation);
   if (c->constraint < 0 || c->constraint > 1) return fail(-5, "bad constraint %d", c->constraint);
   if (c->solver < 0 || c->solver > 2) return fail(-5, "bad solver %d", c->solver);
-  if (c->strategy < 0 || c->strategy > 2) return fail(-5, "bad strategy %d", c->strategy);
+  if (c->strategy < 0 || c->strategy > 3) return fail(-5, "bad strategy %d", c->strategy);
   if (c->error < 0 || c->error > 1) return fail(-5, "bad error estimator %d", c->error);
   if (c->error_norm < 0 || c->error_norm > 1) return fail(-5, "bad error norm %d", c->error_norm);
   if (c->control < 0 || c->control > 1) return fail(-5, "bad control %d", c->control);
@@ -205,7 +205,7 @@ int pdeq_solve_adaptive_save_at(const pdeq_config* cfg, const pdeq_problem* prob
   int rc = check_common(cfg, problem, solution, num_checkpoints, workspace, workspace_bytes);
   if (rc != 0) return rc;
   if (save_at == nullptr || dt0 == nullptr) return fail(-25, "save_at/dt0 is NULL");
-  if (cfg->strategy == PDEQ_STRATEGY_FIXEDINTERVAL)
+  if (cfg->strategy == PDEQ_STRATEGY_FIXEDINTERVAL || cfg->strategy == PDEQ_STRATEGY_FIXEDINTERVAL_ALIGNED)
     return fail(-10, "the fixed-interval smoother is for solve_fixed_grid; use the fixed-point smoother with save_at "
                      "(the reference warns likewise, solvers_via_adaptive_steps.py:81-85)");
   return run_loop(cfg, problem, solution, save_at, num_checkpoints, 0, atol, rtol, dt0, dt0_stride, eps, damp,

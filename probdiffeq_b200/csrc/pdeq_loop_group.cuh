@@ -382,7 +382,12 @@ struct GroupLoop {
               // the last checkpoint, then run the backward recursion over the stored conditionals.
               double mo[n], Lo[n][n];
               BlockCond<n> c;
-              cond_load(st_from + F_G * d, d, j, c);
+              // On a fixed grid the carried conditional is the identity (the aligned pass); the reference hands
+              // finalize the last grid state itself, whose conditional is the one stored for the last interval.
+              if (!adaptive && cfg.strategy == PDEQ_STRATEGY_FIXEDINTERVAL && T > 1)
+                cond_load(ring + (size_t)(T - 1) * NFC * d, d, j, c);
+              else
+                cond_load(st_from + F_G * d, d, j, c);
               cond_marginalise<n>(c, m, L, mo, Lo);
               for (int k = T - 1; k >= 0; --k) {
                 const long bt = b * T + k;

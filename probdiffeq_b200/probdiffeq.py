@@ -338,14 +338,25 @@ class strategy_smoother_fixedpoint:
 
 
 class strategy_smoother_fixedinterval:
-    """reference: estimators_and_losses.py:594-717. Accelerated for `solve_fixed_grid` (its intended use)."""
+    """reference: estimators_and_losses.py:594-717. Accelerated for `solve_fixed_grid` (its intended use).
 
-    kind = "fixedinterval"
+    `terminal="reference"` (default) reproduces the reference literally: `Smoother.finalize` (:437-470) treats the
+    last grid state as an overstepped state and marginalises it through its own backward conditional first, so on
+    a fixed grid the returned marginals are one interval late at the terminal point. `terminal="aligned"` starts
+    the backward recursion from the filtering marginal at the last grid point (the Rauch-Tung-Striebel pass).
+    """
+
     is_suitable_for_save_at = False
     is_suitable_for_save_every_step = True
 
+    def __init__(self, *, terminal="reference"):
+        if terminal not in ("reference", "aligned"):
+            raise ValueError(f"terminal must be 'reference' or 'aligned', got {terminal!r}")
+        self.terminal = terminal
+        self.kind = "fixedinterval" if terminal == "reference" else "fixedinterval_aligned"
+
     def __repr__(self):
-        return "strategy_smoother_fixedinterval()"
+        return f"strategy_smoother_fixedinterval(terminal={self.terminal!r})"
 
 
 class _Solver:

@@ -30,8 +30,12 @@ def spec(**kw):
 def _build(mod_pdq, mod_ivp, s, vf):
     ssm = getattr(mod_pdq, "state_space_model_" + s["fact"])()
     cons = getattr(ssm, "constraint_ode_" + s["constraint"])(vf)
-    strat = {"filter": mod_pdq.strategy_filter, "fixedpoint": mod_pdq.strategy_smoother_fixedpoint,
-             "fixedinterval": mod_pdq.strategy_smoother_fixedinterval}[s["strategy"]]()
+    if s["strategy"] == "fixedinterval_aligned":  # product-only option; the oracle takes it in solve_fixed_grid
+        aligned = {"terminal": "aligned"} if mod_pdq is not o_pdq else {}
+        strat = mod_pdq.strategy_smoother_fixedinterval(**aligned)
+    else:
+        strat = {"filter": mod_pdq.strategy_filter, "fixedpoint": mod_pdq.strategy_smoother_fixedpoint,
+                 "fixedinterval": mod_pdq.strategy_smoother_fixedinterval}[s["strategy"]]()
     solver = getattr(mod_pdq, s["solver"])(strategy=strat, constraint=cons)
     norm = getattr(mod_pdq, "error_norm_" + s["error_norm"])()
     if s["error"] == "state_std":
@@ -70,7 +74,8 @@ def oracle_solve_fixed(s, tcoeffs, params, grid, output_scale=None):
 
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        return o_ivp.solve_fixed_grid(solver=solver)(prior, grid=grid)
+        terminal = "aligned" if s["strategy"] == "fixedinterval_aligned" else "reference"
+        return o_ivp.solve_fixed_grid(solver=solver, terminal=terminal)(prior, grid=grid)
 
 
 def product_build(s, params):

@@ -209,6 +209,34 @@ def test_fixedpoint_smoother_equals_fixedinterval_smoother_on_the_same_grid():
         assert np.allclose(fp.u_std, every.u_std, rtol=1e-7, atol=1e-14)
 
 
+def test_fixedinterval_smoother_on_a_fixed_grid_reference_vs_aligned():
+    """solve_fixed_grid hands Smoother.finalize the last grid state as `solution1` (solvers_via_fixed_steps.py:30-32),
+    and finalize marginalises it through its own conditional (estimators_and_losses.py:453-454). Literally restated,
+    the last entry is the smoothed marginal one grid point earlier; with an identity conditional ("aligned") the
+    pass ends in the filtering marginal and equals a hand-rolled Rauch-Tung-Striebel recursion."""
+    for kind in ("isotropic", "blockdiag", "dense"):
+        prior, slv_fi, _ = _setup(kind, "ts0", "solver", pdq.strategy_smoother_fixedinterval, "error_residual_std", num=2)
+        _, slv_f, _ = _setup(kind, "ts0", "solver", pdq.strategy_filter, "error_residual_std", num=2)
+        grid = np.linspace(0.0, 1.0, 11)
+        lit = ivpsolve.solve_fixed_grid(solver=slv_fi)(prior, grid=grid)
+        ali = ivpsolve.solve_fixed_grid(solver=slv_fi, terminal="aligned")(prior, grid=grid)
+        filt = ivpsolve.solve_fixed_grid(solver=slv_f)(prior, grid=grid)
+        assert np.allclose(ali.u_mean[-1], filt.u_mean[-1], rtol=1e-9, atol=1e-12)
+        assert np.allclose(ali.u_std[-1], filt.u_std[-1], rtol=1e-7, atol=1e-14)
+        # the literal terminal entry is the aligned entry one grid point earlier
+        assert np.allclose(lit.u_mean[-1], ali.u_mean[-2], rtol=1e-9, atol=1e-12)
+        assert not np.allclose(lit.u_mean[-1], ali.u_mean[-1], rtol=1e-3)
+        # hand-rolled backward recursion over the stored conditionals
+        conds = lit.solution_full.posterior.conditional  # one per step, t_k -> t_{k-1}
+        rv = filt.u[-1] if isinstance(filt.u, list) else None
+        if rv is not None:
+            for k in range(len(conds) - 1, -1, -1):
+                rv = conds[k].marginalise(rv)
+                assert np.allclose(rv.tcoeffs, ali.u_mean[k], rtol=1e-8, atol=1e-10), (kind, k)
+        # smoothing never widens the filter's uncertainty
+        assert np.all(ali.u_std <= filt.u_std * (1 + 1e-9) + 1e-14)
+
+
 def test_save_at_is_invariant_to_cutting_the_grid():
     """test_probdiffeq/test_dense_output/test_behaviour_close_to_t1.py:59-94: solving to [t0, t1] equals solving
     on a grid that contains t1 and reading off t1 (filter, no clipping)."""
