@@ -20,7 +20,7 @@
 
 namespace pdeq {
 
-constexpr int K3_THREADS = 64;
+constexpr int K3_THREADS = 256;
 
 struct DenseSmemLayout {
   int N, d, ld;  // ld = N + d
@@ -42,7 +42,8 @@ struct DenseSmemLayout {
     o += needs_interp ? tri : 0;
     s.off_vec = o;
     // m_from, mp, m_new, m_if (4N) | Hs d x (order+1) d | mobs, wht, std, ref, lam (5d) | p, pinv (2 * 8) | red 8 | bc 8
-    o += (size_t)4 * s.N + (size_t)d * (order + 1) * d + 5 * d + 16 + 16;
+    // | rdiag N + d
+    o += (size_t)4 * s.N + (size_t)d * (order + 1) * d + 5 * d + 16 + 16 + s.ld;
     s.total = o;
     return s;
   }
@@ -54,6 +55,11 @@ struct DenseLoop {
   static constexpr int q = VF::order;
   static constexpr int P = VF::num_params > 0 ? VF::num_params : 1;
   static constexpr int G = K3_THREADS;
+  // All extents are compile-time: the dense kernels exist for fixed-dimension vector fields only (the host checks
+  // cfg.ode_dim == VF::fixed_dim), so every index split (e / N, e % d, ...) is a multiply-shift, not a division.
+  static constexpr int D = VF::fixed_dim;
+  static_assert(D > 0, "the dense kernels need a compile-time ODE dimension");
+  static constexpr int N = n * D, LD = N + D, HW = (q + 1) * D, TRI_N = N * (N + 1) / 2;
 
   struct VecAcc {
     const double* u;  // coefficient-major mean
@@ -69,44 +75,121 @@ struct DenseLoop {
     __syncthreads();
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
-    return red[0] + red[1];
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < G / 32; ++w) tot += red[w];
+    return tot;
   }
 
-  // Cooperative in-place Householder triangularisation of the M x ncols matrix at W (leading dimension ld).
-  // hi(c) = min(hi_a + c, M - 1) for c < csplit, M - 1 otherwise.
-  PDEQ_DI static void coop_qr(double* W, int ld, int M, int ncols, int csplit, int hi_a, double* red) {
-    const int tid = threadIdx.x;
-    for (int j = 0; j < ncols; ++j) {
-      const int hj = (j < csplit) ? min(hi_a + j, M - 1) : M - 1;
-      if (hj <= j) continue;
+  // Sum of squares of W[j+1..h][j], by warp 0, into *dst; ends with a block barrier.
+  PDEQ_DI static void column_ss(const double* W, int j, int h, double* dst) {
+    if (threadIdx.x < 32) {
       double part = 0.0;
-      for (int r = j + 1 + tid; r <= hj; r += G) part = fma(W[r * ld + j], W[r * ld + j], part);
+      for (int r = j + 1 + (int)threadIdx.x; r <= h; r += 32) part = fma(W[r * LD + j], W[r * LD + j], part);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if (threadIdx.x == 0) *dst = part;
+    }
+    __syncthreads();
+  }
+
+  // Cooperative in-place Householder triangularisation of the M x ncols matrix at W (leading dimension LD).
+  // hi(c) = min(hi_a + c, M - 1) for c < csplit, M - 1 otherwise: the last non-zero row of column c.
+  //
+  // 256 threads = 64 column slots x 4 row groups. A warp holds 8 adjacent columns x 4 row groups (rows r, r+1 of
+  // LD = 56 doubles are 16 banks apart: each half-warp is conflict-free), so the four partial dot products of one
+  // column meet by two shuffles and there is ONE block barrier per column: the sum of squares of the next column
+  // is accumulated by the lanes that update it (always slot 0, i.e. warp 0), and the new diagonal goes to `rdiag`
+  // so that nobody races with the readers of alpha. Reflectors follow LAPACK dlarfg (H = I for a zero sub-column).
+  template <int M, int ncols, int csplit, int hi_a>
+  PDEQ_DI static void coop_qr(double* W, double* red, double* rdiag) {
+    constexpr int ld = LD;
+    const int tid = threadIdx.x;
+    const int cslot = (tid >> 5) * 8 + (tid & 7);
+    const int rg = (tid >> 3) & 3;
+    const bool warp0 = tid < 32;
+    auto hi = [](int c) { return (c < csplit) ? min(hi_a + c, M - 1) : M - 1; };
+    column_ss(W, 0, hi(0), red);
+    for (int j = 0; j < ncols; ++j) {
+      const int hj = hi(j);
       const double alpha = W[j * ld + j];
-      const double ss = block_sum(part, red);
-      if (ss == 0.0) continue;  // uniform: dlarfg's H = I
+      const double ss = red[j & 1];
+      const bool last = j + 1 >= ncols;
+      if (hj <= j || ss == 0.0) {  // uniform: nothing to annihilate
+        if (tid == 0) rdiag[j] = alpha;
+        if (!last) column_ss(W, j + 1, hi(j + 1), red + ((j + 1) & 1));
+        continue;
+      }
       const double tt = fma(alpha, alpha, ss);
       const double y = fast_rsqrt(tt);
       const double nrm = tt * y;
       const double sgn_nrm = copysign(nrm, alpha);
       const double v0 = alpha + sgn_nrm;
       const double tp = y * fast_rcp(nrm + fabs(alpha));
-      for (int c = j + 1 + tid; c < ncols; c += G) {
-        double w = v0 * W[j * ld + c];
-        for (int r = j + 1; r <= hj; ++r) w = fma(W[r * ld + j], W[r * ld + c], w);
+      if (tid == 0) rdiag[j] = -sgn_nrm;
+      const int h1 = last ? hj : hi(j + 1);
+      for (int c0 = j + 1; c0 < ncols; c0 += G / 4) {
+        const int c = c0 + cslot;
+        const bool active = c < ncols;
+        double w0 = 0.0, w1 = 0.0;
+        if (active) {
+          int r = j + 1 + rg;
+          for (; r + 4 <= hj; r += 8) {
+            w0 = fma(W[r * ld + j], W[r * ld + c], w0);
+            w1 = fma(W[(r + 4) * ld + j], W[(r + 4) * ld + c], w1);
+          }
+          if (r <= hj) w0 = fma(W[r * ld + j], W[r * ld + c], w0);
+          if (rg == 0) w1 = fma(v0, W[j * ld + c], w1);
+        }
+        double w = w0 + w1;
+        w += __shfl_xor_sync(0xffffffffu, w, 8);
+        w += __shfl_xor_sync(0xffffffffu, w, 16);
         w *= tp;
-        W[j * ld + c] = fma(-w, v0, W[j * ld + c]);
-        for (int r = j + 1; r <= hj; ++r) W[r * ld + c] = fma(-w, W[r * ld + j], W[r * ld + c]);
+        const bool gather = warp0 && c0 == j + 1;  // warp-uniform: this warp owns column j + 1
+        double sq = 0.0, sq1 = 0.0;
+        if (active) {
+          if (rg == 0) W[j * ld + c] = fma(-w, v0, W[j * ld + c]);
+          if (gather) {
+            // ... and gathers that column's sum of squares below its diagonal for the next reflector
+            int r = j + 1 + rg;
+            for (; r + 4 <= hj; r += 8) {
+              const double x0 = fma(-w, W[r * ld + j], W[r * ld + c]);
+              const double x1 = fma(-w, W[(r + 4) * ld + j], W[(r + 4) * ld + c]);
+              W[r * ld + c] = x0;
+              W[(r + 4) * ld + c] = x1;
+              sq = (cslot == 0 && r > j + 1) ? fma(x0, x0, sq) : sq;
+              sq1 = (cslot == 0) ? fma(x1, x1, sq1) : sq1;
+            }
+            if (r <= hj) {
+              const double x0 = fma(-w, W[r * ld + j], W[r * ld + c]);
+              W[r * ld + c] = x0;
+              sq = (cslot == 0 && r > j + 1) ? fma(x0, x0, sq) : sq;
+            }
+            sq += sq1;
+          } else {
+#pragma unroll 2
+            for (int r = j + 1 + rg; r <= hj; r += 4) W[r * ld + c] = fma(-w, W[r * ld + j], W[r * ld + c]);
+          }
+        }
+        if (gather) {
+          if (tid == 0)  // rows of column j + 1 below this reflector's reach
+            for (int r = hj + 1; r <= h1; ++r) sq = fma(W[r * ld + c], W[r * ld + c], sq);
+          sq += __shfl_xor_sync(0xffffffffu, sq, 8);
+          sq += __shfl_xor_sync(0xffffffffu, sq, 16);
+          if (tid == 0) red[(j + 1) & 1] = sq;
+        }
       }
-      if (tid == 0) W[j * ld + j] = -sgn_nrm;
       __syncthreads();
     }
+    for (int j = tid; j < ncols; j += G) W[j * ld + j] = rdiag[j];
+    __syncthreads();
   }
 
   // Write one checkpoint (mean [n][d], chol [N][N]) from shared memory.
   PDEQ_DI static void emit(const LoopArgs& a, long b, int ck, const DenseSmemLayout& lay, double t, const double* m,
                            const double* Lpk, double chol_scale, double scale, int nsteps) {
     const long bt = b * a.T + ck;
-    const int N = lay.N;
+    (void)lay;
     if (threadIdx.x == 0) {
       a.sol.t[bt] = t;
       a.sol.num_steps[bt] = nsteps;
@@ -128,7 +211,8 @@ struct DenseLoop {
                                        const double* pinv, const double* lam, double s,
                                        const double (*A)[PDEQ_MAX_COEFFS], const double (*Qm)[PDEQ_MAX_COEFFS],
                                        double* red) {
-    const int N = lay.N, d = lay.d, ld = lay.ld;
+    constexpr int d = D, ld = LD;
+    (void)lay;
     for (int e = threadIdx.x; e < N * N; e += G) {
       const int r = e / N, c = e % N;
       const int ci = c / d, cj = c % d;
@@ -143,7 +227,7 @@ struct DenseLoop {
       W[(N + r) * ld + d + c] = (cj == rj && ci >= ri) ? s * Qm[ci][ri] * lam[cj] : 0.0;
     }
     __syncthreads();
-    coop_qr(W + d, ld, 2 * N, N, N, N, red);
+    coop_qr<2 * N, N, N, N>(W + d, red, red + 16);
     for (int e = threadIdx.x; e < N * N; e += G) {
       const int r = e / N, c = e % N;
       if (r <= c) W[r * ld + d + c] *= fabs(p[c / d]);
@@ -155,7 +239,8 @@ struct DenseLoop {
   // With rows 0..N-1, cols d..d+N-1 of W holding an upper-triangular factor U = L^T, build and triangularise
   // [(H L)^T | L^T ; damp I | 0]. Afterwards R_Y = W[0..d)[0..d), R12 = W[0..d)[d..), R_XY = W[d..d+N)[d..).
   PDEQ_DI static void revert_stack(double* W, const DenseSmemLayout& lay, const double* Hs, double damp, double* red) {
-    const int N = lay.N, d = lay.d, ld = lay.ld, hw = (q + 1) * d;
+    constexpr int d = D, ld = LD, hw = HW;
+    (void)lay;
     for (int e = threadIdx.x; e < N * d; e += G) {
       const int r = e / d, a_ = e % d;
       double acc = 0.0;  // (H L)[a][r] = sum_e' H[a][e'] L[e'][r], L[e'][r] = U[r][e'] (e' >= r)
@@ -167,7 +252,7 @@ struct DenseLoop {
       W[(N + r) * ld + c] = (c == r) ? damp : 0.0;
     }
     __syncthreads();
-    coop_qr(W, ld, N + d, N + d, d, N, red);
+    coop_qr<N + d, N + d, d, N>(W, red, red + 16);
   }
 
   PDEQ_DI static void run(const LoopArgs& a, double* __restrict__ smem) {
@@ -180,14 +265,14 @@ struct DenseLoop {
     const bool clip = cfg.clip_dt != 0;
     const bool needs_interp = adaptive && !clip;
     const int T = a.T;
-    const int d = cfg.ode_dim;
+    constexpr int d = D;
     const long B = a.prob.num_instances;
     const int max_attempts = cfg.max_attempts > 0 ? cfg.max_attempts : 0x7fffffff;
     const double inv_sqrt_d = rsqrt((double)d);
     const double neg_inv_n = -1.0 / (double)n;
     const int tid = threadIdx.x;
     const DenseSmemLayout lay = DenseSmemLayout::make(n, d, q, needs_interp);
-    const int N = lay.N, ld = lay.ld, hw = (q + 1) * d;
+    constexpr int ld = LD, hw = HW;
 
     double* W = smem + lay.off_W;
     double* Lfrom = smem + lay.off_Lfrom;
@@ -207,9 +292,18 @@ struct DenseLoop {
     double* p = lam + d;               // 8
     double* pinv = p + 8;              // 8
     double* red = pinv + 8;            // 8
-    double* bc = red + 8;              // 8: broadcast slots
-    const int TRI_N = N * (N + 1) / 2;
+    double* bc = red + 8;              // 8: broadcast slots; red + 16: N + d new diagonal entries (coop_qr)
 
+#ifdef PDEQ_K3_PROFILE
+    // phase cycle counters (development aid): totals per instance go to the first 8 trace slots
+    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, prof_last = clock64();
+#define PDEQ_K3_TICK(i) { const long long now_ = clock64(); prof_acc[i] += now_ - prof_last; prof_last = now_; }
+#define PDEQ_K3_DUMP if (tid == 0 && a.sol.trace != nullptr && a.sol.trace_capacity >= 2) { \
+      for (int i_ = 0; i_ < 8; ++i_) { a.sol.trace[b * a.sol.trace_capacity * 4 + i_] = (double)prof_acc[i_]; prof_acc[i_] = 0; } }
+#else
+#define PDEQ_K3_TICK(i)
+#define PDEQ_K3_DUMP
+#endif
     double params[P];
     double t = 0.0, dt = 0.0, ctrl_lprev = 0.0, ndata = 0.0, t_next = 0.0, t_if = 0.0, sig = 1.0, run_scale = 0.0;
     int nsteps = 0, nattempts = 0, ck = 0, status = 0;
@@ -280,13 +374,9 @@ struct DenseLoop {
               mp[e] = p[i] * acc;
             }
             extrapolate_chol(W, lay, Lif, p, pinv, lam, safe_sqrt(fabs(dti)) * sig, A, Qm, red);
-            for (int e = tid; e < TRI_N; e += G) {
-              // packed index -> (i, j): L[i][j] = W[j][d + i]
-              int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-              while (tri(i, 0) > e) --i;
-              while (tri(i + 1, 0) <= e) ++i;
-              const int jj = e - tri(i, 0);
-              Lif[e] = W[jj * ld + d + i];
+            for (int e = tid; e < N * N; e += G) {
+              const int jj = e / N, i = e % N;  // L[i][jj] = W[jj][d + i], lower triangle only
+              if (jj <= i) Lif[tri(i, jj)] = W[jj * ld + d + i];
             }
             for (int e = tid; e < N; e += G) m_if[e] = mp[e];
             __syncthreads();
@@ -321,6 +411,7 @@ struct DenseLoop {
           for (int e = tid; e < N; e += G) bad += isfinite(m_from[e]) ? 0.0 : 1.0;
           bad = block_sum(bad, red);
           if (status == 0 && bad > 0.0) status = PDEQ_STATUS_NONFINITE;
+          PDEQ_K3_DUMP
           if (tid == 0) {
             a.sol.status[b] = status;
             if (a.sol.num_attempts != nullptr) a.sol.num_attempts[b] = nattempts;
@@ -333,6 +424,7 @@ struct DenseLoop {
 
       // ------------------------------------------------------------------ one step attempt
       nattempts += 1;
+      PDEQ_K3_TICK(0)
       double dtc;
       if (adaptive) {
         dtc = clip ? fmin(dt, t_next - t) : dt;
@@ -386,6 +478,7 @@ struct DenseLoop {
       }
       __syncthreads();
 
+      PDEQ_K3_TICK(1)
       // observation of the zero-error extrapolation: R_obs = qr_r([(H L_u)^T ; damp I]) (solver_dynamic, residual error)
       const bool need_obs = adaptive ? (cfg.solver == PDEQ_SOLVER_DYNAMIC || cfg.error == PDEQ_ERROR_RESIDUAL_STD)
                                      : (cfg.solver == PDEQ_SOLVER_DYNAMIC);
@@ -401,7 +494,7 @@ struct DenseLoop {
         }
         for (int e = tid; e < d * d; e += G) W[(N + e / d) * ld + (e % d)] = (e / d == e % d) ? a.damp : 0.0;
         __syncthreads();
-        coop_qr(W, ld, N + d, d, 0, 0, red);
+        coop_qr<N + d, d, 0, 0>(W, red, red + 16);
         if (tid == 0) {
           // whitened residual: solve R_obs^T w = mobs (forward substitution), rms; and the row norms of R_obs^T
           double ss = 0.0;
@@ -422,8 +515,11 @@ struct DenseLoop {
       }
 
       // extrapolate the factor, correct
+      PDEQ_K3_TICK(2)
       extrapolate_chol(W, lay, Lfrom, p, pinv, lam, sq * sig_new, A, Qm, red);
+      PDEQ_K3_TICK(3)
       revert_stack(W, lay, Hs, a.damp, red);
+      PDEQ_K3_TICK(4)
       // gain^T = R_Y^-1 R12 (d x N), in place over R12; one column per thread
       for (int c = tid; c < N; c += G) {
         for (int i = d - 1; i >= 0; --i) {
@@ -438,12 +534,9 @@ struct DenseLoop {
         for (int a_ = 0; a_ < d; ++a_) acc = fma(-W[a_ * ld + d + e], mobs[a_], acc);
         m_new[e] = acc;
       }
-      for (int e = tid; e < TRI_N; e += G) {
-        int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-        while (tri(i, 0) > e) --i;
-        while (tri(i + 1, 0) <= e) ++i;
-        const int jj = e - tri(i, 0);
-        Lprop[e] = W[(d + jj) * ld + d + i];
+      for (int e = tid; e < N * N; e += G) {
+        const int jj = e / N, i = e % N;
+        if (jj <= i) Lprop[tri(i, jj)] = W[(d + jj) * ld + d + i];
       }
       double run_new = run_scale;
       if (cfg.solver == PDEQ_SOLVER_MLE) {
@@ -464,6 +557,7 @@ struct DenseLoop {
       }
       __syncthreads();
 
+      PDEQ_K3_TICK(5)
       // ------------------------------------------------------------------ error estimate + control
       bool accept = true;
       double dt_next = dt;
@@ -559,6 +653,7 @@ struct DenseLoop {
       }
 
       // ------------------------------------------------------------------ commit
+      PDEQ_K3_TICK(6)
       dt = dt_next;
       if (accept) {
         if (needs_interp) {
@@ -585,7 +680,7 @@ struct DenseLoop {
 };
 
 template <class VF, int NU, bool TS0>
-__global__ void __launch_bounds__(K3_THREADS) k3_loop_kernel(const __grid_constant__ LoopArgs a) {
+__global__ void __launch_bounds__(K3_THREADS, 3) k3_loop_kernel(const __grid_constant__ LoopArgs a) {
   extern __shared__ double smem_k3[];
   DenseLoop<VF, NU, TS0>::run(a, smem_k3);
 }
