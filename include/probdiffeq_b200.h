@@ -118,7 +118,10 @@ typedef struct pdeq_solution {
   int32_t* status;       /* [B] PDEQ_STATUS_* */
   /* fixed-point smoother only (may be NULL): backward conditionals checkpoint k -> k-1, k = 1..T-1,
      with the preconditioner folded in: x_{k-1} | x_k ~ N(G x_k + xi, Xi Xi^T). */
-  double* bw_gain;       /* blockdiag [B][T][d][n][n] (entry 0 unused) */
+  /* optional (smoothers): the backward conditionals of the posterior (MarkovSequence.conditional), calibrated and
+     in natural coordinates (preconditioner applied, cf. LatentCond.preconditioner_apply). Entry k maps grid
+     point k to k-1: x_{k-1} | x_k ~ N(gain x_k + mean, chol chol^T); entry 0 is left untouched. */
+  double* bw_gain;       /* blockdiag [B][T][d][n][n], isotropic [B][T][n][n] */
   double* bw_mean;       /* [B][T][n][d] */
   double* bw_chol;       /* like chol */
   /* optional attempt log (NULL = off): for attempt a < trace_capacity of instance b,
@@ -184,6 +187,18 @@ int pdeq_lml_terminal_values(const pdeq_config* cfg, int64_t num_instances, int3
                              const double* mean, const double* chol, const double* data,
                              int64_t data_stride, const double* std, int64_t std_stride,
                              double* out, void* stream);
+
+/* loss_lml_timeseries (probdiffeq/_probdiffeq/estimators_and_losses.py:53-105 with MarkovSequence.evaluate_lml
+   :180-218): log-density of `data` [.][T][d] observed at all T grid points through noise `std`
+   ([.][T] isotropic, [.][T][d] block-diagonal) under the smoothing posterior. mean / chol are the solution
+   arrays of a smoother run ([B][T]...; entry T-1 is the posterior's terminal marginal), bw_* the backward
+   conditionals it emitted (pdeq_solution.bw_*). average_pdfs != 0 returns the running mean of the per-point
+   log-densities like the reference's default. workspace: num_instances * ode_dim doubles. out [B]. */
+int pdeq_lml_timeseries(const pdeq_config* cfg, int64_t num_instances, int32_t num_gridpoints,
+                        int32_t tcoeff_index, int32_t average_pdfs, const double* mean, const double* chol,
+                        const double* bw_gain, const double* bw_mean, const double* bw_chol,
+                        const double* data, int64_t data_stride, const double* std, int64_t std_stride,
+                        double* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Sum `n` doubles in place across the ranks of an NCCL communicator (ncclComm_t passed as void*):
    the ensemble log-marginal-likelihood reduction. The only collective on this path. */

@@ -72,6 +72,21 @@ def sum_of_sqrtm_factors(R_stack):
     return triu_via_qr(np.concatenate(R_stack, axis=-2))
 
 
+def lstsq_triu(matrix, rhs):
+    """backend/linalg.py:60-61 (`jnp.linalg.lstsq`): minimum-norm least squares, batched over leading axes.
+
+    Equals `solve_triu` for a non-singular matrix; a zero pivot (noise-free observation of an exactly known
+    state) yields a zero gain instead of NaN."""
+    matrix = np.asarray(matrix, dtype=np.float64)
+    rhs = np.asarray(rhs, dtype=np.float64)
+    if matrix.ndim == 2:
+        return np.linalg.lstsq(matrix, rhs, rcond=None)[0]
+    out = np.empty(np.broadcast_shapes(matrix.shape[:-2], rhs.shape[:-2]) + rhs.shape[-2:])
+    for idx in np.ndindex(out.shape[:-2]):
+        out[idx] = np.linalg.lstsq(matrix[idx], rhs[idx], rcond=None)[0]
+    return out
+
+
 def revert_conditional(R_X_F, R_X, R_YX, solve=solve_triu):
     """Square-root change of parametrisation p(Y|X)p(X) -> p(X|Y)p(Y).
 

@@ -151,6 +151,26 @@ class MarkovSequence:
         return out
 
 
+    def remove_filtering_distributions(self):
+        """:220-231: keep the terminal marginal only."""
+        if isinstance(self.marginal, list):
+            return MarkovSequence(self.marginal[-1], self.conditional, self.reverse)
+        return self
+
+    def evaluate_lml(self, u, *, model, average_pdfs, solve=None):
+        """:180-218: backward scan -- observe the terminal state, then alternately step back through a
+        conditional and observe. `u[k]`, `model[k]` belong to grid point k; conditional[k-1] maps k -> k-1."""
+        assert self.reverse and not isinstance(self.marginal, list)
+        pdf, rv = model[-1].bayes_rule_and_logpdf(u[-1], self.marginal, solve=solve)
+        num = 1
+        for k in range(len(self.conditional) - 1, -1, -1):
+            predicted = self.conditional[k].marginalise(rv)
+            pdf_n, rv = model[k].bayes_rule_and_logpdf(u[k], predicted, solve=solve)
+            pdf = (pdf * num + pdf_n) / (num + 1) if average_pdfs else pdf + pdf_n
+            num += 1
+        return pdf
+
+
 def _map(fn, x):
     return [fn(s) for s in x] if isinstance(x, list) else fn(x)
 
@@ -618,6 +638,30 @@ class error_state_std:
 # ------------------------------------------------------------------------------------------------
 # Log-marginal-likelihood of terminal-value data
 # ------------------------------------------------------------------------------------------------
+
+
+def loss_lml_timeseries(*, average_pdfs=True, tcoeff_index=0, solve=None):
+    """estimators_and_losses.py:53-105. `solve` defaults to the least-squares triangular solve the reference
+    passes (backend/linalg.py:60-61), which equals the exact solve whenever the observed factor is non-singular.
+    `u`: (T, d) data; `std`: (T,) isotropic, (T, d) block-diagonal / dense."""
+    if solve is None:
+        solve = linalg.lstsq_triu
+
+    def loss(u, /, *, posterior, std):
+        if not isinstance(posterior, MarkovSequence):
+            raise TypeError("The datatype of the posterior is not as expected. Did you perhaps use a filter?")
+        u = np.asarray(u, dtype=np.float64)
+        std = np.asarray(std, dtype=np.float64)
+        posterior = posterior.remove_filtering_distributions()
+        alg = posterior.marginal.alg
+        std_expected = np.stack([np.asarray(posterior.marginal.std)[tcoeff_index]] * u.shape[0])
+        if std.shape != std_expected.shape:
+            raise ValueError("The standard deviation container differs from what was expected.")
+        model = [alg.to_derivative(posterior.marginal, tcoeff_index, s) for s in std]
+        data = [alg.from_nd(x[None, :]) for x in u]
+        return posterior.evaluate_lml(data, model=model, average_pdfs=average_pdfs, solve=solve)
+
+    return loss
 
 
 def loss_lml_terminal_values(*, tcoeff_index=0):

@@ -58,8 +58,8 @@ class Cond:
     def marginalise(self, rv):
         return self.alg.marginalise(self, rv)
 
-    def revert(self, rv):
-        return self.alg.revert(self, rv)
+    def revert(self, rv, solve=None):
+        return self.alg.revert(self, rv) if solve is None else self.alg.revert(self, rv, solve=solve)
 
     def merge(self, other):
         return self.alg.merge(self, other)
@@ -78,8 +78,8 @@ class Cond:
         rms = self.alg.residual_whitened_rms(observed, data)
         return rms, reverted.apply_flat(data)
 
-    def bayes_rule_and_logpdf(self, data, rv):
-        observed, reverted = self.revert(rv)
+    def bayes_rule_and_logpdf(self, data, rv, solve=None):
+        observed, reverted = self.revert(rv, solve=solve)
         return self.alg.logpdf(observed, data), reverted.apply_flat(data)
 
 
@@ -113,11 +113,11 @@ class Isotropic:
         Xi = linalg.sum_of_sqrtm_factors((R1, outer.noise.chol.T))
         return Cond(g, Normal(xi, Xi.T, self), inner.to_latent, outer.to_observed)
 
-    def revert(self, c, rv):
+    def revert(self, c, rv, solve=linalg.solve_triu):
         mean = c.to_latent[:, None] * rv.mean
         chol = np.abs(c.to_latent[:, None]) * rv.chol
         r_obs, (r_cor, gain) = linalg.revert_conditional(
-            R_X_F=(c.A @ chol).T, R_X=chol.T, R_YX=c.noise.chol.T
+            R_X_F=(c.A @ chol).T, R_X=chol.T, R_YX=c.noise.chol.T, solve=solve
         )
         m_obs = c.A @ mean + c.noise.mean
         corrected = Normal(mean - gain @ m_obs, r_cor.T, self)
@@ -267,11 +267,11 @@ class Dense:
         Xi = linalg.sum_of_sqrtm_factors((R1, outer.noise.chol.T))
         return Cond(g, Normal(xi, Xi.T, self), inner.to_latent, outer.to_observed)
 
-    def revert(self, c, rv):
+    def revert(self, c, rv, solve=linalg.solve_triu):
         mean = c.to_latent * rv.mean
         chol = np.abs(c.to_latent[:, None]) * rv.chol
         r_obs, (r_cor, gain) = linalg.revert_conditional(
-            R_X_F=(c.A @ chol).T, R_X=chol.T, R_YX=c.noise.chol.T
+            R_X_F=(c.A @ chol).T, R_X=chol.T, R_YX=c.noise.chol.T, solve=solve
         )
         m_obs = c.A @ mean + c.noise.mean
         corrected = Normal(mean - gain @ m_obs, r_cor.T, self)
@@ -417,11 +417,11 @@ class BlockDiag:
         Xi = linalg.sum_of_sqrtm_factors((_T(A1 @ C2), _T(outer.noise.chol)))
         return Cond(g, Normal(xi, _T(Xi), self), inner.to_latent, outer.to_observed)
 
-    def revert(self, c, rv):
+    def revert(self, c, rv, solve=linalg.solve_triu):
         mean = c.to_latent * rv.mean
         chol = np.abs(c.to_latent[:, :, None]) * rv.chol
         r_obs, (r_cor, gain) = linalg.revert_conditional(
-            R_X_F=_T(c.A @ chol), R_X=_T(chol), R_YX=_T(c.noise.chol)
+            R_X_F=_T(c.A @ chol), R_X=_T(chol), R_YX=_T(c.noise.chol), solve=solve
         )
         m_obs = np.einsum("ijk,ik->ij", c.A, mean) + c.noise.mean
         m_cor = mean - np.einsum("ijk,ik->ij", gain, m_obs)

@@ -120,6 +120,11 @@ SYMBOLS = {
         [_P(Config), C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
          C.c_int64, C.c_void_p, C.c_void_p],
     ),  # fmt: skip
+    "pdeq_lml_timeseries": (
+        C.c_int,
+        [_P(Config), C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
+    ),  # fmt: skip
     "pdeq_allreduce_sum_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pdeq_fp64_peak_probe": (C.c_int, [C.c_int32, _P(C.c_double), _P(C.c_double), C.c_void_p]),
 }

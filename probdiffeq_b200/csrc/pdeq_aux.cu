@@ -212,6 +212,97 @@ __global__ void lml_terminal_kernel(int64_t B, int n, int d, int blockdiag, int 
   if (lane == 0) out[b] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// loss_lml_timeseries for the isotropic and block-diagonal factorisations
+// (probdiffeq/_probdiffeq/estimators_and_losses.py:53-105; MarkovSequence.evaluate_lml :180-218;
+// AbstractLatentCond.bayes_rule_and_logpdf_tree, ssm_impl_api.py:124-132): a backward scan over the grid that
+// observes the terminal marginal, then alternately steps back through a stored backward conditional
+// (cond_marginalise) and observes again (revert_obs with the measurement noise in the place of damp).
+// Thread (b, j) runs the scan of dimension j of instance b and leaves its share of the log-density in
+// `partial` [B][d]; lml_reduce_kernel adds the d shares of an instance in a fixed order.
+// The conditionals are in natural coordinates (preconditioner applied), as the step loop emits them.
+// A zero observed factor gives a zero gain -- the reference's least-squares solve (backend/linalg.py:60-61).
+// ---------------------------------------------------------------------------------------------------
+template <int n>
+__global__ void lml_timeseries_kernel(int64_t B, int T, int d, int blockdiag, int idx, int average,
+                                      const double* __restrict__ mean, const double* __restrict__ chol,
+                                      const double* __restrict__ bw_gain, const double* __restrict__ bw_mean,
+                                      const double* __restrict__ bw_chol, const double* __restrict__ data,
+                                      int64_t data_stride, const double* __restrict__ std_, int64_t std_stride,
+                                      double* __restrict__ partial) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= B * d) return;
+  const int64_t b = gid / d;
+  const int j = (int)(gid % d);
+  const double log2pi = 1.8378770664093453;
+  auto mat = [&](const double* base, int k) {  // the n x n block of grid point k
+    return blockdiag ? base + ((b * T + k) * (int64_t)d + j) * (n * n) : base + (b * T + k) * (int64_t)(n * n);
+  };
+  double m[n], L[n][n], h[n];
+#pragma unroll
+  for (int i = 0; i < n; ++i) {
+    m[i] = mean[((b * T + (T - 1)) * n + i) * (int64_t)d + j];
+    h[i] = (i == idx) ? 1.0 : 0.0;
+#pragma unroll
+    for (int c = 0; c < n; ++c) L[i][c] = (c <= i) ? mat(chol, T - 1)[i * n + c] : 0.0;
+  }
+  double acc = 0.0;
+  int num = 0;
+  for (int k = T - 1; k >= 0; --k) {
+    if (k < T - 1) {  // step back through the conditional that maps grid point k + 1 to k
+      BlockCond<n> c;
+      const double* G = mat(bw_gain, k + 1);
+      const double* X = mat(bw_chol, k + 1);
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        c.xi[i] = bw_mean[((b * T + (k + 1)) * n + i) * (int64_t)d + j];
+        c.tl[i] = 1.0;
+        c.to[i] = 1.0;
+#pragma unroll
+        for (int cc = 0; cc < n; ++cc) {
+          c.G[i][cc] = G[i * n + cc];
+          c.Xi[i][cc] = (cc <= i) ? X[i * n + cc] : 0.0;
+        }
+      }
+      double mo[n], Lo[n][n];
+      cond_marginalise<n>(c, m, L, mo, Lo);
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        m[i] = mo[i];
+#pragma unroll
+        for (int cc = 0; cc < n; ++cc) L[i][cc] = (cc <= i) ? Lo[i][cc] : 0.0;
+      }
+    }
+    const double sd = std_[b * std_stride + (blockdiag ? (int64_t)k * d + j : k)];
+    const double y = data[b * data_stride + (int64_t)k * d + j];
+    double ry, gain[n], Ln[n][n];
+    revert_obs<n, n - 1, false>(L, h, sd, ry, gain, Ln);
+    double mi = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) mi = (i == idx) ? m[i] : mi;
+    const double res = y - mi;
+    const double w = res / ry;
+    const double pdf = -0.5 * (2.0 * log(fabs(ry)) + w * w + log2pi);
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      m[i] = fma((ry != 0.0) ? gain[i] : 0.0, res, m[i]);
+#pragma unroll
+      for (int cc = 0; cc < n; ++cc) L[i][cc] = (cc <= i) ? Ln[i][cc] : 0.0;
+    }
+    acc = average ? (acc * (double)num + pdf) / (double)(num + 1) : acc + pdf;
+    num += 1;
+  }
+  partial[gid] = acc;
+}
+
+__global__ void lml_reduce_kernel(int64_t B, int d, const double* __restrict__ partial, double* __restrict__ out) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double acc = 0.0;
+  for (int j = 0; j < d; ++j) acc += partial[b * d + j];
+  out[b] = acc;
+}
+
 }  // namespace pdeq
 
 using namespace pdeq;
@@ -299,6 +390,57 @@ int pdeq_lml_terminal_values(const pdeq_config* cfg, int64_t num_instances, int3
       data, data_stride, std, std_stride, fact == PDEQ_FACT_BLOCKDIAG, out);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return api_cuda_fail(e, "lml_terminal_values");
+  return 0;
+}
+
+int pdeq_lml_timeseries(const pdeq_config* cfg, int64_t num_instances, int32_t num_gridpoints, int32_t tcoeff_index,
+                        int32_t average_pdfs, const double* mean, const double* chol, const double* bw_gain,
+                        const double* bw_mean, const double* bw_chol, const double* data, int64_t data_stride,
+                        const double* std, int64_t std_stride, double* out, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  int rc = api_validate(cfg);
+  if (rc != 0) return rc;
+  if (mean == nullptr || chol == nullptr || bw_gain == nullptr || bw_mean == nullptr || bw_chol == nullptr ||
+      data == nullptr || std == nullptr || out == nullptr)
+    return api_fail(-22, "NULL argument");
+  if (num_gridpoints < 1) return api_fail(-23, "num_gridpoints must be >= 1");
+  if (tcoeff_index < 0 || tcoeff_index > cfg->num_derivatives) return api_fail(-5, "bad tcoeff_index");
+  int fact = cfg->factorisation;
+  if (fact == PDEQ_FACT_DENSE && cfg->ode_dim == 1) fact = PDEQ_FACT_ISOTROPIC;
+  if (fact == PDEQ_FACT_DENSE) return api_fail(-10, "lml_timeseries: dense factorisation with d > 1 not built");
+  if (num_instances == 0) return 0;
+  const int64_t total = num_instances * (int64_t)cfg->ode_dim;
+  if (workspace == nullptr || workspace_bytes < (size_t)total * sizeof(double))
+    return api_fail(-24, "lml_timeseries needs %zu workspace bytes (num_instances * ode_dim doubles)",
+                    (size_t)total * sizeof(double));
+  const int threads = 64;
+  const int grid = (int)((total + threads - 1) / threads);
+  const int bd = fact == PDEQ_FACT_BLOCKDIAG;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* partial = (double*)workspace;
+#define PDEQ_LML_CASE(NN)                                                                                         \
+  case NN:                                                                                                        \
+    lml_timeseries_kernel<NN><<<grid, threads, 0, st>>>(num_instances, num_gridpoints, cfg->ode_dim, bd,          \
+                                                        tcoeff_index, average_pdfs, mean, chol, bw_gain, bw_mean, \
+                                                        bw_chol, data, data_stride, std, std_stride, partial);    \
+    break;
+  switch (cfg->num_derivatives + 1) {
+    PDEQ_LML_CASE(2)
+    PDEQ_LML_CASE(3)
+    PDEQ_LML_CASE(4)
+    PDEQ_LML_CASE(5)
+    PDEQ_LML_CASE(6)
+    PDEQ_LML_CASE(7)
+    PDEQ_LML_CASE(8)
+    default:
+      return api_fail(-10, "lml_timeseries: num_derivatives must be in 1..7");
+  }
+#undef PDEQ_LML_CASE
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return api_cuda_fail(e, "lml_timeseries");
+  lml_reduce_kernel<<<(int)((num_instances + 127) / 128), 128, 0, st>>>(num_instances, cfg->ode_dim, partial, out);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return api_cuda_fail(e, "lml_timeseries (reduce)");
   return 0;
 }
 

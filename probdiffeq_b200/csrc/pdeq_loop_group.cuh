@@ -145,6 +145,24 @@ struct GroupLoop {
     for (int i = 0; i < n; ++i) c.to[i] = base[(e++) * d + j];
   }
 
+  // One backward conditional of the posterior (MarkovSequence.conditional after rescale_cholesky,
+  // estimators_and_losses.py:151-154), written in natural coordinates (LatentCond.preconditioner_apply,
+  // ssm_impl_blockdiag.py:86-96): gain = T_o G T_l, mean = T_o xi, chol = scale |T_o| Xi.
+  PDEQ_DI static void emit_conditional(const LoopArgs& a, long bt, int d, int j, const BlockCond<n>& c, double scale) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) a.sol.bw_mean[(bt * n + i) * (long)d + j] = c.to[i] * c.xi[i];
+    if (ISO && j != 0) return;
+    const long off = ISO ? bt * (long)(n * n) : (bt * d + j) * (long)(n * n);
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+      for (int k = 0; k < n; ++k) {
+        a.sol.bw_gain[off + i * n + k] = c.to[i] * c.G[i][k] * c.tl[k];
+        a.sol.bw_chol[off + i * n + k] = (k <= i) ? scale * fabs(c.to[i]) * c.Xi[i][k] : 0.0;
+      }
+    }
+  }
+
   PDEQ_DI static void write_chol(const LoopArgs& a, long bt, int d, int j, const double (&L)[n][n], double scale) {
     if (a.sol.chol == nullptr || (ISO && j != 0)) return;
     double* co = ISO ? a.sol.chol + bt * (long)(n * n) : a.sol.chol + (bt * d + j) * (long)(n * n);
@@ -397,6 +415,7 @@ struct GroupLoop {
                 write_chol(a, bt, d, j, Lo, fin);
                 if (k > 0) {
                   cond_load(ring + (size_t)k * NFC * d, d, j, c);
+                  if (a.sol.bw_gain != nullptr) emit_conditional(a, bt, d, j, c, fin);
 #pragma unroll
                   for (int i = 0; i < n; ++i) {
                     m[i] = mo[i];

@@ -119,7 +119,10 @@ def _problem(prior, vf):
     return pr, (params,)
 
 
-def _alloc_solution(prior, T, want_chol=True, trace_capacity=0):
+POSTERIOR_AUTO_BYTES = 2 << 30  # smoothers return their backward conditionals by default up to this size
+
+
+def _alloc_solution(prior, T, want_chol=True, trace_capacity=0, want_posterior=False):
     B, n, d = prior.tcoeffs.shape
     dev = prior.tcoeffs.device
     fact = prior.factorisation
@@ -139,6 +142,12 @@ def _alloc_solution(prior, T, want_chol=True, trace_capacity=0):
     )
     if trace_capacity > 0:
         bufs["trace"] = torch.full((B, trace_capacity, 4), float("nan"), **f64)
+    if want_posterior:
+        if fact == "dense" and d > 1:
+            raise ValueError("the dense factorisation has no smoother on device; no posterior to return")
+        bufs["bw_gain"] = torch.zeros(chol_shape, **f64)
+        bufs["bw_mean"] = torch.zeros((B, T, n, d), **f64)
+        bufs["bw_chol"] = torch.zeros(chol_shape, **f64)
     so = _lib.Solution()
     for k, v in bufs.items():
         setattr(so, k, _pdq._ptr(v))
@@ -146,15 +155,38 @@ def _alloc_solution(prior, T, want_chol=True, trace_capacity=0):
     return so, bufs
 
 
+def _want_posterior(flag, solver, prior, T, want_chol):
+    """Smoothers return the posterior (terminal marginal + backward conditionals) like the reference does;
+    `None` = yes unless the conditionals would exceed POSTERIOR_AUTO_BYTES."""
+    if solver.strategy.kind == "filter" or not want_chol:
+        if flag:
+            raise ValueError("want_posterior needs a smoother and want_cholesky=True")
+        return False
+    if flag is not None:
+        return bool(flag)
+    B, n, d = prior.tcoeffs.shape
+    blocks = 1 if prior.factorisation == "isotropic" else d
+    return 8 * B * T * (2 * blocks * n * n + n * d) <= POSTERIOR_AUTO_BYTES
+
+
 def _wrap(prior, bufs, *, terminal: bool):
+    fact_u = prior.factorisation if not (prior.factorisation == "dense" and prior.ode_dim == 1) else "isotropic"
+    full = None
+    if "bw_gain" in bufs:
+        pick = (lambda x: x[0]) if prior.unbatched else (lambda x: x)
+        post = _pdq.MarkovSequence(
+            marginal=_pdq.Normal(fact_u, pick(bufs["mean"][:, -1]), pick(bufs["chol"][:, -1])),
+            conditional=_pdq.BackwardConditional(pick(bufs["bw_gain"]), pick(bufs["bw_mean"]), pick(bufs["bw_chol"])),
+        )
+        full = _pdq.SmoothingSolution(posterior=post)
     sol = _pdq.ProbabilisticSolution(
         t=bufs["t"],
-        u=_pdq.Normal(prior.factorisation if not (prior.factorisation == "dense" and prior.ode_dim == 1) else "isotropic",
-                      bufs["mean"], bufs["chol"]),
+        u=_pdq.Normal(fact_u, bufs["mean"], bufs["chol"]),
         output_scale=bufs["output_scale"],
         num_steps=bufs["num_steps"],
         num_attempts=bufs["num_attempts"],
         status=bufs["status"],
+        solution_full=full,
     )  # fmt: skip
     trace = bufs.get("trace")
     if terminal:
@@ -174,7 +206,7 @@ def _workspace(cfg, B, T, device):
 
 
 def _run_adaptive(prior, solver, error, control, clip_dt, save_at, atol, rtol, dt0, eps, damp, *, terminal,
-                  want_chol=True, max_attempts=0, trace_capacity=0):  # fmt: skip
+                  want_chol=True, max_attempts=0, trace_capacity=0, want_posterior=None):  # fmt: skip
     if control is None:
         control = control_integral()  # solvers_via_adaptive_steps.py:87-90
     cfg = _lower(prior, solver, error, control, clip_dt, max_attempts)
@@ -187,7 +219,8 @@ def _run_adaptive(prior, solver, error, control, clip_dt, save_at, atol, rtol, d
     if dt0_t.shape[0] not in (1, B):
         raise ValueError("dt0 must be a scalar or have one entry per ensemble member.")
     pr, keep = _problem(prior, solver.constraint.ode)
-    so, bufs = _alloc_solution(prior, T, want_chol, trace_capacity)
+    so, bufs = _alloc_solution(prior, T, want_chol, trace_capacity,
+                               _want_posterior(want_posterior, solver, prior, T, want_chol) and not terminal)
     if B > 0:  # an empty ensemble returns empty arrays (there is nothing to launch)
         ws, nbytes = _workspace(cfg, B, T, prior.tcoeffs.device)
         rc = _lib.load().pdeq_solve_adaptive_save_at(
@@ -222,10 +255,11 @@ def solve_adaptive_save_at(*, solver, error, control=None, clip_dt: bool = False
         msg += " Try using filters or fixed-point smoothers."
         warnings.warn(msg, stacklevel=1)
 
-    def solve(u, save_at, atol, rtol, dt0=0.1, eps=1e-8, damp=0.0, want_cholesky=True, trace_capacity=0):
+    def solve(u, save_at, atol, rtol, dt0=0.1, eps=1e-8, damp=0.0, want_cholesky=True, trace_capacity=0,
+              want_posterior=None):
         return _run_adaptive(u, solver, error, control, clip_dt, save_at, atol, rtol, dt0, eps, damp,
                              terminal=False, want_chol=want_cholesky, max_attempts=max_attempts,
-                             trace_capacity=trace_capacity)  # fmt: skip
+                             trace_capacity=trace_capacity, want_posterior=want_posterior)  # fmt: skip
 
     return solve
 
@@ -238,7 +272,7 @@ def solve_fixed_grid(*, solver):
         msg += " Try using filters or fixed-interval smoothers instead."
         warnings.warn(msg, stacklevel=1)
 
-    def solve(u, /, *, grid, damp: float = 0.0, want_cholesky=True):
+    def solve(u, /, *, grid, damp: float = 0.0, want_cholesky=True, want_posterior=None):
         prior = u
         cfg = _lower(prior, solver, None, None, False)
         B = prior.tcoeffs.shape[0]
@@ -247,7 +281,8 @@ def solve_fixed_grid(*, solver):
             raise ValueError("grid must be one-dimensional (shared by the ensemble).")
         T = g.shape[0]
         pr, keep = _problem(prior, solver.constraint.ode)
-        so, bufs = _alloc_solution(prior, T, want_cholesky)
+        so, bufs = _alloc_solution(prior, T, want_cholesky, 0,
+                                   _want_posterior(want_posterior, solver, prior, T, want_cholesky))
         if B > 0:
             ws, nbytes = _workspace(cfg, B, T, prior.tcoeffs.device)
             rc = _lib.load().pdeq_solve_fixed_grid(

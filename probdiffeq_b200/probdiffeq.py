@@ -38,6 +38,10 @@ __all__ = [
     "jetexpand_ode_padded_scan",
     "jetexpand_ode_unroll",
     "loss_lml_terminal_values",
+    "loss_lml_timeseries",
+    "MarkovSequence",
+    "SmoothingSolution",
+    "BackwardConditional",
     "ode",
     "registered_vector_fields",
     "solver",
@@ -543,9 +547,98 @@ class ProbabilisticSolution:
         )  # fmt: skip
 
 
+@dataclasses.dataclass
+class BackwardConditional:
+    """The backward conditionals of a smoothing posterior, calibrated and in natural coordinates
+    (reference: `LatentCond.preconditioner_apply`): entry k maps grid point k to k - 1,
+    ``x[k-1] | x[k] ~ N(gain[k] x[k] + mean[k], cholesky[k] cholesky[k]^T)``; entry 0 is unused (zeros)."""
+
+    gain: torch.Tensor  # isotropic (..., T, n, n); blockdiag (..., T, d, n, n)
+    mean: torch.Tensor  # (..., T, n, d)
+    cholesky: torch.Tensor  # like gain
+
+
+@dataclasses.dataclass
+class MarkovSequence:
+    """reference: `MarkovSequence` (estimators_and_losses.py:121-231) with ``reverse=True``: the terminal marginal
+    plus one backward conditional per grid interval."""
+
+    marginal: Normal  # at the last grid point
+    conditional: BackwardConditional
+    reverse: bool = True
+
+
+@dataclasses.dataclass
+class SmoothingSolution:
+    """reference: `SmoothingSolution` (estimators_and_losses.py:107-118)."""
+
+    posterior: MarkovSequence
+    filtering: Any = None
+
+
 # ------------------------------------------------------------------------------------------------------
-# Log-marginal likelihood of terminal values
+# Log-marginal likelihoods
 # ------------------------------------------------------------------------------------------------------
+
+
+def loss_lml_timeseries(*, average_pdfs: bool = True, tcoeff_index: int = 0):
+    """reference: estimators_and_losses.py:53-105 (+ `MarkovSequence.evaluate_lml` :180-218).
+
+    ``loss(u, posterior=sol.solution_full.posterior, std=...)`` with data ``u`` (T, d) -- or (B, T, d), one series per
+    ensemble member -- and ``std`` (T,) for the isotropic model, (T, d) for the block-diagonal one (optionally with
+    a leading ensemble axis). Returns one value per ensemble member, shape (B,)."""
+
+    def loss(u, /, *, posterior, std):
+        if not isinstance(posterior, MarkovSequence):
+            msg = "The datatype of the posterior is not as expected."
+            msg += f" Expected: {MarkovSequence}."
+            msg += f" Received: {type(posterior)}."
+            msg += " Did you perhaps use a filter instead of a smoother"
+            msg += ", forget to extract the posterior from the smoothing-solution"
+            msg += ", or mean to use a different loss?"
+            raise TypeError(msg)
+        marg, cond = posterior.marginal, posterior.conditional
+        fact = marg.factorisation
+        mean, chol = marg.mean_flat, marg.cholesky_flat
+        gain, cmean, cchol = cond.gain, cond.mean, cond.cholesky
+        unbatched = mean.ndim == 2
+        if unbatched:
+            mean, chol, gain, cmean, cchol = mean[None], chol[None], gain[None], cmean[None], cchol[None]
+        B, n, d = mean.shape
+        T = cmean.shape[1]
+        data = _as_device_f64(u)
+        sd = _as_device_f64(std)
+        data_b = data if data.ndim == 3 else data[None]
+        std_core = (T,) if fact == "isotropic" else (T, d)
+        sd_b = sd if sd.ndim == len(std_core) + 1 else sd[None]
+        msg = "The standard deviation container differs from what was expected."
+        msg += f" Expected: shape={std_core}. Received: shape={tuple(sd.shape)}."
+        msg += f" For reference: data-shape={tuple(data.shape)}."
+        if tuple(sd_b.shape[1:]) != std_core or tuple(data_b.shape[1:]) != (T, d):
+            raise ValueError(msg)
+        for name, arr in (("data", data_b), ("std", sd_b)):
+            if arr.shape[0] not in (1, B):
+                raise ValueError(f"{name} batch axis does not match the ensemble.")
+        # the kernel reads the terminal marginal as entry T - 1 of (B, T, ...) arrays
+        mean_t = torch.zeros((B, T, n, d), dtype=torch.float64, device=mean.device)
+        mean_t[:, -1] = mean
+        chol_t = torch.zeros((B, T, *chol.shape[1:]), dtype=torch.float64, device=mean.device)
+        chol_t[:, -1] = chol
+        cfg = _make_config(fact=fact, nu=n - 1, d=d, vf=VectorField("linear", params=[1.0]))
+        out = torch.empty((B,), dtype=torch.float64, device=mean.device)
+        ws = torch.empty((max(B * d, 1),), dtype=torch.float64, device=mean.device)
+        data_b, sd_b = data_b.contiguous(), sd_b.contiguous()
+        rc = _lib.load().pdeq_lml_timeseries(
+            C.byref(cfg), B, T, int(tcoeff_index), int(bool(average_pdfs)), _ptr(mean_t), _ptr(chol_t),
+            _ptr(gain.contiguous()), _ptr(cmean.contiguous()), _ptr(cchol.contiguous()),
+            _ptr(data_b), 0 if data_b.shape[0] == 1 else T * d, _ptr(sd_b),
+            0 if sd_b.shape[0] == 1 else int(np.prod(std_core)), _ptr(out), _ptr(ws), ws.numel() * 8, _stream(),
+        )  # fmt: skip
+        _lib.check(rc, "pdeq_lml_timeseries")
+        return out[0] if unbatched else out
+
+    return loss
+
 
 
 def loss_lml_terminal_values(*, tcoeff_index: int = 0):

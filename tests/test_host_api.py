@@ -106,3 +106,8 @@ def test_constructors_mirror_the_reference_error_behaviour():
         ivpsolve.solve_fixed_grid(solver=fp)  # reference: solvers_via_fixed_steps.py:14-18
     assert ivpsolve.control_integral().safety == 0.95
     assert ivpsolve.control_proportional_integral().exponent_proportional == 0.4
+    # loss_lml_timeseries wants the posterior of a smoother (reference: estimators_and_losses.py:60-68)
+    with pytest.raises(TypeError, match="datatype"):
+        probdiffeq.loss_lml_timeseries()(np.zeros((3, 2)), posterior=object(), std=np.ones(3))
+    with pytest.raises(ValueError, match="terminal"):
+        probdiffeq.strategy_smoother_fixedinterval(terminal="nonsense")

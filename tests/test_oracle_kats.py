@@ -295,5 +295,51 @@ def test_lml_terminal_values_matches_dense_gaussian():
         assert np.isclose(lml, expected, rtol=1e-9), kind
 
 
+def test_lml_timeseries_matches_joint_gaussian():
+    """estimators_and_losses.py:53-105, 180-218 (setup of test_losses/test_lml_timeseries.py:19-46). The backward
+    scan must equal the log-density of all observations under the joint Gaussian that the Markov sequence
+    defines; isotropic == dense (ts0) as in test_dynamic_across_factorisations.py."""
+    rng = np.random.default_rng(1)
+    save_at = np.linspace(0.0, 2.0, 7)
+    values = {}
+    for kind in ("isotropic", "blockdiag", "dense"):
+        prior, slv, err = _setup(kind, "ts0", "solver_mle", pdq.strategy_smoother_fixedpoint, "error_residual_std", num=2)
+        sol = ivpsolve.solve_adaptive_save_at(solver=slv, error=err)(prior, save_at=save_at, atol=1e-3, rtol=1e-3)
+        post = sol.solution_full.posterior
+        data = np.asarray(sol.u_mean)[:, 0] + 0.05 * rng.normal(size=(7, 2))
+        sd = 0.05 + 0.01 * np.arange(7)
+        std = sd if kind == "isotropic" else np.stack([sd, 2 * sd], axis=1)
+        total = pdq.loss_lml_timeseries(average_pdfs=False)(data, posterior=post, std=std)
+        mean_of = pdq.loss_lml_timeseries(average_pdfs=True)(data, posterior=post, std=std)
+        assert np.isclose(mean_of, total / 7, rtol=1e-12)
+        values[kind] = (total, data, std)
+        with pytest.raises(ValueError, match="container differs"):
+            pdq.loss_lml_timeseries()(data, posterior=post, std=std[:-1])
+        with pytest.raises(TypeError, match="datatype"):
+            pdq.loss_lml_timeseries()(data, posterior=sol.u, std=std)
+        if kind != "dense":
+            continue
+        # joint Gaussian over the stacked states, built from the terminal marginal and the natural-form conditionals
+        post = post.remove_filtering_distributions()
+        m, C = post.marginal.cov_dense()
+        N, T = m.size, len(save_at)
+        means, covs = {T - 1: m}, {(T - 1, T - 1): C}
+        for k in range(T - 1, 0, -1):
+            c = post.conditional[k - 1].alg.preconditioner_apply(post.conditional[k - 1])
+            G, xi, Xi = c.A, c.noise.mean.reshape(-1), c.noise.chol
+            means[k - 1] = G @ means[k] + xi
+            for l in range(k, T):
+                covs[(k - 1, l)] = G @ covs[(k, l)]
+                covs[(l, k - 1)] = covs[(k - 1, l)].T
+            covs[(k - 1, k - 1)] = G @ covs[(k, k)] @ G.T + Xi @ Xi.T
+        H = np.zeros((2, N))
+        H[0, 0] = H[1, 1] = 1.0  # coefficient-major: the state is the first d entries
+        mu = np.concatenate([H @ means[k] for k in range(T)])
+        S = np.block([[H @ covs[(k, l)] @ H.T for l in range(T)] for k in range(T)])
+        S = S + np.diag(np.concatenate([std[k] ** 2 for k in range(T)]))
+        expected = scipy.stats.multivariate_normal(mu, S, allow_singular=True).logpdf(data.reshape(-1))
+        assert np.isclose(total, expected, rtol=1e-8), (total, expected)
+
+
 def test_unused_import_guard():
     assert ssm.Normal is not None
