@@ -116,14 +116,17 @@ typedef struct pdeq_solution {
   int32_t* num_steps;    /* [B][T] accepted steps up to each checkpoint (entry 0 is 0) */
   int32_t* num_attempts; /* [B] attempted steps (accepted + rejected); may be NULL */
   int32_t* status;       /* [B] PDEQ_STATUS_* */
-  /* fixed-point smoother only (may be NULL): backward conditionals checkpoint k -> k-1, k = 1..T-1,
-     with the preconditioner folded in: x_{k-1} | x_k ~ N(G x_k + xi, Xi Xi^T). */
   /* optional (smoothers): the backward conditionals of the posterior (MarkovSequence.conditional), calibrated and
      in natural coordinates (preconditioner applied, cf. LatentCond.preconditioner_apply). Entry k maps grid
      point k to k-1: x_{k-1} | x_k ~ N(gain x_k + mean, chol chol^T); entry 0 is left untouched. */
   double* bw_gain;       /* blockdiag [B][T][d][n][n], isotropic [B][T][n][n] */
   double* bw_mean;       /* [B][T][n][d] */
   double* bw_chol;       /* like chol */
+  /* optional (fixed-interval smoother on a fixed grid): the calibrated filtering marginals
+     (SmoothingSolution.filtering, estimators_and_losses.py:464-467), laid out like mean / chol. Dense output of a
+     smoothing solution starts from them (pdeq_offgrid_marginals). */
+  double* filt_mean;
+  double* filt_chol;
   /* optional attempt log (NULL = off): for attempt a < trace_capacity of instance b,
      trace[(b * trace_capacity + a) * 4 + {0,1,2,3}] = {t_from, dt_used, error_power, accepted ? 1 : 0}.
      Lets a caller check the accepted-step sequence against the reference attempt by attempt. */
@@ -199,6 +202,20 @@ int pdeq_lml_timeseries(const pdeq_config* cfg, int64_t num_instances, int32_t n
                         const double* bw_gain, const double* bw_mean, const double* bw_chol,
                         const double* data, int64_t data_stride, const double* std, int64_t std_stride,
                         double* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ProbabilisticSolver.offgrid_marginals (probdiffeq/_probdiffeq/solvers.py:149-203) with
+   strategy_filter.interpolate_offgrid_marginals (estimators_and_losses.py:403-414) or
+   strategy_smoother_fixedinterval.interpolate_offgrid_marginals (:677-709): dense output. For each of the Q query
+   times (strictly inside the grid and not on it, as the reference requires; shared by the ensemble) the marginal is
+   extrapolated from the grid point to its left with the output scale of the grid point to its right; a smoothing
+   solution (cfg->strategy fixed-interval) additionally pulls the marginal of the right grid point back through the
+   new conditional and needs filt_mean / filt_chol. grid [T]; mean / chol / output_scale as in pdeq_solution;
+   prior_scale as in pdeq_problem (NULL = ones); out_mean [B][Q][n][d], out_chol [B][Q]([d])[n][n]. */
+int pdeq_offgrid_marginals(const pdeq_config* cfg, int64_t num_instances, int32_t num_gridpoints, const double* grid,
+                           int32_t num_queries, const double* queries, const double* mean, const double* chol,
+                           const double* filt_mean, const double* filt_chol, const double* output_scale,
+                           const double* prior_scale, int64_t prior_scale_stride, double* out_mean,
+                           double* out_chol, void* stream);
 
 /* Sum `n` doubles in place across the ranks of an NCCL communicator (ncclComm_t passed as void*):
    the ensemble log-marginal-likelihood reduction. The only collective on this path. */

@@ -212,6 +212,11 @@ class strategy_filter:
     def interpolate_fwd_at_t1(self, *, posterior_t1):
         return (posterior_t1, posterior_t1), InterpResult(posterior_t1, posterior_t1)
 
+    def interpolate_offgrid_marginals(self, *, posterior_t0, posterior_t1, transition_t0_t, transition_t_t1):
+        """:403-414: a filter extrapolates from the left grid point."""
+        _, interpolated = self.predict(posterior_t0, transition=transition_t0_t)
+        return (interpolated, interpolated), InterpResult(posterior_t1, interpolated)
+
 
 class _Smoother:
     """estimators_and_losses.py:424-470."""
@@ -286,6 +291,17 @@ class strategy_smoother_fixedinterval(_Smoother):
     def interpolate_fwd_at_t1(self, *, posterior_t1):
         return (posterior_t1.marginal, posterior_t1), InterpResult(posterior_t1, posterior_t1)
 
+    def interpolate_offgrid_marginals(self, *, posterior_t0, posterior_t1, transition_t0_t, transition_t_t1):
+        """:677-709: extrapolate the FILTERING distribution t0 -> t -> t1, then pull the (smoothed) marginal at t1
+        back through the new t1 -> t conditional. `posterior_t0` is the filtering marginal at t0."""
+        _, post = self.init_posterior(u=posterior_t0)
+        _, ext_t = self.predict(post, transition=transition_t0_t)
+        _, ext_t1 = self.predict(ext_t, transition=transition_t_t1)
+        rv_at_t = ext_t1.conditional.marginalise(posterior_t1.marginal)
+        sol_t = MarkovSequence(rv_at_t, ext_t.conditional, True)
+        sol_t1 = MarkovSequence(posterior_t1.marginal, ext_t1.conditional, True)
+        return (rv_at_t, sol_t), InterpResult(sol_t1, sol_t)
+
 
 # ------------------------------------------------------------------------------------------------
 # Solutions and solvers
@@ -357,6 +373,26 @@ class _ProbabilisticSolver:
         fx, _ = self.constraint.linearize(rv, None, damp=damp, t=t)
         noise = ssm.Normal(0.0 * fx.noise.mean, 0.0 * fx.noise.chol, fx.alg)
         return ssm.Cond(0.0 * fx.A, noise, 0.0 * fx.to_latent, 0.0 * fx.to_observed)
+
+    def offgrid_marginals(self, t, *, solution):
+        """solvers.py:149-203: the marginal at one time strictly inside the grid and not on it."""
+        if not self.strategy.is_suitable_for_offgrid_marginals:
+            raise NotImplementedError
+        index = int(np.searchsorted(solution.t, t))
+        full = solution.solution_full
+        posterior_t0 = full.filtering[index - 1] if isinstance(full, SmoothingSolution) else full[index - 1]
+        t0, t1 = solution.t[index - 1], solution.t[index]
+        # solver / solver_mle return T - 1 (identical) scales for T grid points (solvers.py:468-469, 744-745); JAX
+        # clamps the out-of-range index of the last interval, which is restated here
+        scales = np.asarray(solution.output_scale)
+        output_scale = scales[min(index, scales.shape[0] - 1)]
+        _, posterior_t1 = self.strategy.init_posterior(u=solution.u[index])
+        tr0 = solution.prior.transition(dt=t - t0, output_scale=output_scale)
+        tr1 = solution.prior.transition(dt=t1 - t, output_scale=output_scale)
+        (estimate, _), _ = self.strategy.interpolate_offgrid_marginals(
+            posterior_t0=posterior_t0, posterior_t1=posterior_t1, transition_t0_t=tr0, transition_t_t1=tr1
+        )
+        return estimate
 
     def interpolate_fwd(self, *, t, interp_from, interp_to):
         """solvers.py:205-269."""

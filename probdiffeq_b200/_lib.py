@@ -75,6 +75,8 @@ class Solution(C.Structure):
         ("bw_gain", C.c_void_p),
         ("bw_mean", C.c_void_p),
         ("bw_chol", C.c_void_p),
+        ("filt_mean", C.c_void_p),
+        ("filt_chol", C.c_void_p),
         ("trace", C.c_void_p),
         ("trace_capacity", C.c_int64),
     ]
@@ -124,6 +126,11 @@ SYMBOLS = {
         C.c_int,
         [_P(Config), C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
          C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
+    ),  # fmt: skip
+    "pdeq_offgrid_marginals": (
+        C.c_int,
+        [_P(Config), C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
     ),  # fmt: skip
     "pdeq_allreduce_sum_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pdeq_fp64_peak_probe": (C.c_int, [C.c_int32, _P(C.c_double), _P(C.c_double), C.c_void_p]),

@@ -295,6 +295,79 @@ __global__ void lml_timeseries_kernel(int64_t B, int T, int d, int blockdiag, in
   partial[gid] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Dense output: ProbabilisticSolver.offgrid_marginals (probdiffeq/_probdiffeq/solvers.py:149-203).
+// Thread (b, query, dimension). A filter extrapolates the marginal of the grid point to the left
+// (strategy_filter.interpolate_offgrid_marginals, estimators_and_losses.py:403-414); the fixed-interval smoother
+// extrapolates the FILTERING marginal t0 -> t -> t1 and pulls the smoothing marginal at t1 back through the
+// new t1 -> t conditional (:677-709). Both transitions use the output scale of the right grid point (:189-194).
+// ---------------------------------------------------------------------------------------------------
+template <int n, bool SMOOTH>
+__global__ void offgrid_kernel(const __grid_constant__ pdeq_config cfg, int64_t B, int T, int Q, int blockdiag,
+                               const double* __restrict__ grid, const double* __restrict__ queries,
+                               const double* __restrict__ mean, const double* __restrict__ chol,
+                               const double* __restrict__ filt_mean, const double* __restrict__ filt_chol,
+                               const double* __restrict__ output_scale, const double* __restrict__ prior_scale,
+                               int64_t prior_scale_stride, double* __restrict__ out_mean,
+                               double* __restrict__ out_chol) {
+  const int d = cfg.ode_dim;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= B * Q * d) return;
+  const int j = (int)(gid % d);
+  const int qi = (int)((gid / d) % Q);
+  const int64_t b = gid / ((int64_t)d * Q);
+  const double t = queries[qi];
+  int lo = 0, hi = T;  // searchsorted(grid, t): first index with grid[index] >= t
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (grid[mid] < t) lo = mid + 1;
+    else hi = mid;
+  }
+  const int i1 = min(max(lo, 1), T - 1), i0 = i1 - 1;
+  auto load = [&](const double* mu, const double* ch, int k, double (&m)[n], double (&L)[n][n]) {
+    const double* c = blockdiag ? ch + ((b * T + k) * (int64_t)d + j) * (n * n) : ch + (b * T + k) * (int64_t)(n * n);
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      m[i] = mu[((b * T + k) * n + i) * (int64_t)d + j];
+#pragma unroll
+      for (int cc = 0; cc < n; ++cc) L[i][cc] = (cc <= i) ? c[i * n + cc] : 0.0;
+    }
+  };
+  const double lam = prior_scale == nullptr ? 1.0 : prior_scale[b * prior_scale_stride + (blockdiag ? j : 0)];
+  const double sig = output_scale[blockdiag ? (b * T + i1) * (int64_t)d + j : b * T + i1] * lam;
+  const double dt0 = t - grid[i0], dt1 = grid[i1] - t;
+  double m0[n], L0[n][n], p[n], pinv[n], mt[n], Lt[n][n];
+  load(SMOOTH ? filt_mean : mean, SMOOTH ? filt_chol : chol, i0, m0, L0);
+  preconditioner<n>(dt0, cfg.inv_factorials, cfg.factorials, p, pinv);
+  predict_mean<n>(m0, p, pinv, cfg.sys_a, mt);
+  predict_chol<n>(L0, p, pinv, safe_sqrt(fabs(dt0)) * sig, cfg.sys_a, cfg.sys_q, Lt);
+  if (SMOOTH) {
+    double m1[n], L1[n][n], Lu[n][n], mo[n], Lo[n][n];
+    BlockCond<n> bw;
+    preconditioner<n>(dt1, cfg.inv_factorials, cfg.factorials, p, pinv);
+    revert_transition<n>(Lt, mt, p, pinv, safe_sqrt(fabs(dt1)) * sig, cfg.sys_a, cfg.sys_q, Lu, bw);
+    load(mean, chol, i1, m1, L1);
+    cond_marginalise<n>(bw, m1, L1, mo, Lo);
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      mt[i] = mo[i];
+#pragma unroll
+      for (int cc = 0; cc < n; ++cc) Lt[i][cc] = (cc <= i) ? Lo[i][cc] : 0.0;
+    }
+  }
+  const int64_t bq = b * Q + qi;
+#pragma unroll
+  for (int i = 0; i < n; ++i) out_mean[(bq * n + i) * (int64_t)d + j] = mt[i];
+  if (out_chol != nullptr && (blockdiag || j == 0)) {
+    double* co = blockdiag ? out_chol + (bq * d + j) * (int64_t)(n * n) : out_chol + bq * (int64_t)(n * n);
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+      for (int cc = 0; cc < n; ++cc) co[i * n + cc] = (cc <= i) ? Lt[i][cc] : 0.0;
+    }
+  }
+}
+
 __global__ void lml_reduce_kernel(int64_t B, int d, const double* __restrict__ partial, double* __restrict__ out) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
@@ -441,6 +514,63 @@ int pdeq_lml_timeseries(const pdeq_config* cfg, int64_t num_instances, int32_t n
   lml_reduce_kernel<<<(int)((num_instances + 127) / 128), 128, 0, st>>>(num_instances, cfg->ode_dim, partial, out);
   e = cudaGetLastError();
   if (e != cudaSuccess) return api_cuda_fail(e, "lml_timeseries (reduce)");
+  return 0;
+}
+
+int pdeq_offgrid_marginals(const pdeq_config* cfg, int64_t num_instances, int32_t num_gridpoints, const double* grid,
+                           int32_t num_queries, const double* queries, const double* mean, const double* chol,
+                           const double* filt_mean, const double* filt_chol, const double* output_scale,
+                           const double* prior_scale, int64_t prior_scale_stride, double* out_mean,
+                           double* out_chol, void* stream) {
+  int rc = api_validate(cfg);
+  if (rc != 0) return rc;
+  if (grid == nullptr || queries == nullptr || mean == nullptr || chol == nullptr || output_scale == nullptr ||
+      out_mean == nullptr)
+    return api_fail(-22, "NULL argument");
+  if (num_gridpoints < 2) return api_fail(-23, "offgrid_marginals needs at least two grid points");
+  // strategy_smoother_fixedpoint.is_suitable_for_offgrid_marginals is False (estimators_and_losses.py:519-523)
+  if (cfg->strategy == PDEQ_STRATEGY_FIXEDPOINT)
+    return api_fail(-10, "offgrid_marginals is not defined for the fixed-point smoother (the reference raises "
+                         "NotImplementedError); use a filter or the fixed-interval smoother");
+  const bool smooth = cfg->strategy != PDEQ_STRATEGY_FILTER;
+  if (smooth && (filt_mean == nullptr || filt_chol == nullptr))
+    return api_fail(-22, "a smoothing solution needs its filtering marginals (filt_mean / filt_chol)");
+  int fact = cfg->factorisation;
+  if (fact == PDEQ_FACT_DENSE && cfg->ode_dim == 1) fact = PDEQ_FACT_ISOTROPIC;
+  if (fact == PDEQ_FACT_DENSE) return api_fail(-10, "offgrid_marginals: dense factorisation with d > 1 not built");
+  if (num_instances == 0 || num_queries == 0) return 0;
+  const int64_t total = num_instances * (int64_t)num_queries * cfg->ode_dim;
+  const int threads = 64;
+  const int nblocks = (int)((total + threads - 1) / threads);
+  const int bd = fact == PDEQ_FACT_BLOCKDIAG;
+  cudaStream_t st = (cudaStream_t)stream;
+#define PDEQ_OFFGRID_CASE(NN)                                                                                       \
+  case NN:                                                                                                          \
+    if (smooth)                                                                                                     \
+      offgrid_kernel<NN, true><<<nblocks, threads, 0, st>>>(*cfg, num_instances, num_gridpoints, num_queries, bd,   \
+                                                            grid, queries, mean, chol, filt_mean, filt_chol,        \
+                                                            output_scale, prior_scale, prior_scale_stride,          \
+                                                            out_mean, out_chol);                                    \
+    else                                                                                                            \
+      offgrid_kernel<NN, false><<<nblocks, threads, 0, st>>>(*cfg, num_instances, num_gridpoints, num_queries, bd,  \
+                                                             grid, queries, mean, chol, filt_mean, filt_chol,       \
+                                                             output_scale, prior_scale, prior_scale_stride,         \
+                                                             out_mean, out_chol);                                   \
+    break;
+  switch (cfg->num_derivatives + 1) {
+    PDEQ_OFFGRID_CASE(2)
+    PDEQ_OFFGRID_CASE(3)
+    PDEQ_OFFGRID_CASE(4)
+    PDEQ_OFFGRID_CASE(5)
+    PDEQ_OFFGRID_CASE(6)
+    PDEQ_OFFGRID_CASE(7)
+    PDEQ_OFFGRID_CASE(8)
+    default:
+      return api_fail(-10, "offgrid_marginals: num_derivatives must be in 1..7");
+  }
+#undef PDEQ_OFFGRID_CASE
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return api_cuda_fail(e, "offgrid_marginals");
   return 0;
 }
 

@@ -163,6 +163,16 @@ struct GroupLoop {
     }
   }
 
+  // SmoothingSolution.filtering (estimators_and_losses.py:464-467): before the smoothing marginal replaces it, the
+  // forward pass's marginal of this lane's dimension moves to filt_mean / filt_chol, calibrated.
+  PDEQ_DI static void keep_filtering(const LoopArgs& a, long bt, int d, int j, double scale) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) a.sol.filt_mean[(bt * n + i) * (long)d + j] = a.sol.mean[(bt * n + i) * (long)d + j];
+    if (a.sol.filt_chol == nullptr || a.sol.chol == nullptr || (ISO && j != 0)) return;
+    const long off = ISO ? bt * (long)(n * n) : (bt * d + j) * (long)(n * n);
+    for (int e = 0; e < n * n; ++e) a.sol.filt_chol[off + e] = scale * a.sol.chol[off + e];
+  }
+
   PDEQ_DI static void write_chol(const LoopArgs& a, long bt, int d, int j, const double (&L)[n][n], double scale) {
     if (a.sol.chol == nullptr || (ISO && j != 0)) return;
     double* co = ISO ? a.sol.chol + bt * (long)(n * n) : a.sol.chol + (bt * d + j) * (long)(n * n);
@@ -410,6 +420,7 @@ struct GroupLoop {
               for (int k = T - 1; k >= 0; --k) {
                 const long bt = b * T + k;
                 double* mout = a.sol.mean + bt * (long)(n * d);
+                if (a.sol.filt_mean != nullptr) keep_filtering(a, bt, d, j, fin);
 #pragma unroll
                 for (int i = 0; i < n; ++i) mout[i * d + j] = mo[i];
                 write_chol(a, bt, d, j, Lo, fin);

@@ -148,6 +148,9 @@ def _alloc_solution(prior, T, want_chol=True, trace_capacity=0, want_posterior=F
         bufs["bw_gain"] = torch.zeros(chol_shape, **f64)
         bufs["bw_mean"] = torch.zeros((B, T, n, d), **f64)
         bufs["bw_chol"] = torch.zeros(chol_shape, **f64)
+        if want_posterior == "with_filtering":
+            bufs["filt_mean"] = torch.zeros((B, T, n, d), **f64)
+            bufs["filt_chol"] = torch.zeros(chol_shape, **f64)
     so = _lib.Solution()
     for k, v in bufs.items():
         setattr(so, k, _pdq._ptr(v))
@@ -178,7 +181,10 @@ def _wrap(prior, bufs, *, terminal: bool):
             marginal=_pdq.Normal(fact_u, pick(bufs["mean"][:, -1]), pick(bufs["chol"][:, -1])),
             conditional=_pdq.BackwardConditional(pick(bufs["bw_gain"]), pick(bufs["bw_mean"]), pick(bufs["bw_chol"])),
         )
-        full = _pdq.SmoothingSolution(posterior=post)
+        filtering = None
+        if "filt_mean" in bufs:
+            filtering = _pdq.Normal(fact_u, pick(bufs["filt_mean"]), pick(bufs["filt_chol"]))
+        full = _pdq.SmoothingSolution(posterior=post, filtering=filtering)
     sol = _pdq.ProbabilisticSolution(
         t=bufs["t"],
         u=_pdq.Normal(fact_u, bufs["mean"], bufs["chol"]),
@@ -187,6 +193,7 @@ def _wrap(prior, bufs, *, terminal: bool):
         num_attempts=bufs["num_attempts"],
         status=bufs["status"],
         solution_full=full,
+        prior=prior,
     )  # fmt: skip
     trace = bufs.get("trace")
     if terminal:
@@ -281,8 +288,9 @@ def solve_fixed_grid(*, solver):
             raise ValueError("grid must be one-dimensional (shared by the ensemble).")
         T = g.shape[0]
         pr, keep = _problem(prior, solver.constraint.ode)
-        so, bufs = _alloc_solution(prior, T, want_cholesky, 0,
-                                   _want_posterior(want_posterior, solver, prior, T, want_cholesky))
+        wp = _want_posterior(want_posterior, solver, prior, T, want_cholesky)
+        # fixed grid + fixed-interval smoother: keep the filtering marginals too (dense output starts from them)
+        so, bufs = _alloc_solution(prior, T, want_cholesky, 0, "with_filtering" if wp else False)
         if B > 0:
             ws, nbytes = _workspace(cfg, B, T, prior.tcoeffs.device)
             rc = _lib.load().pdeq_solve_fixed_grid(

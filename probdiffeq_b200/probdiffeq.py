@@ -386,6 +386,60 @@ class _Solver:
     def __repr__(self):
         return f"{self.kind}(strategy={self.strategy!r}, constraint={self.constraint!r})"
 
+    def offgrid_marginals(self, t, *, solution):
+        """Dense output (reference: solvers.py:149-203): marginals at times strictly inside the grid and not on it.
+
+        ``t`` is a scalar or a (Q,) array shared by the ensemble; ``solution`` comes from `solve_adaptive_save_at`
+        or `solve_fixed_grid` (grid shared by the ensemble). Returns a `Normal` with mean (B, Q, n, d) -- the Q axis
+        is dropped for a scalar ``t``, the B axis for an unbatched solve. Filters extrapolate from the grid point to
+        the left; the fixed-interval smoother also conditions on the right one. The fixed-point smoother raises
+        NotImplementedError like the reference (estimators_and_losses.py:519-523)."""
+        kind = self.strategy.kind
+        if kind == "fixedpoint":
+            raise NotImplementedError
+        prior = getattr(solution, "prior", None)
+        if prior is None:
+            raise ValueError("solution carries no prior; pass the object a solve_* call returned")
+        mean, chol, scale, grid = solution.u.mean_flat, solution.u.cholesky_flat, solution.output_scale, solution.t
+        if chol is None:
+            raise ValueError("offgrid_marginals needs the Cholesky factors (want_cholesky=True)")
+        unbatched = mean.ndim == 3
+        if unbatched:
+            mean, chol, scale, grid = mean[None], chol[None], scale[None], grid[None]
+        B, T, n, d = mean.shape
+        fact = solution.u.factorisation
+        filt_mean = filt_chol = None
+        if kind != "filter":
+            full = solution.solution_full
+            if full is None or full.filtering is None:
+                raise ValueError("the smoothing solution carries no filtering marginals (want_posterior=True)")
+            filt_mean, filt_chol = full.filtering.mean_flat, full.filtering.cholesky_flat
+            if unbatched:
+                filt_mean, filt_chol = filt_mean[None], filt_chol[None]
+        scalar_t = (t.ndim if isinstance(t, torch.Tensor) else np.ndim(t)) == 0
+        tq = _as_device_f64(t).reshape(-1).contiguous()
+        Q = tq.shape[0]
+        g0 = grid[0].contiguous() if B > 0 else torch.zeros((T,), dtype=torch.float64, device=mean.device)
+        cfg = _make_config(fact=fact, nu=n - 1, d=d, vf=self.constraint.ode, strategy=_lib.STRATEGY[kind])
+        out_mean = torch.empty((B, Q, n, d), dtype=torch.float64, device=mean.device)
+        out_chol = torch.empty((B, Q, *chol.shape[2:]), dtype=torch.float64, device=mean.device)
+        ps = prior.output_scale
+        ps_stride = 0 if ps is None or ps.shape[0] == 1 else ps.shape[1]
+        if B > 0:
+            rc = _lib.load().pdeq_offgrid_marginals(
+                C.byref(cfg), B, T, _ptr(g0), Q, _ptr(tq), _ptr(mean.contiguous()), _ptr(chol.contiguous()),
+                _ptr(filt_mean.contiguous()) if filt_mean is not None else None,
+                _ptr(filt_chol.contiguous()) if filt_chol is not None else None,
+                _ptr(scale.contiguous()), _ptr(ps) if ps is not None else None, ps_stride,
+                _ptr(out_mean), _ptr(out_chol), _stream(),
+            )  # fmt: skip
+            _lib.check(rc, "pdeq_offgrid_marginals")
+        if scalar_t:
+            out_mean, out_chol = out_mean[:, 0], out_chol[:, 0]
+        if unbatched:
+            out_mean, out_chol = out_mean[0], out_chol[0]
+        return Normal(fact, out_mean, out_chol)
+
 
 class solver(_Solver):
     """Uncalibrated solver (reference: solvers.py:636-767)."""
@@ -533,6 +587,7 @@ class ProbabilisticSolution:
     status: torch.Tensor
     solution_full: Any = None
     trace: Any = None
+    prior: Any = None
 
     def _index(self, fn):
         return ProbabilisticSolution(
@@ -544,6 +599,7 @@ class ProbabilisticSolution:
             num_attempts=self.num_attempts,
             status=self.status,
             solution_full=self.solution_full,
+            prior=self.prior,
         )  # fmt: skip
 
 

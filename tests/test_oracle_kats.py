@@ -237,6 +237,27 @@ def test_fixedinterval_smoother_on_a_fixed_grid_reference_vs_aligned():
         assert np.all(ali.u_std <= filt.u_std * (1 + 1e-9) + 1e-14)
 
 
+@pytest.mark.parametrize("kind", ["isotropic", "blockdiag", "dense"])
+@pytest.mark.parametrize("smoother", [False, True])
+def test_offgrid_marginals_match_the_save_at_solution(kind, smoother):
+    """test_probdiffeq/test_dense_output/test_offgrid_marginals_vs_solve_and_save_at.py:51-85 (ts1, solver_dynamic)."""
+    every_strategy = pdq.strategy_smoother_fixedinterval if smoother else pdq.strategy_filter
+    at_strategy = pdq.strategy_smoother_fixedpoint if smoother else pdq.strategy_filter
+    prior, slv_every, err = _setup(kind, "ts1", "solver_dynamic", every_strategy, "error_residual_std", num=2)
+    _, slv_at, err_at = _setup(kind, "ts1", "solver_dynamic", at_strategy, "error_residual_std", num=2)
+    ts = np.linspace(0.0, 2.0, 5)
+    every = ivpsolve.solve_adaptive_save_every_step(solver=slv_every, error=err)(
+        prior, t0=0.0, t1=2.0, atol=1e-2, rtol=1e-2
+    )
+    at = ivpsolve.solve_adaptive_save_at(solver=slv_at, error=err_at)(prior, save_at=ts, atol=1e-2, rtol=1e-2)
+    for k, t in enumerate(ts[1:-1], start=1):
+        rv = slv_every.offgrid_marginals(t, solution=every)
+        m1, C1 = rv.cov_dense()
+        m2, C2 = at.u[k].cov_dense()
+        assert np.allclose(m1, m2, rtol=1e-8, atol=1e-10), (kind, smoother, k)
+        assert np.allclose(C1, C2, rtol=1e-6, atol=1e-12), (kind, smoother, k)
+
+
 def test_save_at_is_invariant_to_cutting_the_grid():
     """test_probdiffeq/test_dense_output/test_behaviour_close_to_t1.py:59-94: solving to [t0, t1] equals solving
     on a grid that contains t1 and reading off t1 (filter, no clipping)."""
