@@ -203,6 +203,16 @@ int pdeq_lml_timeseries(const pdeq_config* cfg, int64_t num_instances, int32_t n
                         const double* data, int64_t data_stride, const double* std, int64_t std_stride,
                         double* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* MarkovSequence.sample (probdiffeq/_probdiffeq/estimators_and_losses.py:233-271): joint samples of the posterior
+   at all T grid points, drawn backwards through the conditionals. The standard-normal numbers are the caller's
+   (`base`: isotropic [B][S][T][n] -- one draw per coefficient shared by all dimensions, as
+   IsotropicNormal.sample_flat, ssm_impl_isotropic.py:255-258 -- block-diagonal [B][S][T][d][n]), so the
+   arithmetic is reproducible whatever generator made them. mean / chol / bw_* as in pdeq_lml_timeseries.
+   out [B][S][T][n][d]. */
+int pdeq_sample_posterior(const pdeq_config* cfg, int64_t num_instances, int32_t num_gridpoints, int32_t num_samples,
+                          const double* mean, const double* chol, const double* bw_gain, const double* bw_mean,
+                          const double* bw_chol, const double* base, double* out, void* stream);
+
 /* ProbabilisticSolver.offgrid_marginals (probdiffeq/_probdiffeq/solvers.py:149-203) with
    strategy_filter.interpolate_offgrid_marginals (estimators_and_losses.py:403-414) or
    strategy_smoother_fixedinterval.interpolate_offgrid_marginals (:677-709): dense output. For each of the Q query

@@ -157,6 +157,28 @@ class MarkovSequence:
             return MarkovSequence(self.marginal[-1], self.conditional, self.reverse)
         return self
 
+    def sample(self, base):
+        """:233-271 with the random draws made explicit: `base[k]` are the standard-normal numbers `sample_flat`
+        would draw at grid point k -- shape (n,) isotropic (ssm_impl_isotropic.py:255-258: ONE draw per coefficient,
+        shared by all dimensions), (d, n) block-diagonal (ssm_impl_blockdiag.py:343-351), (n d,) dense.
+        Returns the sampled states, one per grid point, in the layout of `Normal.mean`."""
+        seq = self.remove_filtering_distributions()
+        assert seq.reverse
+
+        def draw(rv, eps):
+            if rv.alg.name == "isotropic":
+                return rv.mean + (rv.chol @ eps)[:, None]
+            if rv.alg.name == "blockdiag":
+                return rv.mean + np.einsum("djk,dk->dj", rv.chol, eps)
+            return rv.mean + rv.chol @ eps
+
+        x = draw(seq.marginal, base[-1])
+        out = [x]
+        for k in range(len(seq.conditional) - 1, -1, -1):
+            x = draw(seq.conditional[k].apply_flat(x), base[k])
+            out.insert(0, x)
+        return out
+
     def evaluate_lml(self, u, *, model, average_pdfs, solve=None):
         """:180-218: backward scan -- observe the terminal state, then alternately step back through a
         conditional and observe. `u[k]`, `model[k]` belong to grid point k; conditional[k-1] maps k -> k-1."""

@@ -127,6 +127,11 @@ SYMBOLS = {
         [_P(Config), C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
          C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p],
     ),  # fmt: skip
+    "pdeq_sample_posterior": (
+        C.c_int,
+        [_P(Config), C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.c_void_p, C.c_void_p, C.c_void_p],
+    ),  # fmt: skip
     "pdeq_offgrid_marginals": (
         C.c_int,
         [_P(Config), C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -368,6 +368,64 @@ __global__ void offgrid_kernel(const __grid_constant__ pdeq_config cfg, int64_t 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// MarkovSequence.sample (probdiffeq/_probdiffeq/estimators_and_losses.py:233-271) with the standard-normal draws
+// supplied by the caller: x_{T-1} = m + L eps_{T-1}, then x_{k-1} = G_k x_k + xi_k + Xi_k eps_{k-1} backwards over
+// the stored conditionals (natural coordinates). Thread (b, sample, dimension). base is [B][S][T][n] for the
+// isotropic model -- one draw per coefficient shared by all dimensions, as IsotropicNormal.sample_flat does
+// (ssm_impl_isotropic.py:255-258) -- and [B][S][T][d][n] for the block-diagonal one (ssm_impl_blockdiag.py:343-351).
+// ---------------------------------------------------------------------------------------------------
+template <int n>
+__global__ void sample_kernel(int64_t B, int S, int T, int d, int blockdiag, const double* __restrict__ mean,
+                              const double* __restrict__ chol, const double* __restrict__ bw_gain,
+                              const double* __restrict__ bw_mean, const double* __restrict__ bw_chol,
+                              const double* __restrict__ base, double* __restrict__ out) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= B * S * d) return;
+  const int j = (int)(gid % d);
+  const int si = (int)((gid / d) % S);
+  const int64_t b = gid / ((int64_t)d * S);
+  const int64_t bs = b * S + si;
+  auto mat = [&](const double* p, int k) {
+    return blockdiag ? p + ((b * T + k) * (int64_t)d + j) * (n * n) : p + (b * T + k) * (int64_t)(n * n);
+  };
+  auto eps = [&](int k) { return blockdiag ? base + ((bs * T + k) * (int64_t)d + j) * n : base + (bs * T + k) * (int64_t)n; };
+  double x[n];
+  {
+    const double* L = mat(chol, T - 1);
+    const double* e = eps(T - 1);
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int c = 0; c < n; ++c) acc = (c <= i) ? fma(L[i * n + c], e[c], acc) : acc;
+      x[i] = mean[((b * T + (T - 1)) * n + i) * (int64_t)d + j] + acc;
+      out[((bs * T + (T - 1)) * n + i) * (int64_t)d + j] = x[i];
+    }
+  }
+  for (int k = T - 1; k >= 1; --k) {
+    const double* G = mat(bw_gain, k);
+    const double* X = mat(bw_chol, k);
+    const double* e = eps(k - 1);
+    double y[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      double acc = 0.0, nz = 0.0;
+#pragma unroll
+      for (int c = 0; c < n; ++c) {
+        acc = fma(G[i * n + c], x[c], acc);
+        nz = (c <= i) ? fma(X[i * n + c], e[c], nz) : nz;
+      }
+      y[i] = (acc + bw_mean[((b * T + k) * n + i) * (int64_t)d + j]) + nz;
+    }
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      x[i] = y[i];
+      out[((bs * T + (k - 1)) * n + i) * (int64_t)d + j] = x[i];
+    }
+  }
+}
+
 __global__ void lml_reduce_kernel(int64_t B, int d, const double* __restrict__ partial, double* __restrict__ out) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
@@ -514,6 +572,46 @@ int pdeq_lml_timeseries(const pdeq_config* cfg, int64_t num_instances, int32_t n
   lml_reduce_kernel<<<(int)((num_instances + 127) / 128), 128, 0, st>>>(num_instances, cfg->ode_dim, partial, out);
   e = cudaGetLastError();
   if (e != cudaSuccess) return api_cuda_fail(e, "lml_timeseries (reduce)");
+  return 0;
+}
+
+int pdeq_sample_posterior(const pdeq_config* cfg, int64_t num_instances, int32_t num_gridpoints, int32_t num_samples,
+                          const double* mean, const double* chol, const double* bw_gain, const double* bw_mean,
+                          const double* bw_chol, const double* base, double* out, void* stream) {
+  int rc = api_validate(cfg);
+  if (rc != 0) return rc;
+  if (mean == nullptr || chol == nullptr || bw_gain == nullptr || bw_mean == nullptr || bw_chol == nullptr ||
+      base == nullptr || out == nullptr)
+    return api_fail(-22, "NULL argument");
+  if (num_gridpoints < 1) return api_fail(-23, "num_gridpoints must be >= 1");
+  int fact = cfg->factorisation;
+  if (fact == PDEQ_FACT_DENSE && cfg->ode_dim == 1) fact = PDEQ_FACT_ISOTROPIC;
+  if (fact == PDEQ_FACT_DENSE) return api_fail(-10, "sample_posterior: dense factorisation with d > 1 not built");
+  if (num_instances == 0 || num_samples == 0) return 0;
+  const int64_t total = num_instances * (int64_t)num_samples * cfg->ode_dim;
+  const int threads = 128;
+  const int nblocks = (int)((total + threads - 1) / threads);
+  const int bd = fact == PDEQ_FACT_BLOCKDIAG;
+#define PDEQ_SAMPLE_CASE(NN)                                                                                    \
+  case NN:                                                                                                      \
+    sample_kernel<NN><<<nblocks, threads, 0, (cudaStream_t)stream>>>(num_instances, num_samples, num_gridpoints, \
+                                                                     cfg->ode_dim, bd, mean, chol, bw_gain,     \
+                                                                     bw_mean, bw_chol, base, out);              \
+    break;
+  switch (cfg->num_derivatives + 1) {
+    PDEQ_SAMPLE_CASE(2)
+    PDEQ_SAMPLE_CASE(3)
+    PDEQ_SAMPLE_CASE(4)
+    PDEQ_SAMPLE_CASE(5)
+    PDEQ_SAMPLE_CASE(6)
+    PDEQ_SAMPLE_CASE(7)
+    PDEQ_SAMPLE_CASE(8)
+    default:
+      return api_fail(-10, "sample_posterior: num_derivatives must be in 1..7");
+  }
+#undef PDEQ_SAMPLE_CASE
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return api_cuda_fail(e, "sample_posterior");
   return 0;
 }
 

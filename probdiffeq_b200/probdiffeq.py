@@ -623,6 +623,53 @@ class MarkovSequence:
     conditional: BackwardConditional
     reverse: bool = True
 
+    def sample(self, key=None, *, shape: tuple = (), base=None):
+        """Joint posterior samples at all grid points (reference: `MarkovSequence.sample`, :233-271).
+
+        ``key`` seeds a `torch.Generator` on the device (an int, or a Generator) -- the reference's JAX PRNG stream
+        is not reproduced, the arithmetic given the normal draws is. Alternatively pass the draws as ``base``:
+        (B, *shape, T, n) for the isotropic model (one draw per coefficient shared by all dimensions, like
+        `IsotropicNormal.sample_flat`), (B, *shape, T, d, n) for the block-diagonal one. Returns a list over Taylor
+        coefficients of tensors (B, *shape, T, d); the B axis is absent for an unbatched posterior."""
+        mean, chol = self.marginal.mean_flat, self.marginal.cholesky_flat
+        gain, cmean, cchol = self.conditional.gain, self.conditional.mean, self.conditional.cholesky
+        unbatched = mean.ndim == 2
+        if unbatched:
+            mean, chol, gain, cmean, cchol = mean[None], chol[None], gain[None], cmean[None], cchol[None]
+        B, n, d = mean.shape
+        T = cmean.shape[1]
+        fact = self.marginal.factorisation
+        core = (T, n) if fact == "isotropic" else (T, d, n)
+        if base is None:
+            gen = key if isinstance(key, torch.Generator) else torch.Generator(device=mean.device)
+            if not isinstance(key, torch.Generator):
+                gen.manual_seed(0 if key is None else int(key))
+            base_t = torch.randn((B, *shape, *core), dtype=torch.float64, device=mean.device, generator=gen)
+        else:
+            base_t = _as_device_f64(base)
+            if unbatched:
+                base_t = base_t[None]
+            shape = tuple(base_t.shape[1 : base_t.ndim - len(core)])
+            if tuple(base_t.shape) != (B, *shape, *core):
+                raise ValueError(f"base must have shape (B, *shape, {core}); got {tuple(base_t.shape)}")
+        S = int(np.prod(shape)) if len(shape) > 0 else 1
+        mean_t = torch.zeros((B, T, n, d), dtype=torch.float64, device=mean.device)
+        mean_t[:, -1] = mean
+        chol_t = torch.zeros((B, T, *chol.shape[1:]), dtype=torch.float64, device=mean.device)
+        chol_t[:, -1] = chol
+        out = torch.empty((B, S, T, n, d), dtype=torch.float64, device=mean.device)
+        cfg = _make_config(fact=fact, nu=n - 1, d=d, vf=VectorField("linear", params=[1.0]))
+        if B > 0:
+            rc = _lib.load().pdeq_sample_posterior(
+                C.byref(cfg), B, T, S, _ptr(mean_t), _ptr(chol_t), _ptr(gain.contiguous()), _ptr(cmean.contiguous()),
+                _ptr(cchol.contiguous()), _ptr(base_t.reshape(B, S, *core).contiguous()), _ptr(out), _stream(),
+            )  # fmt: skip
+            _lib.check(rc, "pdeq_sample_posterior")
+        out = out.reshape(B, *shape, T, n, d)
+        if unbatched:
+            out = out[0]
+        return _CoefficientList(out, out.ndim - 2)
+
 
 @dataclasses.dataclass
 class SmoothingSolution:

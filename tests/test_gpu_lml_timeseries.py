@@ -133,3 +133,60 @@ def test_unbatched_solve_returns_an_unbatched_posterior(cuda):
         ssm.prior_wiener_integrated(tcoeffs), save_at=np.linspace(0, 2, 5), atol=1e-3, rtol=1e-3
     )
     assert sol_f.solution_full is None
+
+
+@pytest.mark.parametrize("fact", ["isotropic", "blockdiag"])
+def test_posterior_samples_match_the_oracle_given_the_same_draws(cuda, fact):
+    """MarkovSequence.sample (estimators_and_losses.py:233-271; shapes as in tests/test_probdiffeq/test_sample.py:
+    36-45): with the standard-normal draws supplied, the sampled trajectories equal the oracle's."""
+    import torch
+
+    s = H.spec(fact=fact, strategy="fixedpoint", solver="solver_mle", error="residual_std", control="i", clip_dt=False)
+    B, T, d, n = 3, 12, 2, 5
+    params, u0 = H.lv_ensemble(B, seed=43)
+    p_pdq, p_ivp, vf, ssm, slv, err, ctrl = H.product_build(s, params)
+    tcoeffs, _ = p_pdq.jetexpand_ode_padded_scan(num=4)(vf, (u0,), t=0.0)
+    save_at = np.linspace(0.0, 3.0, T)
+    sol = p_ivp.solve_adaptive_save_at(solver=slv, error=err, control=ctrl)(
+        ssm.prior_wiener_integrated(tcoeffs), save_at=save_at, atol=1e-3, rtol=1e-3
+    )
+    post = sol.solution_full.posterior
+    rng = np.random.Generator(np.random.PCG64(7))
+    core = (T, n) if fact == "isotropic" else (T, d, n)
+    base = rng.normal(size=(B, 2, 3, *core))
+    smp = post.sample(base=base)
+    torch.cuda.synchronize()
+    assert len(smp) == n and smp[0].shape == (B, 2, 3, T, d)
+    tc = tcoeffs.cpu().numpy()
+    for b in range(B):
+        osol, _ = H.oracle_solve_save_at(s, tc[b], params[b], save_at, 1e-3, 1e-3)
+        opost = osol.solution_full.posterior
+        # A Cholesky factor is unique only up to the signs of its columns (LAPACK's reflector signs depend on the
+        # row order of the stacked matrix, and the product triangularises a row-permuted stack), and L eps depends
+        # on them. Feed the oracle the same draws with the product's column signs.
+        onat = _oracle_natural_conditionals(opost.remove_filtering_distributions())
+        omarg = opost.remove_filtering_distributions().marginal.chol
+        sign = np.ones((T, *core[1:]))
+
+        def colsign(Lp, Lo):
+            sp, so = np.sign(np.diagonal(Lp, axis1=-1, axis2=-2)), np.sign(np.diagonal(Lo, axis1=-1, axis2=-2))
+            return np.where(sp * so == 0, 1.0, sp * so)
+
+        sign[T - 1] = colsign(post.marginal.cholesky_flat[b].cpu().numpy(), omarg)
+        for k in range(1, T):
+            sign[k - 1] = colsign(post.conditional.cholesky[b, k].cpu().numpy(), onat[k - 1][2])
+        for idx in ((0, 0), (1, 2)):
+            ref = opost.sample(base[b][idx] * sign)  # list over grid points of (n, d) / (d, n)
+            ref = np.stack([x if fact == "isotropic" else x.T for x in ref])  # (T, n, d)
+            got = smp.flat[b][idx].cpu().numpy()
+            for i in range(n):
+                assert _rel(got[:, i], ref[:, i]) < (1e-7 if i <= 1 else 1e-4), (b, idx, i)
+    # seeded draws: reproducible, of the requested shape, and centred on the smoothing mean
+    s1 = post.sample(3, shape=(256,))
+    s2 = post.sample(3, shape=(256,))
+    assert s1[0].shape == (B, 256, T, d) and torch.equal(s1.flat, s2.flat)
+    assert not torch.equal(s1.flat, post.sample(4, shape=(256,)).flat)
+    dev = (s1[0].mean(dim=1) - sol.u.mean[0]).abs() / (sol.u.std[0].reshape(B, T, -1) + 1e-12)
+    assert float(dev.max()) < 0.5  # |sample mean - mean| well within one standard deviation
+    one = post.sample(1)
+    assert one[0].shape == (B, T, d)

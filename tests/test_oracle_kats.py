@@ -362,5 +362,24 @@ def test_lml_timeseries_matches_joint_gaussian():
         assert np.isclose(total, expected, rtol=1e-8), (total, expected)
 
 
+def test_posterior_sample_with_zero_draws_is_the_smoothing_mean_and_has_the_right_spread():
+    """estimators_and_losses.py:233-271 with explicit draws: zero draws walk the means backwards; unit draws, averaged,
+    reproduce the smoothing covariance of the state at a grid point."""
+    rng = np.random.default_rng(3)
+    for kind in ("isotropic", "blockdiag", "dense"):
+        prior, slv, err = _setup(kind, "ts0", "solver", pdq.strategy_smoother_fixedpoint, "error_residual_std", num=2)
+        sol = ivpsolve.solve_adaptive_save_at(solver=slv, error=err)(prior, save_at=np.linspace(0, 2, 5), atol=1e-2, rtol=1e-2)
+        post = sol.solution_full.posterior
+        shape = {"isotropic": (5, 3), "blockdiag": (5, 2, 3), "dense": (5, 6)}[kind]
+        zero = post.sample(np.zeros(shape))
+        for k in range(5):
+            assert np.allclose(zero[k], sol.u[k].mean, rtol=1e-9, atol=1e-12), (kind, k)
+        if kind == "blockdiag":
+            draws = np.stack([np.stack(post.sample(rng.normal(size=shape)))[2] for _ in range(4000)])  # (S, d, n)
+            emp = np.einsum("sdi,sdj->dij", draws - draws.mean(0), draws - draws.mean(0)) / 4000
+            cov = sol.u[2].chol @ np.swapaxes(sol.u[2].chol, -1, -2)
+            assert np.allclose(emp, cov, rtol=0.2, atol=0.05 * np.abs(cov).max())
+
+
 def test_unused_import_guard():
     assert ssm.Normal is not None
