@@ -93,6 +93,13 @@ typedef struct pdeq_config {
   double sys_q[PDEQ_MAX_COEFFS][PDEQ_MAX_COEFFS];
   double factorials[PDEQ_MAX_COEFFS + 1]; /* factorials[k] = k! as the reference evaluates it */
   double inv_factorials[PDEQ_MAX_COEFFS + 1]; /* 1 / factorials[k], so the kernels multiply instead of divide */
+  /* Optional (all zeros = off). error_state_std applies Bayes' rule to the zero-error extrapolation
+     (solvers.py:1070-1086), whose factor is diag(|p|) sqrt(dt) lambda q: a constant matrix with scaled columns. For
+     the ts0 constraint (h = e_order) and damp == 0 the triangularisation R = qr_r([[0, 0], [(h q)^T, q^T]])
+     therefore commutes with the scaling, and the kernels need only err_const[0] = R[0][0] (observed factor) and
+     err_const[1 + i] = ||R[1:2+i, 1+i]|| (std of coefficient i), times |p_order| resp. |p_i| times
+     sqrt(dt) lambda. Computed on the host from sys_q (probdiffeq_b200/_iwp.py). */
+  double err_const[PDEQ_MAX_COEFFS + 1];
 } pdeq_config;
 
 /* Inputs shared by the loop entry points. A `*_stride` of 0 broadcasts one row to all instances. */

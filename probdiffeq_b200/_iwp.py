@@ -34,6 +34,26 @@ def _hilbert_cholesky(n: int) -> np.ndarray:
 
 
 @functools.lru_cache(maxsize=None)
+def error_constants(num_derivatives: int, order: int) -> np.ndarray:
+    """Constants of `error_state_std` for the ts0 constraint and damp = 0 (see `pdeq_config.err_const`).
+
+    The estimator's Bayes rule (reference solvers.py:1070-1086) triangularises [[0, 0], [(h L)^T, L^T]] with
+    L = diag(|p|) sqrt(dt) lambda q and h = e_order; column scalings commute with the triangularisation, so only
+    R = qr_r([[0, 0], [q[order, :]^T, q^T]]) is needed: entry 0 is R[0, 0], entry 1 + i the norm of R[1:2+i, 1+i]."""
+    _, q, _ = system_matrices(num_derivatives)
+    n = num_derivatives + 1
+    m = np.zeros((n + 1, n + 1))
+    m[1:, 0] = q[order, :]
+    m[1:, 1:] = q.T
+    r = np.linalg.qr(m, mode="r")
+    out = np.zeros(n + 1)
+    out[0] = r[0, 0]
+    for i in range(n):
+        out[1 + i] = np.linalg.norm(r[1 : 2 + i, 1 + i])
+    return out
+
+
+@functools.lru_cache(maxsize=None)
 def system_matrices(num_derivatives: int) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
     """(A, Q, factorials): flipped Pascal matrix, Cholesky factor of the flipped Hilbert matrix, k!."""
     n = num_derivatives + 1

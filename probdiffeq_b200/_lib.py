@@ -47,6 +47,7 @@ class Config(C.Structure):
         ("sys_q", (C.c_double * MAX_COEFFS) * MAX_COEFFS),
         ("factorials", C.c_double * (MAX_COEFFS + 1)),
         ("inv_factorials", C.c_double * (MAX_COEFFS + 1)),
+        ("err_const", C.c_double * (MAX_COEFFS + 1)),
     ]
 
 

@@ -565,14 +565,30 @@ struct GroupLoop {
             ref = fmax(fabs(m[0]), fabs(mn[0]));
           } else {
             const int idx = cfg.derivative_idx;
-            double Lc[n][n], g_unused[n], rye;
+            double rye, sd;
+            if (TS0 && a.damp == 0.0 && cfg.err_const[0] != 0.0) {
+              // constant matrix with scaled columns: no triangularisation needed (pdeq_config.err_const)
+              double pq = 0.0, pi = 0.0, ci = 0.0;
 #pragma unroll
-            for (int i = 0; i < n; ++i) {
+              for (int i = 0; i < n; ++i) {
+                pq = (i == q) ? fabs(p[i]) : pq;
+                pi = (i == idx) ? fabs(p[i]) : pi;
+                ci = (i == idx) ? cfg.err_const[1 + i] : ci;
+              }
+              const double s = sq * prior;
+              rye = cfg.err_const[0] * (pq * s);
+              sd = ci * (pi * s);
+            } else {
+              double Lc[n][n], g_unused[n];
 #pragma unroll
-              for (int c = 0; c <= i; ++c) Lc[i][c] = 0.0;
+              for (int i = 0; i < n; ++i) {
+#pragma unroll
+                for (int c = 0; c <= i; ++c) Lc[i][c] = 0.0;
+              }
+              revert_obs<n, q, TS0>(Lq, h, a.damp, rye, g_unused, Lc);
+              sd = row_norm<n>(Lc, idx);
             }
-            revert_obs<n, q, TS0>(Lq, h, a.damp, rye, g_unused, Lc);
-            err = whitened(g, mobs * fast_rcp(rye), active, inv_sqrt_d) * row_norm<n>(Lc, idx);
+            err = whitened(g, mobs * fast_rcp(rye), active, inv_sqrt_d) * sd;
             double a0 = 0.0, a1 = 0.0;
 #pragma unroll
             for (int i = 0; i < n; ++i) {

@@ -452,7 +452,23 @@ struct ThreadLoop {
           // solvers.py:1070-1086: Bayes rule on the zero-error extrapolation, std of one coefficient
           const int idx = cfg.derivative_idx;
           double rye[NB], sd[NB];
-          if (idx == 0) {
+          if (TS0 && a.damp == 0.0 && cfg.err_const[0] != 0.0) {
+            // The zero-error extrapolation's factor is a constant matrix with scaled columns, and column scalings
+            // commute with the triangularisation (pdeq_config.err_const): no reflector is needed at all.
+            double pq = 0.0, pi = 0.0, ci = 0.0;
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              pq = (i == q) ? fabs(p[i]) : pq;
+              pi = (i == idx) ? fabs(p[i]) : pi;
+              ci = (i == idx) ? cfg.err_const[1 + i] : ci;
+            }
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+              const double s = sq * prior[k];
+              rye[k] = cfg.err_const[0] * (pq * s);
+              sd[k] = ci * (pi * s);
+            }
+          } else if (idx == 0) {
             // common case: only R_Y and the first row of the corrected factor are needed, which lets the
             // compiler drop all but the first two reflectors of the (n+1)x(n+1) triangularisation
 #pragma unroll

@@ -160,6 +160,9 @@ def _make_config(*, fact: str, nu: int, d: int, vf: VectorField, **kw) -> _lib.C
     for k in range(n + 1):
         cfg.factorials[k] = facts[k]
         cfg.inv_factorials[k] = 1.0 / facts[k]
+    if vf.order <= nu:
+        for k, c in enumerate(_iwp.error_constants(nu, vf.order)):
+            cfg.err_const[k] = c
     return cfg
 
 
