@@ -80,18 +80,20 @@ struct K1Registrar {
 // ---------------------------------------------------------------------------------------------------
 struct K2Plan {
   bool cta;
+  int mode;  // GroupLoop MODE
   int threads, groups_per_cta, grid;
   size_t smem_bytes, ring_bytes_per_group;
 };
 
 template <class VF, int NU, int FACT, bool TS0, bool FP>
 cudaError_t k2_plan(const pdeq_config& cfg, int64_t B, int32_t T, bool needs_interp, K2Plan* plan) {
-  using GL = GroupLoop<VF, NU, FACT, TS0, FP, false>;
+  using GL = GroupLoop<VF, NU, FACT, TS0, FP, 0>;
   const int d = cfg.ode_dim;
   const size_t per_group = GL::smem_doubles_per_group(d, needs_interp) * sizeof(double);
   plan->cta = d > 32;
+  plan->mode = d <= 32 ? 0 : (d <= K2_CTA_THREADS ? 1 : 2);
   if (plan->cta) {
-    using GC = GroupLoop<VF, NU, FACT, TS0, FP, true>;
+    using GC = GroupLoop<VF, NU, FACT, TS0, FP, 2>;
     plan->threads = std::min(K2_CTA_THREADS, ((d + 31) / 32) * 32);
     if ((d + plan->threads - 1) / plan->threads > GC::MAXR) return cudaErrorInvalidValue;
     plan->groups_per_cta = 1;
@@ -106,13 +108,18 @@ cudaError_t k2_plan(const pdeq_config& cfg, int64_t B, int32_t T, bool needs_int
   plan->ring_bytes_per_group = FP ? ((size_t)T * GL::NFC + GL::NF) * d * sizeof(double) : 0;
   int per_sm = 0;
   cudaError_t err;
-  if (plan->cta) {
-    auto kern = k2_loop_kernel<VF, NU, FACT, TS0, FP, true>;
+  if (plan->mode == 2) {
+    auto kern = k2_loop_kernel<VF, NU, FACT, TS0, FP, 2>;
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
+    if (err != cudaSuccess) return err;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, plan->threads, plan->smem_bytes);
+  } else if (plan->mode == 1) {
+    auto kern = k2_loop_kernel<VF, NU, FACT, TS0, FP, 1>;
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
     if (err != cudaSuccess) return err;
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, plan->threads, plan->smem_bytes);
   } else {
-    auto kern = k2_loop_kernel<VF, NU, FACT, TS0, FP, false>;
+    auto kern = k2_loop_kernel<VF, NU, FACT, TS0, FP, 0>;
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
     if (err != cudaSuccess) return err;
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, plan->threads, plan->smem_bytes);
@@ -146,7 +153,7 @@ cudaError_t k2_launch(const LoopArgs& a, void* workspace, size_t workspace_bytes
   info.cond_ring = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
   info.if_scratch = nullptr;
   if (FP) {  // never launch more groups than the scratch has room for
-    using GL = GroupLoop<VF, NU, FACT, TS0, FP, false>;
+    using GL = GroupLoop<VF, NU, FACT, TS0, FP, 0>;
     const size_t room = (workspace_bytes - 256) / plan.ring_bytes_per_group;
     const int max_grid = (int)(room / plan.groups_per_cta);
     if (max_grid < 1) return cudaErrorMemoryAllocation;
@@ -154,10 +161,12 @@ cudaError_t k2_launch(const LoopArgs& a, void* workspace, size_t workspace_bytes
     const size_t groups = (size_t)plan.grid * plan.groups_per_cta;
     info.if_scratch = info.cond_ring + groups * (size_t)a.T * GL::NFC * a.cfg.ode_dim;
   }
-  if (plan.cta)
-    k2_loop_kernel<VF, NU, FACT, TS0, FP, true><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);
+  if (plan.mode == 2)
+    k2_loop_kernel<VF, NU, FACT, TS0, FP, 2><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);
+  else if (plan.mode == 1)
+    k2_loop_kernel<VF, NU, FACT, TS0, FP, 1><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);
   else
-    k2_loop_kernel<VF, NU, FACT, TS0, FP, false><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);
+    k2_loop_kernel<VF, NU, FACT, TS0, FP, 0><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);
   return cudaGetLastError();
 }
 

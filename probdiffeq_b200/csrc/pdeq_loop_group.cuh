@@ -27,8 +27,12 @@ namespace pdeq {
 constexpr int K2_MAX_DPL = 4;       // dimensions per lane in CTA mode
 constexpr int K2_CTA_THREADS = 256;  // upper bound of a CTA-mode block
 
-template <class VF, int NU, int FACT, bool TS0, bool FP, bool CTA>
+// MODE 0: a warp per instance (d <= 32). MODE 1: a CTA per instance, one dimension per lane (d <= 256).
+// MODE 2: a CTA per instance, up to K2_MAX_DPL dimensions per lane (d <= 1024); its proposal arrays cost ~160
+// registers, which is why the one-dimension-per-lane case has its own instantiation (two CTAs per SM instead of one).
+template <class VF, int NU, int FACT, bool TS0, bool FP, int MODE>
 struct GroupLoop {
+  static constexpr bool CTA = MODE != 0;
   static constexpr int n = NU + 1;
   static constexpr int q = VF::order;
   static constexpr int TRI = n * (n + 1) / 2;
@@ -41,7 +45,7 @@ struct GroupLoop {
   static constexpr int F_RUN = F_SIG + 1, F_PRIOR = F_RUN + 1;  // scale, prior scale
   static constexpr int NF = F_PRIOR + 1;
   static constexpr int NFC = n * n + n + TRI + 2 * n;  // fields of a stored conditional
-  static constexpr int MAXR = (CTA && !FP && !ISO) ? K2_MAX_DPL : 1;
+  static constexpr int MAXR = (MODE == 2 && !FP && !ISO) ? K2_MAX_DPL : 1;
   static_assert(q < n, "need more Taylor coefficients than the ODE order");
 
   struct Group {
@@ -702,11 +706,11 @@ struct GroupLaunchInfo {
   int groups_per_cta;
 };
 
-template <class VF, int NU, int FACT, bool TS0, bool FP, bool CTA>
-__global__ void __launch_bounds__(CTA ? K2_CTA_THREADS : 128)
+template <class VF, int NU, int FACT, bool TS0, bool FP, int MODE>
+__global__ void __launch_bounds__(MODE != 0 ? K2_CTA_THREADS : 128, MODE == 1 ? 2 : 1)
     k2_loop_kernel(const __grid_constant__ LoopArgs a, const __grid_constant__ GroupLaunchInfo info) {
   extern __shared__ double smem_k2[];
-  GroupLoop<VF, NU, FACT, TS0, FP, CTA>::run(a, smem_k2, info.cond_ring, info.if_scratch, info.groups_per_cta);
+  GroupLoop<VF, NU, FACT, TS0, FP, MODE>::run(a, smem_k2, info.cond_ring, info.if_scratch, info.groups_per_cta);
 }
 
 }  // namespace pdeq
