@@ -24,7 +24,7 @@ constexpr int K3_THREADS = 256;
 
 struct DenseSmemLayout {
   int N, d, ld;  // ld = N + d
-  size_t off_W, off_Lfrom, off_Lprop, off_Lif, off_vec, total;
+  size_t off_W, off_Lfrom, off_Lif, off_vec, total;
   __host__ __device__ static DenseSmemLayout make(int n, int d, int order, bool needs_interp) {
     DenseSmemLayout s;
     s.N = n * d;
@@ -35,8 +35,6 @@ struct DenseSmemLayout {
     s.off_W = o;
     o += (size_t)2 * s.N * s.ld;
     s.off_Lfrom = o;
-    o += tri;
-    s.off_Lprop = o;
     o += tri;
     s.off_Lif = o;
     o += needs_interp ? tri : 0;
@@ -276,7 +274,6 @@ struct DenseLoop {
 
     double* W = smem + lay.off_W;
     double* Lfrom = smem + lay.off_Lfrom;
-    double* Lprop = smem + lay.off_Lprop;
     double* Lif = smem + lay.off_Lif;
     double* v = smem + lay.off_vec;
     double* m_from = v;
@@ -514,6 +511,37 @@ struct DenseLoop {
         if (cfg.solver == PDEQ_SOLVER_DYNAMIC) sig_new = whitened_obs;
       }
 
+      if (adaptive && cfg.error != PDEQ_ERROR_RESIDUAL_STD) {
+        // error_state_std (solvers.py:1070-1086): Bayes rule on the zero-error extrapolation. Done first because
+        // it needs the work buffer, which afterwards holds the proposal until the step is accepted or rejected.
+        const int idx = cfg.derivative_idx;
+        for (int e = tid; e < N * N; e += G) {
+          const int r = e / N, c = e % N;  // U = L_u^T: U[r][c] = L_u[c][r], block lower in (ci >= ri), same l
+          const int ci = c / d, cj = c % d, ri = r / d, rj = r % d;
+          W[r * ld + d + c] = (cj == rj && ci >= ri) ? fabs(p[ci]) * sq * Qm[ci][ri] * lam[cj] : 0.0;
+        }
+        __syncthreads();
+        revert_stack(W, lay, Hs, a.damp, red);
+        if (tid == 0) {
+          double ss = 0.0;
+          for (int i = 0; i < d; ++i) {
+            double acc = mobs[i];
+            for (int l = 0; l < i; ++l) acc = fma(-W[l * ld + i], wht[l], acc);
+            wht[i] = acc * fast_rcp(W[i * ld + i]);
+            ss = fma(wht[i], wht[i], ss);
+          }
+          bc[3] = safe_sqrt(ss) * inv_sqrt_d;
+        }
+        __syncthreads();
+        for (int e = tid; e < d; e += G) {
+          const int col = idx * d + e;  // std of coefficient idx, dimension e: column norm of R_XY
+          double rn = 0.0;
+          for (int r = 0; r <= col; ++r) rn = fma(W[(d + r) * ld + d + col], W[(d + r) * ld + d + col], rn);
+          stdv[e] = bc[3] * safe_sqrt(rn);
+        }
+        __syncthreads();
+      }
+
       // extrapolate the factor, correct
       PDEQ_K3_TICK(2)
       extrapolate_chol(W, lay, Lfrom, p, pinv, lam, sq * sig_new, A, Qm, red);
@@ -534,10 +562,7 @@ struct DenseLoop {
         for (int a_ = 0; a_ < d; ++a_) acc = fma(-W[a_ * ld + d + e], mobs[a_], acc);
         m_new[e] = acc;
       }
-      for (int e = tid; e < N * N; e += G) {
-        const int jj = e / N, i = e % N;
-        if (jj <= i) Lprop[tri(i, jj)] = W[(d + jj) * ld + d + i];
-      }
+      // the proposal's factor stays in W (rows / columns d .. d+N) until the step is accepted
       double run_new = run_scale;
       if (cfg.solver == PDEQ_SOLVER_MLE) {
         if (tid == 0) {
@@ -572,32 +597,8 @@ struct DenseLoop {
           kpow = q;
         } else {
           // error_state_std (solvers.py:1070-1086): Bayes rule on the zero-error extrapolation
-          idx = cfg.derivative_idx;
-          for (int e = tid; e < N * N; e += G) {
-            const int r = e / N, c = e % N;  // U = L_u^T: U[r][c] = L_u[c][r], block lower in (ci >= ri), same l
-            const int ci = c / d, cj = c % d, ri = r / d, rj = r % d;
-            W[r * ld + d + c] = (cj == rj && ci >= ri) ? fabs(p[ci]) * sq * Qm[ci][ri] * lam[cj] : 0.0;
-          }
-          __syncthreads();
-          revert_stack(W, lay, Hs, a.damp, red);
-          if (tid == 0) {
-            double ss = 0.0;
-            for (int i = 0; i < d; ++i) {
-              double acc = mobs[i];
-              for (int l = 0; l < i; ++l) acc = fma(-W[l * ld + i], wht[l], acc);
-              wht[i] = acc * fast_rcp(W[i * ld + i]);
-              ss = fma(wht[i], wht[i], ss);
-            }
-            bc[3] = safe_sqrt(ss) * inv_sqrt_d;
-          }
-          __syncthreads();
-          for (int e = tid; e < d; e += G) {
-            const int col = idx * d + e;  // std of coefficient idx, dimension e: column norm of R_XY
-            double rn = 0.0;
-            for (int r = 0; r <= col; ++r) rn = fma(W[(d + r) * ld + d + col], W[(d + r) * ld + d + col], rn);
-            stdv[e] = bc[3] * safe_sqrt(rn);
-            refv[e] = fmax(fabs(m_from[idx * d + e]), fabs(m_new[idx * d + e]));
-          }
+          idx = cfg.derivative_idx;  // stdv was computed ahead of the extrapolation (W is the proposal's home)
+          for (int e = tid; e < d; e += G) refv[e] = fmax(fabs(m_from[idx * d + e]), fabs(m_new[idx * d + e]));
           kpow = idx;
         }
         if (cfg.error_per_unit_step) kpow += 1;
@@ -663,7 +664,10 @@ struct DenseLoop {
         }
         __syncthreads();
         for (int e = tid; e < N; e += G) m_from[e] = m_new[e];
-        for (int e = tid; e < TRI_N; e += G) Lfrom[e] = Lprop[e];
+        for (int e = tid; e < N * N; e += G) {
+          const int jj = e / N, i = e % N;
+          if (jj <= i) Lfrom[tri(i, jj)] = W[(d + jj) * ld + d + i];
+        }
         if (cfg.solver == PDEQ_SOLVER_DYNAMIC) sig = sig_new;
         run_scale = run_new;
         ndata += 1.0;
@@ -680,7 +684,7 @@ struct DenseLoop {
 };
 
 template <class VF, int NU, bool TS0>
-__global__ void __launch_bounds__(K3_THREADS, 3) k3_loop_kernel(const __grid_constant__ LoopArgs a) {
+__global__ void __launch_bounds__(K3_THREADS, 4) k3_loop_kernel(const __grid_constant__ LoopArgs a) {
   extern __shared__ double smem_k3[];
   DenseLoop<VF, NU, TS0>::run(a, smem_k3);
 }
