@@ -1,6 +1,7 @@
 // Kernel registry: explicit template instantiations live in their own translation units (so that nvcc
 // can build them in parallel) and register a launcher under a small key at load time.
 #pragma once
+#include <cstdlib>
 
 #include <cuda_runtime.h>
 
@@ -126,6 +127,10 @@ cudaError_t k2_plan(const pdeq_config& cfg, int64_t B, int32_t T, bool needs_int
   }
   if (err != cudaSuccess) return err;
   if (per_sm < 1) per_sm = 1;
+  if (const char* cap = std::getenv("PDEQ_K2_CTAS_PER_SM")) {  // tuning knob: fewer resident CTAs per SM
+    const int c = std::atoi(cap);
+    if (c >= 1 && c < per_sm) per_sm = c;
+  }
   const long want = (B + plan->groups_per_cta - 1) / plan->groups_per_cta;
   plan->grid = (int)std::max(1L, std::min(want, (long)per_sm * device_sm_count()));
   return cudaSuccess;

@@ -219,17 +219,60 @@ struct GroupLoop {
 
   // The per-lane part of one extrapolation with the transition (dt, scale s): predicted factor, and for the
   // smoother the merged backward conditional.
+  // A stored conditional -- NFC rows [field][dim] in the order of cond_store -- read in place, written in place,
+  // or copied row by row. With these the carried and the merged conditional never occupy registers (they were
+  // 2 x 90 doubles per lane at nu = 5 and the reason for a 4.7 KB stack frame whose spill traffic reached DRAM).
+  struct CondFields {
+    const double* base;
+    int d, j;
+    PDEQ_DI double G(int i, int k) const { return base[(i * n + k) * d + j]; }
+    PDEQ_DI double xi(int i) const { return base[(n * n + i) * d + j]; }
+    PDEQ_DI double Xi(int i, int k) const { return base[(n * n + n + i * (i + 1) / 2 + k) * d + j]; }
+    PDEQ_DI double tl(int i) const { return base[(n * n + n + TRI + i) * d + j]; }
+    PDEQ_DI double to(int i) const { return base[(n * n + n + TRI + n + i) * d + j]; }
+  };
+  struct CondIdentity {  // *Normal.identity_conditional (ssm_impl_blockdiag.py:353-359)
+    PDEQ_DI double G(int i, int k) const { return i == k ? 1.0 : 0.0; }
+    PDEQ_DI double xi(int) const { return 0.0; }
+    PDEQ_DI double Xi(int, int) const { return 0.0; }
+    PDEQ_DI double tl(int) const { return 1.0; }
+    PDEQ_DI double to(int) const { return 1.0; }
+  };
+  struct CondSink {
+    double* base;
+    int d, j;
+    PDEQ_DI void set_G(int i, int k, double v) { base[(i * n + k) * d + j] = v; }
+    PDEQ_DI void set_xi(int i, double v) { base[(n * n + i) * d + j] = v; }
+    PDEQ_DI void set_Xi(int i, int k, double v) { base[(n * n + n + i * (i + 1) / 2 + k) * d + j] = v; }
+    PDEQ_DI void set_tl(int i, double v) { base[(n * n + n + TRI + i) * d + j] = v; }
+    PDEQ_DI void set_to(int i, double v) { base[(n * n + n + TRI + n + i) * d + j] = v; }
+  };
+  PDEQ_DI static void cond_copy(double* dst, const double* src, int d, int j) {
+#pragma unroll
+    for (int e = 0; e < NFC; ++e) dst[e * d + j] = src[e * d + j];
+  }
+  PDEQ_DI static void cond_store_identity(double* dst, int d, int j) {
+    BlockCond<n> ident;
+    cond_identity<n>(ident);
+    cond_store(dst, d, j, ident);
+  }
+
   PDEQ_DI static void extrapolate(const double (&L)[n][n], const double (&m)[n], const double (&p)[n],
                                   const double (&pinv)[n], double s, const double (*A)[PDEQ_MAX_COEFFS],
-                                  const double (*Q)[PDEQ_MAX_COEFFS], const BlockCond<n>* carried,
-                                  double (&Lp)[n][n], BlockCond<n>* merged) {
-    if (FP) {
-      BlockCond<n> bw;
-      revert_transition<n>(L, m, p, pinv, s, A, Q, Lp, bw);
-      merge_cond<n>(*carried, bw, *merged);
-    } else {
-      predict_chol<n>(L, p, pinv, s, A, Q, Lp);
-    }
+                                  const double (*Q)[PDEQ_MAX_COEFFS], double (&Lp)[n][n]) {
+    predict_chol<n>(L, p, pinv, s, A, Q, Lp);
+  }
+  // Smoother: the transition is reverted, and the new backward conditional is composed with the one found at
+  // `carried` into `merged` (strategy_smoother_fixedpoint.predict, estimators_and_losses.py:526-532).
+  template <class Outer>
+  PDEQ_DI static void extrapolate_smoother(const double (&L)[n][n], const double (&m)[n], const double (&p)[n],
+                                           const double (&pinv)[n], double s, const double (*A)[PDEQ_MAX_COEFFS],
+                                           const double (*Q)[PDEQ_MAX_COEFFS], const Outer& carried,
+                                           double (&Lp)[n][n], double* merged, int d, int j) {
+    BlockCond<n> bw;
+    revert_transition<n>(L, m, p, pinv, s, A, Q, Lp, bw);
+    CondSink sink{merged, d, j};
+    merge_cond_streamed<n>(carried, bw, sink);
   }
 
   // For the smoother the interp_from copy of the state (written on every accepted step, read only when a checkpoint
@@ -282,7 +325,9 @@ struct GroupLoop {
 
     // thread-local proposal scratch (registers when a lane serves one dimension)
     double pm[MAXR][n], pL[MAXR][n][n], psig[MAXR], prun[MAXR];
-    BlockCond<n> pcond, pcarried;  // smoother only (one dimension per lane)
+    // smoother: slot 0 of the ring (conditionals are stored from checkpoint 1 on) holds the merged conditional of
+    // the current attempt until the step is accepted
+    double* pending = ring;
 
     while (true) {
       // ------------------------------------------------------------------ fetch the next instance
@@ -355,9 +400,13 @@ struct GroupLoop {
               const double dt0_ = t_next - t_if;
               preconditioner<n>(dt0_, ifact, fact, p, pinv);
               predict_mean<n>(mi, p, pinv, A, mo);
-              BlockCond<n> c_if, c0;
-              if (FP) cond_load(st_if + F_G * d, d, j, c_if);
-              extrapolate(Li, mi, p, pinv, safe_sqrt(fabs(dt0_)) * prior * sig, A, Q, &c_if, Lo, &c0);
+              if (FP) {  // the conditional checkpoint ck -> ck - 1 goes straight to its ring slot
+                const CondFields c_if{st_if + F_G * d, d, j};
+                extrapolate_smoother(Li, mi, p, pinv, safe_sqrt(fabs(dt0_)) * prior * sig, A, Q, c_if, Lo,
+                                     ring + (size_t)ck * NFC * d, d, j);
+              } else {
+                extrapolate(Li, mi, p, pinv, safe_sqrt(fabs(dt0_)) * prior * sig, A, Q, Lo);
+              }
               emit(a, b, ck, d, j, t_next, mo, Lo, sig, nsteps);
               if (FP) {
                 // second half: from the interpolated point to the overstepped state, with a fresh backward
@@ -365,12 +414,9 @@ struct GroupLoop {
                 double p1[n], pinv1[n], Ltmp[n][n];
                 const double dt1_ = t - t_next;
                 preconditioner<n>(dt1_, ifact, fact, p1, pinv1);
-                BlockCond<n> ident, c1;
-                cond_identity<n>(ident);
-                extrapolate(Lo, mo, p1, pinv1, safe_sqrt(fabs(dt1_)) * prior * sig, A, Q, &ident, Ltmp, &c1);
-                cond_store(ring + (size_t)ck * NFC * d, d, j, c0);
-                cond_store(st_from + F_G * d, d, j, c1);
-                cond_store(st_if + F_G * d, d, j, ident);
+                extrapolate_smoother(Lo, mo, p1, pinv1, safe_sqrt(fabs(dt1_)) * prior * sig, A, Q, CondIdentity{}, Ltmp,
+                                     st_from + F_G * d, d, j);
+                cond_store_identity(st_if + F_G * d, d, j);
               }
               st_store(st_if, d, j, mo, Lo);
             } else {
@@ -379,12 +425,9 @@ struct GroupLoop {
               st_load(st_from, d, j, m, L);
               emit(a, b, ck, d, j, t, m, L, sig, nsteps);
               if (FP) {
-                BlockCond<n> c, ident;
-                cond_load(st_from + F_G * d, d, j, c);
-                cond_identity<n>(ident);
-                cond_store(ring + (size_t)ck * NFC * d, d, j, c);
-                cond_store(st_from + F_G * d, d, j, ident);
-                if (needs_interp) cond_store(st_if + F_G * d, d, j, ident);
+                cond_copy(ring + (size_t)ck * NFC * d, st_from + F_G * d, d, j);
+                cond_store_identity(st_from + F_G * d, d, j);
+                if (needs_interp) cond_store_identity(st_if + F_G * d, d, j);
               }
               if (needs_interp) st_store(st_if, d, j, m, L);
             }
@@ -548,8 +591,12 @@ struct GroupLoop {
         if (cfg.solver == PDEQ_SOLVER_DYNAMIC) sig_new = whitened(g, mobs * fast_rcp(robs), active, inv_sqrt_d);
 
         double Lp[n][n], Ln[n][n], gain[n], ry, mn[n];
-        if (FP) cond_load(st_from + F_G * d, d, jj, pcarried);
-        extrapolate(L, m, p, pinv, sq * prior * sig_new, A, Q, &pcarried, Lp, &pcond);
+        if (FP) {
+          const CondFields carried{st_from + F_G * d, d, jj};
+          extrapolate_smoother(L, m, p, pinv, sq * prior * sig_new, A, Q, carried, Lp, pending, d, jj);
+        } else {
+          extrapolate(L, m, p, pinv, sq * prior * sig_new, A, Q, Lp);
+        }
         revert_obs<n, q, TS0>(Lp, h, a.damp, ry, gain, Ln);
 #pragma unroll
         for (int i = 0; i < n; ++i) mn[i] = fma(-gain[i], mobs, mp[i]);
@@ -671,19 +718,17 @@ struct GroupLoop {
             double m[n], L[n][n];
             st_load(st_from, d, j, m, L);
             st_store(st_if, d, j, m, L);
-            if (FP) cond_store(st_if + F_G * d, d, j, pcarried);
+            if (FP) cond_copy(st_if + F_G * d, st_from + F_G * d, d, j);
           }
           st_store(st_from, d, j, pm[r], pL[r]);
           if (FP) {
             if (!adaptive) {
               // fixed grid: every grid point is a checkpoint. Store the backward conditional of this step and
               // restart from the identity -- the fixed-interval smoother (estimators_and_losses.py:612-620).
-              cond_store(ring + (size_t)ck * NFC * d, d, j, pcond);
-              BlockCond<n> ident;
-              cond_identity<n>(ident);
-              cond_store(st_from + F_G * d, d, j, ident);
+              cond_copy(ring + (size_t)ck * NFC * d, pending, d, j);
+              cond_store_identity(st_from + F_G * d, d, j);
             } else {
-              cond_store(st_from + F_G * d, d, j, pcond);
+              cond_copy(st_from + F_G * d, pending, d, j);
             }
           }
           if (cfg.solver == PDEQ_SOLVER_DYNAMIC) st_from[F_SIG * d + j] = psig[r];
