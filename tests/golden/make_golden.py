@@ -55,6 +55,26 @@ def build():
     out["smoother_mean"] = sol.u_mean
     out["smoother_chol"] = sol.u_chol
     out["smoother_num_steps"] = np.asarray(sol.num_steps)
+    # ... its time-series log-marginal-likelihood for fixed data
+    rng = np.random.Generator(np.random.PCG64(2024))
+    data = np.asarray(sol.u_mean)[:, 0] + 0.1 * rng.normal(size=(6, 2))
+    std = 0.1 + 0.02 * np.arange(6)[:, None] * np.ones((1, 2))
+    out["lml_data"], out["lml_std"] = data, std
+    post = sol.solution_full.posterior
+    out["lml_mean_of_pdfs"] = np.asarray(o_pdq.loss_lml_timeseries()(data, posterior=post, std=std))
+    out["lml_sum_of_pdfs"] = np.asarray(o_pdq.loss_lml_timeseries(average_pdfs=False)(data, posterior=post, std=std))
+    # dense output of a filter solution between the checkpoints
+    sf = H.spec(fact="isotropic", solver="solver_mle", error="residual_std", control="i", clip_dt=False)
+    solf, _ = H.oracle_solve_save_at(sf, tcb, params[0], save_at, 1e-6, 1e-4)
+    import pdeq_test_helpers as H2
+    from oracle import ivpsolve as o_ivp
+
+    _, oslv, _, _ = H2._build(o_pdq, o_ivp, sf, H.oracle_vf(sf, params[0]))
+    ts = np.asarray([0.1, 0.9, 1.7])
+    rvs = [oslv.offgrid_marginals(t, solution=solf) for t in ts]
+    out["offgrid_t"] = ts
+    out["offgrid_mean"] = np.stack([rv.mean for rv in rvs])
+    out["offgrid_chol"] = np.stack([rv.chol for rv in rvs])
     return out
 
 

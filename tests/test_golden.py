@@ -69,3 +69,19 @@ def test_cuda_path_matches_golden_vectors(cuda, golden):
     assert np.array_equal(sol.num_steps[0, 1:].cpu().numpy(), golden["smoother_num_steps"])
     assert np.allclose(sol.u.mean_flat[0].cpu().numpy(), golden["smoother_mean"], rtol=1e-7, atol=1e-9)
     assert np.allclose(_cov(sol.u.cholesky_flat[0].cpu().numpy()), _cov(golden["smoother_chol"]), rtol=1e-5, atol=1e-14)
+    # its time-series log-marginal-likelihood
+    post = sol.solution_full.posterior
+    for avg, key in ((True, "lml_mean_of_pdfs"), (False, "lml_sum_of_pdfs")):
+        lml = p_pdq.loss_lml_timeseries(average_pdfs=avg)(golden["lml_data"], posterior=post, std=golden["lml_std"])
+        assert np.isclose(float(lml[0]), float(golden[key]), rtol=1e-8), (key, float(lml[0]), float(golden[key]))
+    # dense output of a filter solution
+    s = H.spec(fact="isotropic", solver="solver_mle", error="residual_std", control="i", clip_dt=False)
+    p_pdq, p_ivp, vf, ssm, solver, err, ctrl = H.product_build(s, params[:1])
+    sol = p_ivp.solve_adaptive_save_at(solver=solver, error=err, control=ctrl)(
+        ssm.prior_wiener_integrated(tc), save_at=golden["smoother_save_at"], atol=1e-6, rtol=1e-4
+    )
+    rv = solver.offgrid_marginals(golden["offgrid_t"], solution=sol)
+    torch.cuda.synchronize()
+    assert np.allclose(rv.mean_flat[0, :, :2].cpu().numpy(), golden["offgrid_mean"][:, :2], rtol=1e-8, atol=1e-10)
+    assert np.allclose(rv.mean_flat[0].cpu().numpy(), golden["offgrid_mean"], rtol=1e-4, atol=1e-7)
+    assert np.allclose(_cov(rv.cholesky_flat[0].cpu().numpy()), _cov(golden["offgrid_chol"]), rtol=1e-5, atol=1e-16)
