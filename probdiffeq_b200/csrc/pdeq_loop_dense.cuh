@@ -179,6 +179,9 @@ struct DenseLoop {
       }
       __syncthreads();
     }
+    // the last column may have taken the barrier-free skip path: make its rdiag entry (and everyone's last read
+    // of the old diagonal) visible before the diagonal is restored
+    __syncthreads();
     for (int j = tid; j < ncols; j += G) W[j * ld + j] = rdiag[j];
     __syncthreads();
   }

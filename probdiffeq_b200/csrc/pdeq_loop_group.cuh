@@ -710,6 +710,8 @@ struct GroupLoop {
       // ------------------------------------------------------------------ commit
       dt = dt_next;
       if (accept) {
+        // every lane has finished reading the accepted state (isotropic: idle lanes read lane 0's copy)
+        g.sync();
         for (int r = 0; r < MAXR; ++r) {
           if (r >= nrounds) break;
           const int j = g.lane + r * g.size;
