@@ -12,8 +12,8 @@ import numpy as np
 import torch
 
 sys.path.insert(0, ".")
-from oracle import problems as o_problems  # initial values only (constants of the benchmark problems)
 from probdiffeq_b200 import ivpsolve, probdiffeq
+from probdiffeq_b200 import problems as pb
 
 BUDGET, ONLY = 60.0, None
 
@@ -55,8 +55,7 @@ def ladder(name, make, sizes):
 
 
 def config3(B):
-    rng = np.random.Generator(np.random.PCG64(1))
-    u0 = o_problems.pleiades_u0()[None, :] + 1e-3 * rng.normal(size=(B, 28))
+    u0 = pb.pleiades_ensemble(B, seed=1)
     vf = probdiffeq.ode("pleiades")
     ssm = probdiffeq.state_space_model_blockdiag()
     tcoeffs, _ = probdiffeq.jetexpand_ode_padded_scan(num=5)(vf, (u0,), t=0.0)
@@ -72,7 +71,7 @@ def config3(B):
 
 def config4a(B):
     rng = np.random.Generator(np.random.PCG64(2))
-    u0 = np.repeat(o_problems.hires_u0()[None, :], B, axis=0)
+    u0 = np.repeat(pb.HIRES_U0[None, :], B, axis=0)
     sc = rng.uniform(0.9, 1.1, size=(B, 2))
     u0[:, 0] *= sc[:, 0]
     u0[:, 7] *= sc[:, 1]
@@ -107,7 +106,7 @@ def config4b(B):
 def config5(B, d=1024, constraint="ts0"):
     rng = np.random.Generator(np.random.PCG64(3))
     nu = 0.01 * rng.uniform(0.5, 2.0, size=(B, 1))
-    u0 = np.repeat(o_problems.burgers_u0(d)[None, :], B, axis=0)
+    u0 = np.repeat(pb.burgers_u0(d)[None, :], B, axis=0)
     vf = probdiffeq.ode("burgers", params=nu)
     ssm = probdiffeq.state_space_model_blockdiag()
     tcoeffs, _ = probdiffeq.jetexpand_ode_padded_scan(num=3)(vf, (u0,), t=0.0)

@@ -1,3 +1,4 @@
+"""Development aid (test infrastructure): print the first attempts of the CUDA path next to the oracle's."""
 import sys, numpy as np, torch
 sys.path.insert(0, "tests"); sys.path.insert(0, ".")
 import pdeq_test_helpers as H
