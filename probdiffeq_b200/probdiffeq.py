@@ -37,6 +37,7 @@ __all__ = [
     "error_state_std",
     "jetexpand_ode_padded_scan",
     "jetexpand_ode_unroll",
+    "jetexpand_ode_coefficient_increment",
     "loss_lml_terminal_values",
     "loss_lml_timeseries",
     "MarkovSequence",
@@ -200,6 +201,27 @@ def jetexpand_ode_padded_scan(*, num: int):
 
 
 jetexpand_ode_unroll = jetexpand_ode_padded_scan  # same output (jet_expansion_algorithms.py:110-152)
+
+
+def jetexpand_ode_coefficient_increment(*, num_arguments: int):
+    """reference: jet_expansion_algorithms.py:155-177 -- ``increment(vf, taylor_coeffs, t=t)`` returns the Taylor
+    series with one more coefficient. The coefficients are functions of the first ``num_arguments`` entries alone,
+    so the device routine recomputes the series to the new length from those (one pass per coefficient)."""
+
+    def increment(vf: VectorField, taylor_coeffs, *, t: float = 0.0):
+        if not isinstance(vf, VectorField):
+            raise TypeError(vf)
+        if num_arguments != vf.order:
+            raise ValueError(f"{vf.name} takes {vf.order} Taylor coefficient(s) as arguments, not {num_arguments}.")
+        tc = _as_device_f64(taylor_coeffs)
+        k = tc.shape[-2]
+        if k < num_arguments:
+            raise ValueError("fewer Taylor coefficients than the vector field has arguments")
+        inits = tuple(tc[..., i, :] for i in range(num_arguments))
+        out, _ = jetexpand_ode_padded_scan(num=k + 1 - num_arguments)(vf, inits, t=t)
+        return out
+
+    return increment
 
 
 # ------------------------------------------------------------------------------------------------------

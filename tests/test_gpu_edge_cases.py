@@ -164,3 +164,23 @@ def test_unsupported_configurations_raise(cuda):
         solve(ssm.prior_wiener_integrated(tcoeffs), t0=0.0, t1=1.0, atol=1e-3, rtol=1e-3)
     with pytest.raises(ValueError):
         ssm.prior_wiener_integrated(tcoeffs, output_scale=np.ones(3))
+
+
+def test_taylor_coefficient_increment(cuda):
+    """jetexpand_ode_coefficient_increment (jet_expansion_algorithms.py:155-177): one more coefficient per call."""
+    from probdiffeq_b200 import probdiffeq
+
+    params, u0 = H.lv_ensemble(6, seed=9)
+    vf = probdiffeq.ode("lotka_volterra", params=params)
+    full, _ = probdiffeq.jetexpand_ode_padded_scan(num=4)(vf, (u0,), t=0.0)
+    inc = probdiffeq.jetexpand_ode_coefficient_increment(num_arguments=1)
+    tc = full[:, :2]
+    for k in range(3, 6):
+        tc = inc(vf, tc, t=0.0)
+        assert tc.shape == (6, k, 2)
+        assert np.array_equal(tc.cpu().numpy(), full[:, :k].cpu().numpy())
+    for b in range(2):
+        ref = o_pdq.ode("lotka_volterra", params[b]).taylor_coefficients((u0[b],), 0.0, 4)
+        assert np.allclose(tc[b].cpu().numpy(), ref, rtol=1e-13)
+    with pytest.raises(ValueError):
+        probdiffeq.jetexpand_ode_coefficient_increment(num_arguments=2)(vf, tc)
