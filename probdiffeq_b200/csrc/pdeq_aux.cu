@@ -212,6 +212,61 @@ __global__ void lml_terminal_kernel(int64_t B, int n, int d, int blockdiag, int 
   if (lane == 0) out[b] = acc;
 }
 
+// loss_lml_terminal_values for the dense factorisation (DenseNormal.to_derivative + marginalise + logpdf,
+// ssm_impl_dense.py:108-234): the observed covariance S = L_i L_i^T + diag(std^2), with L_i the d rows of the
+// (nd x nd) factor that belong to coefficient idx (coefficient-major state, row idx * d + a), is formed in shared
+// memory by one warp per instance, factorised (Cholesky, d <= 32) and the Gaussian log-density evaluated.
+// The reference triangularises a stacked square root instead; the value is the same up to rounding.
+constexpr int LML_DENSE_MAX_D = 32;
+__global__ void lml_terminal_dense_kernel(int64_t B, int n, int d, int idx, const double* __restrict__ mean,
+                                          const double* __restrict__ chol, const double* __restrict__ data,
+                                          int64_t data_stride, const double* __restrict__ std_, int64_t std_stride,
+                                          double* __restrict__ out) {
+  __shared__ double S_all[4][LML_DENSE_MAX_D][LML_DENSE_MAX_D + 1];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * 4 + w;
+  if (b >= B) return;  // whole warps leave together; no block barrier below
+  double(*S)[LML_DENSE_MAX_D + 1] = S_all[w];
+  const int N = n * d;
+  const double* L = chol + b * (int64_t)N * N;
+  for (int e = lane; e < d * d; e += 32) {
+    const int a = e / d, c = e % d;
+    if (c > a) continue;
+    const double* ra = L + (int64_t)(idx * d + a) * N;
+    const double* rc = L + (int64_t)(idx * d + c) * N;
+    double acc = 0.0;
+    for (int k = 0; k <= idx * d + c; ++k) acc = fma(ra[k], rc[k], acc);  // lower-triangular factor
+    if (a == c) {
+      const double sd = std_[b * std_stride + a];
+      acc = fma(sd, sd, acc);
+    }
+    S[a][c] = acc;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    const double log2pi = 1.8378770664093453;
+    double logdet = 0.0, quad = 0.0;
+    double y[LML_DENSE_MAX_D];
+    for (int j = 0; j < d; ++j) {  // in-place Cholesky, then forward substitution with the residual
+      double s = S[j][j];
+      for (int k = 0; k < j; ++k) s = fma(-S[j][k], S[j][k], s);
+      const double piv = sqrt(s);
+      S[j][j] = piv;
+      for (int i = j + 1; i < d; ++i) {
+        double t = S[i][j];
+        for (int k = 0; k < j; ++k) t = fma(-S[i][k], S[j][k], t);
+        S[i][j] = t / piv;
+      }
+      double r = data[b * data_stride + j] - mean[(b * n + idx) * (int64_t)d + j];
+      for (int k = 0; k < j; ++k) r = fma(-S[j][k], y[k], r);
+      y[j] = r / piv;
+      quad = fma(y[j], y[j], quad);
+      logdet += log(piv);
+    }
+    out[b] = -0.5 * (2.0 * logdet + quad + (double)d * log2pi);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // loss_lml_timeseries for the isotropic and block-diagonal factorisations
 // (probdiffeq/_probdiffeq/estimators_and_losses.py:53-105; MarkovSequence.evaluate_lml :180-218;
@@ -512,10 +567,19 @@ int pdeq_lml_terminal_values(const pdeq_config* cfg, int64_t num_instances, int3
   if (tcoeff_index < 0 || tcoeff_index > cfg->num_derivatives) return api_fail(-5, "bad tcoeff_index");
   int fact = cfg->factorisation;
   if (fact == PDEQ_FACT_DENSE && cfg->ode_dim == 1) fact = PDEQ_FACT_ISOTROPIC;
-  if (fact == PDEQ_FACT_DENSE) return api_fail(-10, "lml_terminal_values: dense factorisation with d > 1 not built");
   if (num_instances == 0) return 0;
   const int threads = 128;
   const int grid = (int)((num_instances * 32 + threads - 1) / threads);
+  if (fact == PDEQ_FACT_DENSE) {
+    if (cfg->ode_dim > LML_DENSE_MAX_D)
+      return api_fail(-10, "lml_terminal_values: dense factorisation supports ode_dim <= %d", LML_DENSE_MAX_D);
+    lml_terminal_dense_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
+        num_instances, cfg->num_derivatives + 1, cfg->ode_dim, tcoeff_index, mean, chol, data, data_stride, std,
+        std_stride, out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return api_cuda_fail(e, "lml_terminal_values (dense)");
+    return 0;
+  }
   lml_terminal_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
       num_instances, cfg->num_derivatives + 1, cfg->ode_dim, fact == PDEQ_FACT_BLOCKDIAG, tcoeff_index, mean, chol,
       data, data_stride, std, std_stride, fact == PDEQ_FACT_BLOCKDIAG, out);

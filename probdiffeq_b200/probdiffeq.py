@@ -451,12 +451,14 @@ class _Solver:
         ps = prior.output_scale
         ps_stride = 0 if ps is None or ps.shape[0] == 1 else ps.shape[1]
         if B > 0:
+            # contiguous copies are bound to names: a temporary would be freed (and its block reused by the next
+            # temporary) before the launch that reads it
+            mean, chol, scale = mean.contiguous(), chol.contiguous(), scale.contiguous()
+            filt_mean = None if filt_mean is None else filt_mean.contiguous()
+            filt_chol = None if filt_chol is None else filt_chol.contiguous()
             rc = _lib.load().pdeq_offgrid_marginals(
-                C.byref(cfg), B, T, _ptr(g0), Q, _ptr(tq), _ptr(mean.contiguous()), _ptr(chol.contiguous()),
-                _ptr(filt_mean.contiguous()) if filt_mean is not None else None,
-                _ptr(filt_chol.contiguous()) if filt_chol is not None else None,
-                _ptr(scale.contiguous()), _ptr(ps) if ps is not None else None, ps_stride,
-                _ptr(out_mean), _ptr(out_chol), _stream(),
+                C.byref(cfg), B, T, _ptr(g0), Q, _ptr(tq), _ptr(mean), _ptr(chol), _ptr(filt_mean), _ptr(filt_chol),
+                _ptr(scale), _ptr(ps), ps_stride, _ptr(out_mean), _ptr(out_chol), _stream(),
             )  # fmt: skip
             _lib.check(rc, "pdeq_offgrid_marginals")
         if scalar_t:
@@ -685,9 +687,11 @@ class MarkovSequence:
         out = torch.empty((B, S, T, n, d), dtype=torch.float64, device=mean.device)
         cfg = _make_config(fact=fact, nu=n - 1, d=d, vf=VectorField("linear", params=[1.0]))
         if B > 0:
+            gain, cmean, cchol = gain.contiguous(), cmean.contiguous(), cchol.contiguous()  # named: see offgrid_marginals
+            base_c = base_t.reshape(B, S, *core).contiguous()
             rc = _lib.load().pdeq_sample_posterior(
-                C.byref(cfg), B, T, S, _ptr(mean_t), _ptr(chol_t), _ptr(gain.contiguous()), _ptr(cmean.contiguous()),
-                _ptr(cchol.contiguous()), _ptr(base_t.reshape(B, S, *core).contiguous()), _ptr(out), _stream(),
+                C.byref(cfg), B, T, S, _ptr(mean_t), _ptr(chol_t), _ptr(gain), _ptr(cmean), _ptr(cchol), _ptr(base_c),
+                _ptr(out), _stream(),
             )  # fmt: skip
             _lib.check(rc, "pdeq_sample_posterior")
         out = out.reshape(B, *shape, T, n, d)
@@ -756,9 +760,10 @@ def loss_lml_timeseries(*, average_pdfs: bool = True, tcoeff_index: int = 0):
         out = torch.empty((B,), dtype=torch.float64, device=mean.device)
         ws = torch.empty((max(B * d, 1),), dtype=torch.float64, device=mean.device)
         data_b, sd_b = data_b.contiguous(), sd_b.contiguous()
+        gain, cmean, cchol = gain.contiguous(), cmean.contiguous(), cchol.contiguous()  # named: see offgrid_marginals
         rc = _lib.load().pdeq_lml_timeseries(
             C.byref(cfg), B, T, int(tcoeff_index), int(bool(average_pdfs)), _ptr(mean_t), _ptr(chol_t),
-            _ptr(gain.contiguous()), _ptr(cmean.contiguous()), _ptr(cchol.contiguous()),
+            _ptr(gain), _ptr(cmean), _ptr(cchol),
             _ptr(data_b), 0 if data_b.shape[0] == 1 else T * d, _ptr(sd_b),
             0 if sd_b.shape[0] == 1 else int(np.prod(std_core)), _ptr(out), _ptr(ws), ws.numel() * 8, _stream(),
         )  # fmt: skip
@@ -790,8 +795,9 @@ def loss_lml_terminal_values(*, tcoeff_index: int = 0):
         vf_ = vf if vf is not None else VectorField("linear", params=[1.0])
         cfg = _make_config(fact=marginals.factorisation, nu=n - 1, d=d, vf=vf_)
         out = torch.empty((B,), dtype=torch.float64, device=mean.device)
+        mean, chol = mean.contiguous(), chol.contiguous()  # named: a temporary's block would be reused before the launch
         rc = _lib.load().pdeq_lml_terminal_values(
-            C.byref(cfg), B, int(tcoeff_index), _ptr(mean.contiguous()), _ptr(chol.contiguous()),
+            C.byref(cfg), B, int(tcoeff_index), _ptr(mean), _ptr(chol),
             _ptr(data), 0 if data.shape[0] == 1 else d, _ptr(sd), 0 if sd.shape[0] == 1 else k,
             _ptr(out), _stream(),
         )  # fmt: skip

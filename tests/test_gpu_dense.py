@@ -64,3 +64,31 @@ def test_dense_fixed_grid(cuda):
         cov, ocov = L @ np.swapaxes(L, -1, -2), osol.u_chol @ np.swapaxes(osol.u_chol, -1, -2)
         for k in range(len(grid)):
             assert np.max(np.abs(cov[k] - ocov[k])) <= 1e-10 * max(np.max(np.abs(ocov[k])), 1e-300), k
+
+
+def test_dense_lml_terminal_values(cuda):
+    """loss_lml_terminal_values on a dense marginal (estimators_and_losses.py:20-50 with ssm_impl_dense.py:108-234)."""
+    import torch
+
+    from oracle import ivpsolve as o_ivp
+    from oracle import probdiffeq as o_pdq
+
+    s = H.spec(fact="dense", constraint="ts1", solver="solver_mle", error="residual_std", control="i")
+    B = 4
+    params, u0 = H.lv_ensemble(B, seed=61)
+    p_pdq, p_ivp, vf, ssm, slv, err, ctrl = H.product_build(s, params)
+    tcoeffs, _ = p_pdq.jetexpand_ode_padded_scan(num=4)(vf, (u0,), t=0.0)
+    sol = p_ivp.solve_adaptive_terminal_values(solver=slv, error=err, control=ctrl)(
+        ssm.prior_wiener_integrated(tcoeffs), t0=0.0, t1=1.0, atol=1e-5, rtol=1e-3
+    )
+    rng = np.random.Generator(np.random.PCG64(8))
+    data = sol.u.mean[0].cpu().numpy() + 1e-2 * rng.normal(size=(B, 2))
+    std = np.asarray([1e-2, 3e-2])
+    for idx in (0, 1):
+        obs = data if idx == 0 else sol.u.mean[1].cpu().numpy() + 1e-2 * rng.normal(size=(B, 2))
+        got = p_pdq.loss_lml_terminal_values(tcoeff_index=idx)(obs, marginals=sol.u, std=std).cpu().numpy()
+        torch.cuda.synchronize()
+        for b in range(B):
+            osol, _ = H.oracle_solve_save_at(s, tcoeffs[b].cpu().numpy(), params[b], np.asarray([0.0, 1.0]), 1e-5, 1e-3)
+            ref = o_pdq.loss_lml_terminal_values(tcoeff_index=idx)(obs[b], marginals=osol.u[-1], std=std)
+            assert np.isclose(got[b], ref, rtol=1e-7, atol=1e-9), (idx, b, got[b], ref)
