@@ -151,6 +151,11 @@ int pdeq_vf_num_params(int vf_id);
 int pdeq_vf_ode_order(int vf_id);
 /* fixed dimension of the problem, or 0 if the functor accepts any d (linear, burgers) */
 int pdeq_vf_dim(int vf_id);
+/* Add a vector field to the registry at run time and return its id. The kernels for it come from a plug-in: a
+   shared object built from csrc/ with the functor (same interface as the built-in ones in csrc/pdeq_vf.cuh) and the
+   instantiation macros, which registers its launchers under this id when loaded (probdiffeq_b200/plugins.py).
+   The reference takes any Python callable (`probdiffeq.ode`, problems.py:283-312); this is the device-side equivalent. */
+int pdeq_register_vf(const char* name, int32_t ode_order, int32_t num_params, int32_t fixed_dim);
 
 /* 0 if (cfg) is a combination the library has a kernel for, negative otherwise (see pdeq_last_error). */
 int pdeq_config_supported(const pdeq_config* cfg);

@@ -224,8 +224,15 @@ def _burgers(xp, p, t, u):
     return -fluxterm + nu * laplacian
 
 
+def _logistic(xp, p, t, u):
+    """u' = r u (1 - u / K): the right-hand side the plug-in test compiles at run time (not a benchmark problem)."""
+    r, cap = p
+    return r * u * (1.0 - u * (1.0 / cap))
+
+
 _REGISTRY = {
     # name: (function, ode order, number of parameters, default parameters)
+    "logistic": (_logistic, 1, 2, (1.0, 1.0)),
     "lotka_volterra": (_lotka_volterra, 1, 4, (0.5, 0.05, 0.5, 0.05)),
     "pleiades": (_pleiades, 1, 0, ()),
     "hires": (_hires, 1, 0, ()),

@@ -7,7 +7,7 @@
 #include <mutex>
 #include <vector>
 
-#include "pdeq_dispatch.cuh"
+#include "pdeq_aux_kernels.cuh"
 
 namespace pdeq {
 
@@ -42,23 +42,49 @@ int device_sm_count() {
   return sms > 0 ? sms : 148;
 }
 
+// Vector-field table: the six built-in functors, then whatever plug-ins register at run time (pdeq_register_vf).
 struct VfInfo {
-  const char* name;
+  char name[64];
   int order, num_params, fixed_dim;
 };
-static const VfInfo kVf[VF_COUNT] = {
-    {"lotka_volterra", LotkaVolterra::order, LotkaVolterra::num_params, LotkaVolterra::fixed_dim},
-    {"pleiades", Pleiades::order, Pleiades::num_params, Pleiades::fixed_dim},
-    {"hires", Hires::order, Hires::num_params, Hires::fixed_dim},
-    {"vanderpol", VanDerPol::order, VanDerPol::num_params, VanDerPol::fixed_dim},
-    {"linear", Linear::order, Linear::num_params, Linear::fixed_dim},
-    {"burgers", Burgers::order, Burgers::num_params, Burgers::fixed_dim},
-};
+static std::vector<VfInfo>& vf_table() {
+  static std::vector<VfInfo> table = {
+      {"lotka_volterra", LotkaVolterra::order, LotkaVolterra::num_params, LotkaVolterra::fixed_dim},
+      {"pleiades", Pleiades::order, Pleiades::num_params, Pleiades::fixed_dim},
+      {"hires", Hires::order, Hires::num_params, Hires::fixed_dim},
+      {"vanderpol", VanDerPol::order, VanDerPol::num_params, VanDerPol::fixed_dim},
+      {"linear", Linear::order, Linear::num_params, Linear::fixed_dim},
+      {"burgers", Burgers::order, Burgers::num_params, Burgers::fixed_dim},
+  };
+  return table;
+}
+static const VfInfo* vf_info(int id) {
+  auto& t = vf_table();
+  return (id >= 0 && id < (int)t.size()) ? &t[id] : nullptr;
+}
+
+static std::vector<AuxEntry>& aux_registry() {
+  static std::vector<AuxEntry> r;
+  return r;
+}
+void register_aux(const AuxEntry& e) {
+  for (auto& x : aux_registry())
+    if (x.vf_id == e.vf_id) {
+      x = e;
+      return;
+    }
+  aux_registry().push_back(e);
+}
+const AuxEntry* find_aux(int vf_id) {
+  for (const auto& x : aux_registry())
+    if (x.vf_id == vf_id) return &x;
+  return nullptr;
+}
 
 static int validate(const pdeq_config* c) {
   if (c == nullptr) return fail(-1, "config is NULL");
-  if (c->vf_id < 0 || c->vf_id >= VF_COUNT) return fail(-2, "unknown vf_id %d", c->vf_id);
-  const VfInfo& v = kVf[c->vf_id];
+  if (vf_info(c->vf_id) == nullptr) return fail(-2, "unknown vf_id %d", c->vf_id);
+  const VfInfo& v = *vf_info(c->vf_id);
   if (c->num_derivatives < 1 || c->num_derivatives + 1 > PDEQ_MAX_COEFFS)
     return fail(-3, "num_derivatives=%d outside [1, %d]", c->num_derivatives, PDEQ_MAX_COEFFS - 1);
   if (c->num_derivatives + 1 <= v.order)
@@ -99,7 +125,7 @@ static const LoopEntry* select_loop(const pdeq_config* c) {
   }
   // K3: dense factorisation, CTA per instance, filter only; the work buffer must fit in shared memory
   if (fact == PDEQ_FACT_DENSE && !fp) {
-    const DenseSmemLayout lay = DenseSmemLayout::make(c->num_derivatives + 1, c->ode_dim, kVf[c->vf_id].order, true);
+    const DenseSmemLayout lay = DenseSmemLayout::make(c->num_derivatives + 1, c->ode_dim, vf_info(c->vf_id)->order, true);
     if (lay.total * sizeof(double) <= 227 * 1024) {
       const LoopEntry* e = find_loop({c->vf_id, c->num_derivatives, fact, 0, ts0, 0});
       if (e != nullptr) return e;
@@ -129,13 +155,29 @@ const char* pdeq_last_error(void) { return g_err; }
 
 int pdeq_vf_id(const char* name) {
   if (name == nullptr) return -1;
-  for (int i = 0; i < VF_COUNT; ++i)
-    if (std::strcmp(name, kVf[i].name) == 0) return i;
+  const auto& t = vf_table();
+  for (int i = 0; i < (int)t.size(); ++i)
+    if (std::strcmp(name, t[i].name) == 0) return i;
   return -1;
 }
-int pdeq_vf_num_params(int vf_id) { return (vf_id >= 0 && vf_id < VF_COUNT) ? kVf[vf_id].num_params : -1; }
-int pdeq_vf_ode_order(int vf_id) { return (vf_id >= 0 && vf_id < VF_COUNT) ? kVf[vf_id].order : -1; }
-int pdeq_vf_dim(int vf_id) { return (vf_id >= 0 && vf_id < VF_COUNT) ? kVf[vf_id].fixed_dim : -1; }
+int pdeq_vf_num_params(int vf_id) { return vf_info(vf_id) ? vf_info(vf_id)->num_params : -1; }
+int pdeq_vf_ode_order(int vf_id) { return vf_info(vf_id) ? vf_info(vf_id)->order : -1; }
+int pdeq_vf_dim(int vf_id) { return vf_info(vf_id) ? vf_info(vf_id)->fixed_dim : -1; }
+
+int pdeq_register_vf(const char* name, int32_t ode_order, int32_t num_params, int32_t fixed_dim) {
+  if (name == nullptr || name[0] == 0 || std::strlen(name) >= sizeof(VfInfo{}.name))
+    return fail(-2, "vector-field name must have 1..63 characters");
+  if (ode_order < 1 || ode_order >= PDEQ_MAX_COEFFS) return fail(-3, "bad ode_order %d", ode_order);
+  if (num_params < 0 || fixed_dim < 0) return fail(-4, "num_params / fixed_dim must be non-negative");
+  if (pdeq_vf_id(name) >= 0) return fail(-2, "vector field '%s' is already registered", name);
+  VfInfo v{};
+  std::strncpy(v.name, name, sizeof(v.name) - 1);
+  v.order = ode_order;
+  v.num_params = num_params;
+  v.fixed_dim = fixed_dim;
+  vf_table().push_back(v);
+  return (int)vf_table().size() - 1;
+}
 
 int pdeq_config_supported(const pdeq_config* cfg) {
   int rc = validate(cfg);
@@ -143,7 +185,7 @@ int pdeq_config_supported(const pdeq_config* cfg) {
   if (select_loop(cfg) == nullptr)
     return fail(-10,
                 "no kernel for vf=%s nu=%d d=%d factorisation=%d constraint=%d strategy=%d",
-                kVf[cfg->vf_id].name, cfg->num_derivatives, cfg->ode_dim, cfg->factorisation, cfg->constraint,
+                vf_info(cfg->vf_id)->name, cfg->num_derivatives, cfg->ode_dim, cfg->factorisation, cfg->constraint,
                 cfg->strategy);
   return 0;
 }
@@ -163,7 +205,7 @@ static int check_common(const pdeq_config* cfg, const pdeq_problem* pr, const pd
   if (pr->num_instances < 0) return fail(-20, "negative num_instances");
   if (T < 1) return fail(-21, "need at least one checkpoint");
   if (pr->tcoeffs == nullptr) return fail(-22, "tcoeffs is NULL");
-  if (kVf[cfg->vf_id].num_params > 0 && pr->params == nullptr) return fail(-22, "params is NULL");
+  if (vf_info(cfg->vf_id)->num_params > 0 && pr->params == nullptr) return fail(-22, "params is NULL");
   if (so->t == nullptr || so->mean == nullptr || so->num_steps == nullptr || so->status == nullptr)
     return fail(-23, "solution.t/mean/num_steps/status must be non-NULL");
   if (ws == nullptr || ws_bytes < pdeq_workspace_bytes(cfg, pr->num_instances, T))

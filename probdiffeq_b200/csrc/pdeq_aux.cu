@@ -2,183 +2,13 @@
 // step size, terminal-value log-marginal-likelihood. All are generic in the ODE dimension d.
 #include <cuda_runtime.h>
 
-#include "pdeq_dispatch.cuh"
+#include "pdeq_aux_kernels.cuh"
 
 namespace pdeq {
 
 int api_fail(int code, const char* fmt, ...);       // pdeq_api.cu
 int api_cuda_fail(cudaError_t e, const char* where);  // pdeq_api.cu
 int api_validate(const pdeq_config* c);              // pdeq_api.cu
-
-// ---------------------------------------------------------------------------------------------------
-// Taylor-mode initialisation (probdiffeq/_probdiffeq/jet_expansion_algorithms.py:49-177).
-// One launch per new coefficient ("pass"); thread (b, i) evaluates component i of the vector field on the
-// truncated series built from the coefficients known so far and writes u^(pass+q)_i.
-// `out` [B][n][d] holds unnormalised derivatives and doubles as the workspace.
-// ---------------------------------------------------------------------------------------------------
-template <int KS>
-struct GlobalSeriesAcc {
-  const double* __restrict__ U;  // [n][d] of one instance, unnormalised derivatives
-  int d, known;                  // coefficients 0..known-1 are valid
-  PDEQ_DI Series<KS> operator()(int j, int i) const {
-    Series<KS> s;
-    double kfact = 1.0;  // k!
-#pragma unroll
-    for (int k = 0; k < KS; ++k) {
-      if (k > 0) kfact *= double(k);
-      s.c[k] = (k + j < known) ? U[(k + j) * d + i] / kfact : 0.0;  // (u^(j))_k = u^(k+j) / k!
-    }
-    return s;
-  }
-};
-
-template <class VF, int KS>
-__global__ void taylor_pass_kernel(int64_t B, int n, int d, int pass, const double* __restrict__ params,
-                                   int64_t params_stride, double t0, double* __restrict__ out) {
-  constexpr int q = VF::order, P = VF::num_params > 0 ? VF::num_params : 1;
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= B * d) return;
-  const int64_t b = gid / d;
-  const int i = (int)(gid % d);
-  double par[P];
-#pragma unroll
-  for (int k = 0; k < P; ++k) par[k] = VF::num_params > 0 ? params[b * params_stride + k] : 0.0;
-  GlobalSeriesAcc<KS> acc{out + b * (int64_t)n * d, d, pass + q};
-  const Series<KS> F = VF::template component<Series<KS>>(i, d, acc, par, t0);
-  double fk = 0.0, pf = 1.0;  // F.c[pass] * pass!  == u^(pass+q)
-#pragma unroll
-  for (int k = 0; k < KS; ++k) {
-    if (k > 0) pf *= double(k);
-    if (k == pass) fk = F.c[k] * pf;
-  }
-  out[(b * n + pass + q) * d + i] = fk;
-}
-
-template <class VF, int KS>
-static cudaError_t taylor_run(int64_t B, int n, int d, const double* u0, const double* params,
-                              int64_t params_stride, double t0, double* out, cudaStream_t s) {
-  constexpr int q = VF::order;
-  // copy the initial values into the first q coefficient slots
-  cudaError_t e = cudaMemcpy2DAsync(out, sizeof(double) * n * d, u0, sizeof(double) * q * d,
-                                    sizeof(double) * q * d, B, cudaMemcpyDeviceToDevice, s);
-  if (e != cudaSuccess) return e;
-  const int threads = 128;
-  const int64_t total = B * d;
-  const int grid = (int)((total + threads - 1) / threads);
-  for (int pass = 0; pass < n - q; ++pass) {
-    taylor_pass_kernel<VF, KS><<<grid, threads, 0, s>>>(B, n, d, pass, params, params_stride, t0, out);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-  }
-  return cudaSuccess;
-}
-
-template <class VF>
-static cudaError_t taylor_dispatch_ks(int ks, int64_t B, int n, int d, const double* u0, const double* params,
-                                      int64_t ps, double t0, double* out, cudaStream_t s) {
-  switch (ks) {
-    case 1: return taylor_run<VF, 1>(B, n, d, u0, params, ps, t0, out, s);
-    case 2: return taylor_run<VF, 2>(B, n, d, u0, params, ps, t0, out, s);
-    case 3: return taylor_run<VF, 3>(B, n, d, u0, params, ps, t0, out, s);
-    case 4: return taylor_run<VF, 4>(B, n, d, u0, params, ps, t0, out, s);
-    case 5: return taylor_run<VF, 5>(B, n, d, u0, params, ps, t0, out, s);
-    case 6: return taylor_run<VF, 6>(B, n, d, u0, params, ps, t0, out, s);
-    case 7: return taylor_run<VF, 7>(B, n, d, u0, params, ps, t0, out, s);
-    default: return cudaErrorInvalidValue;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// ivpsolve.dt0 (probdiffeq/_ivpsolve/stepsize_initialisers.py:7-21): scale * ||u0|| / (||f(u0)|| + nugget).
-// One warp per instance; lanes stride over the components.
-// ---------------------------------------------------------------------------------------------------
-struct GlobalAcc {
-  const double* __restrict__ u;  // [order][d]
-  int d;
-  PDEQ_DI double operator()(int k, int i) const { return u[k * d + i]; }
-};
-
-template <class VF>
-__global__ void dt0_kernel(int64_t B, int d, const double* __restrict__ u0, const double* __restrict__ params,
-                           int64_t params_stride, double t0, double scale, double nugget,
-                           double* __restrict__ out) {
-  constexpr int q = VF::order, P = VF::num_params > 0 ? VF::num_params : 1;
-  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
-  const int lane = threadIdx.x % 32;
-  if (b >= B) return;
-  double par[P];
-#pragma unroll
-  for (int k = 0; k < P; ++k) par[k] = VF::num_params > 0 ? params[b * params_stride + k] : 0.0;
-  GlobalAcc acc{u0 + b * (int64_t)q * d, d};
-  double su = 0.0, sf = 0.0;
-  for (int i = lane; i < d; i += 32) {
-    const double ui = acc(0, i);
-    const double fi = VF::template component<double>(i, d, acc, par, t0);
-    su = fma(ui, ui, su);
-    sf = fma(fi, fi, sf);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    su += __shfl_xor_sync(0xffffffffu, su, o);
-    sf += __shfl_xor_sync(0xffffffffu, sf, o);
-  }
-  if (lane == 0) out[b] = scale * sqrt(su) / (sqrt(sf) + nugget);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// ivpsolve.dt0_adaptive (probdiffeq/_ivpsolve/stepsize_initialisers.py:24-64; Hairer et al., Sec. II.4).
-// First-order ODEs only, as in the reference. The Euler point y1 = y0 + h0 f(y0) is evaluated on the fly.
-// ---------------------------------------------------------------------------------------------------
-template <class VF>
-struct EulerAcc {
-  GlobalAcc base;
-  const double* par;
-  double t0, h0;
-  PDEQ_DI double operator()(int k, int i) const {
-    return base(k, i) + h0 * VF::template component<double>(i, base.d, base, par, t0);
-  }
-};
-
-template <class VF>
-__global__ void dt0_adaptive_kernel(int64_t B, int d, const double* __restrict__ u0,
-                                    const double* __restrict__ params, int64_t params_stride, double t0,
-                                    double rate, double rtol, double atol, double* __restrict__ out) {
-  constexpr int P = VF::num_params > 0 ? VF::num_params : 1;
-  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
-  const int lane = threadIdx.x % 32;
-  if (b >= B) return;
-  double par[P];
-#pragma unroll
-  for (int k = 0; k < P; ++k) par[k] = VF::num_params > 0 ? params[b * params_stride + k] : 0.0;
-  GlobalAcc acc{u0 + b * (int64_t)d, d};
-  double s0 = 0.0, s1 = 0.0;
-  for (int i = lane; i < d; i += 32) {
-    const double yi = acc(0, i);
-    const double fi = VF::template component<double>(i, d, acc, par, t0);
-    s0 = fma(yi, yi, s0);
-    s1 = fma(fi, fi, s1);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-  }
-  const double d0 = sqrt(s0), d1 = sqrt(s1);
-  const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-  EulerAcc<VF> acc1{acc, par, t0, h0};
-  double s2 = 0.0;
-  for (int i = lane; i < d; i += 32) {
-    const double f0 = VF::template component<double>(i, d, acc, par, t0);
-    const double f1 = VF::template component<double>(i, d, acc1, par, t0 + h0);
-    const double w = (f1 - f0) / (atol + fabs(acc(0, i)) * rtol);
-    s2 = fma(w, w, s2);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-  const double d2 = sqrt(s2) / h0;
-  const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 1.0 / (rate + 1.0));
-  if (lane == 0) out[b] = fmin(100.0 * h0, h1);
-}
 
 // ---------------------------------------------------------------------------------------------------
 // loss_lml_terminal_values for the isotropic and block-diagonal factorisations
@@ -493,16 +323,16 @@ __global__ void lml_reduce_kernel(int64_t B, int d, const double* __restrict__ p
 
 using namespace pdeq;
 
-#define PDEQ_VF_SWITCH(vf_id, CALL)                                 \
-  switch (vf_id) {                                                  \
-    case VF_LOTKA_VOLTERRA: { using VF = LotkaVolterra; CALL; } break; \
-    case VF_PLEIADES: { using VF = Pleiades; CALL; } break;         \
-    case VF_HIRES: { using VF = Hires; CALL; } break;               \
-    case VF_VANDERPOL: { using VF = VanDerPol; CALL; } break;       \
-    case VF_LINEAR: { using VF = Linear; CALL; } break;             \
-    case VF_BURGERS: { using VF = Burgers; CALL; } break;           \
-    default: break;                                                 \
-  }
+// the built-in vector fields register their Taylor / step-size routines here; plug-ins do the same from their own
+// translation unit (pdeq_aux_kernels.cuh)
+namespace {
+AuxRegistrar<LotkaVolterra> aux_lotka_volterra;
+AuxRegistrar<Pleiades> aux_pleiades;
+AuxRegistrar<Hires> aux_hires;
+AuxRegistrar<VanDerPol> aux_vanderpol;
+AuxRegistrar<Linear> aux_linear;
+AuxRegistrar<Burgers> aux_burgers;
+}  // namespace
 
 extern "C" {
 
@@ -514,9 +344,9 @@ int pdeq_taylor_init(const pdeq_config* cfg, int64_t num_instances, const double
   if (pdeq_vf_num_params(cfg->vf_id) > 0 && params == nullptr) return api_fail(-22, "params is NULL");
   if (num_instances == 0) return 0;
   const int n = cfg->num_derivatives + 1, d = cfg->ode_dim, q = pdeq_vf_ode_order(cfg->vf_id);
-  cudaError_t e = cudaErrorInvalidValue;
-  PDEQ_VF_SWITCH(cfg->vf_id, e = taylor_dispatch_ks<VF>(n - q, num_instances, n, d, u0, params, params_stride, t0,
-                                                        tcoeffs, (cudaStream_t)stream));
+  const AuxEntry* aux = find_aux(cfg->vf_id);
+  if (aux == nullptr) return api_fail(-10, "no Taylor initialisation registered for vf_id %d", cfg->vf_id);
+  cudaError_t e = aux->taylor(n - q, num_instances, n, d, u0, params, params_stride, t0, tcoeffs, (cudaStream_t)stream);
   if (e != cudaSuccess) return api_cuda_fail(e, "taylor_init");
   return 0;
 }
@@ -528,11 +358,10 @@ int pdeq_dt0(const pdeq_config* cfg, int64_t num_instances, const double* u0, co
   if (u0 == nullptr || out == nullptr) return api_fail(-22, "u0/out is NULL");
   if (pdeq_vf_num_params(cfg->vf_id) > 0 && params == nullptr) return api_fail(-22, "params is NULL");
   if (num_instances == 0) return 0;
-  const int threads = 128;
-  const int grid = (int)((num_instances * 32 + threads - 1) / threads);
-  PDEQ_VF_SWITCH(cfg->vf_id, (dt0_kernel<VF><<<grid, threads, 0, (cudaStream_t)stream>>>(
-                                 num_instances, cfg->ode_dim, u0, params, params_stride, t0, scale, nugget, out)));
-  cudaError_t e = cudaGetLastError();
+  const AuxEntry* aux = find_aux(cfg->vf_id);
+  if (aux == nullptr) return api_fail(-10, "no dt0 registered for vf_id %d", cfg->vf_id);
+  cudaError_t e = aux->dt0(num_instances, cfg->ode_dim, u0, params, params_stride, t0, scale, nugget, out,
+                           (cudaStream_t)stream);
   if (e != cudaSuccess) return api_cuda_fail(e, "dt0");
   return 0;
 }
@@ -547,12 +376,10 @@ int pdeq_dt0_adaptive(const pdeq_config* cfg, int64_t num_instances, const doubl
     return api_fail(-5, "dt0_adaptive is defined for first-order ODEs only (stepsize_initialisers.py:37-38)");
   if (pdeq_vf_num_params(cfg->vf_id) > 0 && params == nullptr) return api_fail(-22, "params is NULL");
   if (num_instances == 0) return 0;
-  const int threads = 128;
-  const int grid = (int)((num_instances * 32 + threads - 1) / threads);
-  PDEQ_VF_SWITCH(cfg->vf_id, (dt0_adaptive_kernel<VF><<<grid, threads, 0, (cudaStream_t)stream>>>(
-                                 num_instances, cfg->ode_dim, u0, params, params_stride, t0,
-                                 error_contraction_rate, rtol, atol, out)));
-  cudaError_t e = cudaGetLastError();
+  const AuxEntry* aux = find_aux(cfg->vf_id);
+  if (aux == nullptr) return api_fail(-10, "no dt0_adaptive registered for vf_id %d", cfg->vf_id);
+  cudaError_t e = aux->dt0_adaptive(num_instances, cfg->ode_dim, u0, params, params_stride, t0,
+                                    error_contraction_rate, rtol, atol, out, (cudaStream_t)stream);
   if (e != cudaSuccess) return api_cuda_fail(e, "dt0_adaptive");
   return 0;
 }

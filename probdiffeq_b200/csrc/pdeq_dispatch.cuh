@@ -67,7 +67,9 @@ cudaError_t k1_launch(const LoopArgs& a, void*, size_t, cudaStream_t stream) {
 template <class VF, int NU, int FACT, int D, bool TS0>
 struct K1Registrar {
   static size_t ws(const pdeq_config&, int64_t, int32_t) { return 256; }
-  K1Registrar() { register_loop({{VF::id, NU, FACT, D, TS0 ? 1 : 0, 0}, &k1_launch<VF, NU, FACT, D, TS0>, &ws, "thread"}); }
+  explicit K1Registrar(int vf_id = VF::id) {
+    register_loop({{vf_id, NU, FACT, D, TS0 ? 1 : 0, 0}, &k1_launch<VF, NU, FACT, D, TS0>, &ws, "thread"});
+  }
 };
 
 #define PDEQ_INSTANTIATE_K1(VF, NU, D)                                              \
@@ -177,8 +179,8 @@ cudaError_t k2_launch(const LoopArgs& a, void* workspace, size_t workspace_bytes
 
 template <class VF, int NU, int FACT, bool TS0, bool FP>
 struct K2Registrar {
-  K2Registrar() {
-    register_loop({{VF::id, NU, FACT, 0, TS0 ? 1 : 0, FP ? 1 : 0}, &k2_launch<VF, NU, FACT, TS0, FP>,
+  explicit K2Registrar(int vf_id = VF::id) {
+    register_loop({{vf_id, NU, FACT, 0, TS0 ? 1 : 0, FP ? 1 : 0}, &k2_launch<VF, NU, FACT, TS0, FP>,
                    &k2_workspace<VF, NU, FACT, TS0, FP>, "group"});
   }
 };
@@ -208,9 +210,9 @@ cudaError_t k3_launch(const LoopArgs& a, void*, size_t, cudaStream_t stream) {
 template <class VF, int NU>
 struct K3Registrar {
   static size_t ws(const pdeq_config&, int64_t, int32_t) { return 256; }
-  K3Registrar() {
-    register_loop({{VF::id, NU, PDEQ_FACT_DENSE, 0, 1, 0}, &k3_launch<VF, NU, true>, &ws, "dense"});
-    register_loop({{VF::id, NU, PDEQ_FACT_DENSE, 0, 0, 0}, &k3_launch<VF, NU, false>, &ws, "dense"});
+  explicit K3Registrar(int vf_id = VF::id) {
+    register_loop({{vf_id, NU, PDEQ_FACT_DENSE, 0, 1, 0}, &k3_launch<VF, NU, true>, &ws, "dense"});
+    register_loop({{vf_id, NU, PDEQ_FACT_DENSE, 0, 0, 0}, &k3_launch<VF, NU, false>, &ws, "dense"});
   }
 };
 #define PDEQ_INSTANTIATE_K3(VF, NU) static K3Registrar<VF, NU> _k3_##VF##_##NU;

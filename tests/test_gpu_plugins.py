@@ -1,0 +1,85 @@
+"""user-supplied vector fields, compiled at run time into a plug-in (probdiffeq_b200/plugins.py).
+
+(1) A clone of the built-in Lotka-Volterra functor must reproduce the built-in kernels bit for bit.
+(2) A right-hand side that is not built in (logistic growth) is checked against the oracle like every other path."""
+
+import numpy as np
+import pytest
+
+import pdeq_test_helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _solve(vf, u0, *, constraint="ts0", t1=2.0):
+    from probdiffeq_b200 import ivpsolve, probdiffeq
+
+    ssm = probdiffeq.state_space_model_isotropic()
+    tcoeffs, _ = probdiffeq.jetexpand_ode_padded_scan(num=4)(vf, (u0,), t=0.0)
+    cons = getattr(ssm, "constraint_ode_" + constraint)(vf)
+    solver = probdiffeq.solver_mle(strategy=probdiffeq.strategy_filter(), constraint=cons)
+    error = probdiffeq.error_residual_std(constraint=cons)
+    solve = ivpsolve.solve_adaptive_save_at(solver=solver, error=error, control=ivpsolve.control_integral())
+    dt0 = ivpsolve.dt0(vf, (u0,), t=0.0)
+    sol = solve(ssm.prior_wiener_integrated(tcoeffs), save_at=np.linspace(0.0, t1, 9), atol=1e-6, rtol=1e-4, dt0=dt0)
+    return tcoeffs, dt0, sol
+
+
+@pytest.mark.parametrize("constraint", ["ts0", "ts1"])
+def test_plugin_clone_of_lotka_volterra_is_bitwise_the_builtin(cuda, constraint):
+    import torch
+
+    from probdiffeq_b200 import plugins, probdiffeq
+
+    params, u0 = H.lv_ensemble(64, seed=71)
+    spec = {k: v for k, v in plugins.LOTKA_VOLTERRA_CLONE.items()}
+    vf_plugin = plugins.ode_from_cuda("lotka_volterra_user", params=params, **spec)
+    vf_builtin = probdiffeq.ode("lotka_volterra", params=params)
+    assert vf_plugin.vf_id >= 6 and vf_plugin.order == 1 and vf_plugin.num_params == 4
+    tc_p, dt0_p, sol_p = _solve(vf_plugin, u0, constraint=constraint)
+    tc_b, dt0_b, sol_b = _solve(vf_builtin, u0, constraint=constraint)
+    torch.cuda.synchronize()
+    assert torch.equal(tc_p, tc_b) and torch.equal(dt0_p, dt0_b)
+    assert int(sol_p.status.abs().max()) == 0
+    assert torch.equal(sol_p.num_steps, sol_b.num_steps)
+    assert torch.equal(sol_p.u.mean_flat, sol_b.u.mean_flat)
+    assert torch.equal(sol_p.u.cholesky_flat, sol_b.u.cholesky_flat)
+    assert torch.equal(sol_p.output_scale, sol_b.output_scale)
+
+
+@pytest.mark.parametrize("constraint", ["ts0", "ts1"])
+def test_plugin_logistic_matches_the_oracle(cuda, constraint):
+    import torch
+
+    from oracle import ivpsolve as o_ivp
+    from oracle import probdiffeq as o_pdq
+    from probdiffeq_b200 import plugins
+
+    B = 6
+    rng = np.random.Generator(np.random.PCG64(72))
+    params = np.stack([rng.uniform(0.5, 3.0, size=B), rng.uniform(2.0, 5.0, size=B)], axis=1)  # rate, capacity
+    u0 = rng.uniform(0.1, 1.0, size=(B, 1))
+    vf = plugins.ode_from_cuda("logistic", params=params, **plugins.LOGISTIC)
+    tcoeffs, dt0, sol = _solve(vf, u0, constraint=constraint, t1=3.0)
+    torch.cuda.synchronize()
+    assert int(sol.status.abs().max()) == 0
+    save_at = np.linspace(0.0, 3.0, 9)
+    for b in range(B):
+        ovf = o_pdq.ode("logistic", params[b])
+        otc, _ = o_pdq.jetexpand_ode_padded_scan(num=4)(ovf, (u0[b],), t=0.0)
+        assert np.allclose(tcoeffs[b].cpu().numpy(), otc, rtol=1e-13, atol=1e-15)
+        ossm = o_pdq.state_space_model_isotropic()
+        ocons = getattr(ossm, "constraint_ode_" + constraint)(ovf)
+        osolver = o_pdq.solver_mle(strategy=o_pdq.strategy_filter(), constraint=ocons)
+        oerr = o_pdq.error_residual_std(constraint=ocons)
+        odt0 = o_ivp.dt0(ovf, (u0[b],), t=0.0)
+        assert abs(float(dt0[b]) - odt0) <= 1e-13 * odt0
+        osol = o_ivp.solve_adaptive_save_at(solver=osolver, error=oerr, control=o_ivp.control_integral(), warn=False)(
+            ossm.prior_wiener_integrated(np.asarray(otc)), save_at=save_at, atol=1e-6, rtol=1e-4, dt0=odt0
+        )
+        assert np.array_equal(sol.num_steps[b, 1:].cpu().numpy(), np.asarray(osol.num_steps)), b
+        got, ref = sol.u.mean_flat[b].cpu().numpy(), np.asarray(osol.u_mean)
+        assert np.allclose(got[:, 0], ref[:, 0], rtol=1e-9, atol=1e-12)  # the solution itself
+        assert np.allclose(got, ref, rtol=1e-5, atol=1e-8)  # all Taylor coefficients
+        exact = params[b, 1] / (1.0 + (params[b, 1] / u0[b, 0] - 1.0) * np.exp(-params[b, 0] * save_at))
+        assert np.allclose(got[:, 0, 0], exact, rtol=1e-3)  # and the closed-form logistic curve

@@ -89,6 +89,21 @@ def test_product_path_fails_loudly_without_a_gpu():
         probdiffeq.jetexpand_ode_padded_scan(num=4)(vf, (np.asarray([20.0, 20.0]),), t=0.0)
 
 
+def test_vector_field_plugin_builds_and_registers_without_a_gpu():
+    """probdiffeq_b200/plugins.py: nvcc cross-compiles the user's right-hand side; loading registers a new id."""
+    from probdiffeq_b200 import plugins
+
+    vf = plugins.ode_from_cuda("logistic", params=np.ones((3, 2)), **plugins.LOGISTIC)
+    lib = _lib.load()
+    assert vf.vf_id >= 6 and lib.pdeq_vf_id(b"logistic") == vf.vf_id
+    assert (lib.pdeq_vf_ode_order(vf.vf_id), lib.pdeq_vf_num_params(vf.vf_id), lib.pdeq_vf_dim(vf.vf_id)) == (1, 2, 1)
+    again = plugins.ode_from_cuda("logistic", params=np.ones((3, 2)), **plugins.LOGISTIC)
+    assert again.vf_id == vf.vf_id
+    with pytest.raises(ValueError, match="different signature"):
+        plugins.ode_from_cuda("logistic", dim=2, component="return u(0, i);")
+    assert lib.pdeq_register_vf(b"logistic", 1, 2, 1) < 0  # the C entry point refuses duplicates
+
+
 def test_constructors_mirror_the_reference_error_behaviour():
     from probdiffeq_b200 import ivpsolve, probdiffeq
 
