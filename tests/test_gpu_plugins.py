@@ -83,3 +83,98 @@ def test_plugin_logistic_matches_the_oracle(cuda, constraint):
         assert np.allclose(got, ref, rtol=1e-5, atol=1e-8)  # all Taylor coefficients
         exact = params[b, 1] / (1.0 + (params[b, 1] / u0[b, 0] - 1.0) * np.exp(-params[b, 0] * save_at))
         assert np.allclose(got[:, 0, 0], exact, rtol=1e-3)  # and the closed-form logistic curve
+
+
+def test_plugin_with_runtime_dimension_and_smoother(cuda):
+    """Lane-per-dimension kernels (run-time d) through a plug-in clone of `linear`: the filter is bitwise the built-in
+    kernel; the fixed-point smoother with ts1 (not instantiated for the built-in) is checked against the oracle."""
+    import torch
+
+    from oracle import ivpsolve as o_ivp
+    from oracle import probdiffeq as o_pdq
+    from probdiffeq_b200 import ivpsolve, plugins, probdiffeq
+
+    B, d = 3, 100
+    rng = np.random.Generator(np.random.PCG64(73))
+    params = rng.uniform(-1.5, -0.5, size=(B, 1))
+    u0 = rng.uniform(0.5, 1.5, size=(B, d))
+    save_at = np.linspace(0.0, 1.0, 5)
+    vf_user = plugins.ode_from_cuda("linear_user", params=params, **plugins.LINEAR_CLONE)
+    out = []
+    for vf in (vf_user, probdiffeq.ode("linear", params=params)):
+        ssm = probdiffeq.state_space_model_blockdiag()
+        tcoeffs, _ = probdiffeq.jetexpand_ode_padded_scan(num=3)(vf, (u0,), t=0.0)
+        ts0 = ssm.constraint_ode_ts0(vf)
+        solver = probdiffeq.solver_dynamic(strategy=probdiffeq.strategy_filter(), constraint=ts0)
+        error = probdiffeq.error_residual_std(constraint=ts0)
+        sol = ivpsolve.solve_adaptive_save_at(solver=solver, error=error)(
+            ssm.prior_wiener_integrated(tcoeffs), save_at=save_at, atol=1e-6, rtol=1e-4
+        )
+        assert int(sol.status.abs().max()) == 0
+        out.append(sol)
+    torch.cuda.synchronize()
+    assert torch.equal(out[0].num_steps, out[1].num_steps)
+    assert torch.equal(out[0].u.mean_flat, out[1].u.mean_flat)
+    assert torch.equal(out[0].u.cholesky_flat, out[1].u.cholesky_flat)
+    # smoother + ts1, against the oracle and the exact solution
+    ssm = probdiffeq.state_space_model_blockdiag()
+    tcoeffs, _ = probdiffeq.jetexpand_ode_padded_scan(num=3)(vf_user, (u0,), t=0.0)
+    ts1 = ssm.constraint_ode_ts1(vf_user)
+    solver = probdiffeq.solver_dynamic(strategy=probdiffeq.strategy_smoother_fixedpoint(), constraint=ts1)
+    error = probdiffeq.error_residual_std(constraint=ts1)
+    sol = ivpsolve.solve_adaptive_save_at(solver=solver, error=error)(
+        ssm.prior_wiener_integrated(tcoeffs), save_at=save_at, atol=1e-6, rtol=1e-4
+    )
+    torch.cuda.synchronize()
+    assert int(sol.status.abs().max()) == 0
+    exact = u0[:, None, :] * np.exp(params[:, :, None] * save_at[None, :, None])
+    assert np.allclose(sol.u.mean[0].cpu().numpy(), exact, rtol=1e-4)
+    ovf = o_pdq.ode("linear", params[0])
+    ossm = o_pdq.state_space_model_blockdiag()
+    ocons = ossm.constraint_ode_ts1(ovf)
+    osol = o_ivp.solve_adaptive_save_at(
+        solver=o_pdq.solver_dynamic(strategy=o_pdq.strategy_smoother_fixedpoint(), constraint=ocons),
+        error=o_pdq.error_residual_std(constraint=ocons),
+    )(ossm.prior_wiener_integrated(tcoeffs[0].cpu().numpy()), save_at=save_at, atol=1e-6, rtol=1e-4)
+    assert np.array_equal(sol.num_steps[0, 1:].cpu().numpy(), np.asarray(osol.num_steps))
+    assert np.allclose(sol.u.mean_flat[0, :, 0].cpu().numpy(), np.asarray(osol.u_mean)[:, 0], rtol=1e-9, atol=1e-12)
+
+
+def test_plugin_dense_and_second_order_clones_are_bitwise_the_builtins(cuda):
+    import torch
+
+    from probdiffeq_b200 import ivpsolve, plugins, probdiffeq
+
+    # dense factorisation (CTA per instance), Lotka-Volterra, nu = 3
+    params, u0 = H.lv_ensemble(5, seed=74)
+    sols = []
+    for vf in (plugins.ode_from_cuda("lotka_volterra_dense_user", params=params, **plugins.LOTKA_VOLTERRA_DENSE_CLONE),
+               probdiffeq.ode("lotka_volterra", params=params)):  # fmt: skip
+        ssm = probdiffeq.state_space_model_dense()
+        tcoeffs, _ = probdiffeq.jetexpand_ode_padded_scan(num=3)(vf, (u0,), t=0.0)
+        ts1 = ssm.constraint_ode_ts1(vf)
+        solver = probdiffeq.solver_dynamic(strategy=probdiffeq.strategy_filter(), constraint=ts1)
+        error = probdiffeq.error_residual_std(constraint=ts1)
+        solve = ivpsolve.solve_adaptive_terminal_values(solver=solver, error=error)
+        sols.append(solve(ssm.prior_wiener_integrated(tcoeffs), t0=0.0, t1=2.0, atol=1e-6, rtol=1e-4))
+    torch.cuda.synchronize()
+    assert int(sols[0].status.abs().max()) == 0 and torch.equal(sols[0].num_steps, sols[1].num_steps)
+    assert torch.equal(sols[0].u.mean_flat, sols[1].u.mean_flat)
+    assert torch.equal(sols[0].u.cholesky_flat, sols[1].u.cholesky_flat)
+    # second-order right-hand side (Van der Pol), thread per instance
+    rng = np.random.Generator(np.random.PCG64(75))
+    params = np.full((7, 1), 5.0)
+    u0, du0 = 2.0 * rng.uniform(0.9, 1.1, size=(7, 1)), np.zeros((7, 1))
+    sols = []
+    for vf in (plugins.ode_from_cuda("vanderpol_user", params=params, **plugins.VANDERPOL_CLONE),
+               probdiffeq.ode("vanderpol", params=params)):  # fmt: skip
+        ssm = probdiffeq.state_space_model_isotropic()
+        tcoeffs, _ = probdiffeq.jetexpand_ode_padded_scan(num=3)(vf, (u0, du0), t=0.0)
+        ts1 = ssm.constraint_ode_ts1(vf)
+        solver = probdiffeq.solver_dynamic(strategy=probdiffeq.strategy_filter(), constraint=ts1)
+        error = probdiffeq.error_state_std(constraint=ts1)
+        solve = ivpsolve.solve_adaptive_terminal_values(solver=solver, error=error)
+        sols.append(solve(ssm.prior_wiener_integrated(tcoeffs), t0=0.0, t1=3.0, atol=1e-7, rtol=1e-5))
+    torch.cuda.synchronize()
+    assert int(sols[0].status.abs().max()) == 0 and torch.equal(sols[0].num_steps, sols[1].num_steps)
+    assert torch.equal(sols[0].u.mean_flat, sols[1].u.mean_flat)
