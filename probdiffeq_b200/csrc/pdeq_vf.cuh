@@ -128,6 +128,29 @@ PDEQ_DI Series<K> constant_like(const Series<K>&, double v) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Forward-mode derivative of a functor's `component`: a Series<2> is a dual number (value, derivative), so seeding
+// one jet coordinate with 1 and reading coefficient 1 of the result gives d f_i / d u^(k)_j. This is what the
+// reference obtains from `jacfwd` (jacobians.py:93-98); a functor can use it as its `jac` instead of stating the
+// derivatives by hand.
+// ---------------------------------------------------------------------------------------------------
+template <class Acc>
+struct SeededAcc {
+  const Acc& u;
+  int k, j;
+  PDEQ_DI Series<2> operator()(int kk, int jj) const {
+    Series<2> s;
+    s.c[0] = u(kk, jj);
+    s.c[1] = (kk == k && jj == j) ? 1.0 : 0.0;
+    return s;
+  }
+};
+template <class VF, class Acc>
+PDEQ_DI double autodiff_jac(int i, int k, int j, int d, const Acc& u, const double* p, double t) {
+  const SeededAcc<Acc> seeded{u, k, j};
+  return VF::template component<Series<2>>(i, d, seeded, p, t).c[1];
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Functors. `Acc` is any callable (k, i) -> T that returns component i of the k-th jet coordinate
 // (k < order): registers for thread-per-instance kernels, shared memory for group kernels.
 // component(i, ...) returns f_i; jac(i, k, j, ...) returns d f_i / d u^(k)_j.

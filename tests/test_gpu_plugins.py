@@ -178,3 +178,27 @@ def test_plugin_dense_and_second_order_clones_are_bitwise_the_builtins(cuda):
     torch.cuda.synchronize()
     assert int(sols[0].status.abs().max()) == 0 and torch.equal(sols[0].num_steps, sols[1].num_steps)
     assert torch.equal(sols[0].u.mean_flat, sols[1].u.mean_flat)
+
+
+def test_plugin_jacobian_by_forward_mode_differentiation(cuda):
+    """Without a `jacobian` body the ts1 derivatives come from `component` evaluated on dual numbers (the reference's
+    jacfwd, jacobians.py:93-98): same solution as with the hand-written Jacobian, and as the oracle's."""
+    import torch
+
+    from probdiffeq_b200 import plugins
+
+    B = 5
+    rng = np.random.Generator(np.random.PCG64(76))
+    params = np.stack([rng.uniform(0.5, 3.0, size=B), rng.uniform(2.0, 5.0, size=B)], axis=1)
+    u0 = rng.uniform(0.1, 1.0, size=(B, 1))
+    vf_auto = plugins.ode_from_cuda("logistic_autodiff", params=params, **plugins.LOGISTIC_AUTODIFF)
+    vf_hand = plugins.ode_from_cuda("logistic", params=params, **plugins.LOGISTIC)
+    _, _, sol_auto = _solve(vf_auto, u0, constraint="ts1", t1=3.0)
+    _, _, sol_hand = _solve(vf_hand, u0, constraint="ts1", t1=3.0)
+    torch.cuda.synchronize()
+    assert int(sol_auto.status.abs().max()) == 0
+    assert torch.equal(sol_auto.num_steps, sol_hand.num_steps)
+    a, h = sol_auto.u.mean_flat.cpu().numpy(), sol_hand.u.mean_flat.cpu().numpy()
+    assert np.allclose(a[:, :, 0], h[:, :, 0], rtol=1e-11, atol=1e-13)
+    assert np.allclose(a, h, rtol=1e-6, atol=1e-9)
+    assert np.allclose(sol_auto.u.std_flat.cpu().numpy(), sol_hand.u.std_flat.cpu().numpy(), rtol=1e-6, atol=1e-12)
