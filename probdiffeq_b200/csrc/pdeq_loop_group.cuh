@@ -24,6 +24,9 @@
 
 namespace pdeq {
 
+#ifndef PDEQ_K2_WARP_FILTER_BLOCKS
+#define PDEQ_K2_WARP_FILTER_BLOCKS 3  // resident 128-thread CTAs per SM of the warp-mode filter kernels (<= 168 registers)
+#endif
 constexpr int K2_MAX_DPL = 4;       // dimensions per lane in CTA mode
 constexpr int K2_CTA_THREADS = 256;  // upper bound of a CTA-mode block
 
@@ -754,7 +757,7 @@ struct GroupLaunchInfo {
 };
 
 template <class VF, int NU, int FACT, bool TS0, bool FP, int MODE>
-__global__ void __launch_bounds__(MODE != 0 ? K2_CTA_THREADS : 128, MODE == 1 ? 2 : 1)
+__global__ void __launch_bounds__(MODE != 0 ? K2_CTA_THREADS : 128, MODE == 1 ? 2 : ((MODE == 0 && !FP) ? PDEQ_K2_WARP_FILTER_BLOCKS : 1))
     k2_loop_kernel(const __grid_constant__ LoopArgs a, const __grid_constant__ GroupLaunchInfo info) {
   extern __shared__ double smem_k2[];
   GroupLoop<VF, NU, FACT, TS0, FP, MODE>::run(a, smem_k2, info.cond_ring, info.if_scratch, info.groups_per_cta);
