@@ -126,3 +126,57 @@ def test_constructors_mirror_the_reference_error_behaviour():
         probdiffeq.loss_lml_timeseries()(np.zeros((3, 2)), posterior=object(), std=np.ones(3))
     with pytest.raises(ValueError, match="terminal"):
         probdiffeq.strategy_smoother_fixedinterval(terminal="nonsense")
+
+
+def test_error_constants_reproduce_the_full_bayes_rule():
+    """pdeq_config.err_const (probdiffeq_b200/_iwp.py): for ts0 and damp = 0 the zero-error extrapolation's factor is
+    diag(|p|) sqrt(dt) lambda q, and error_state_std's triangularisation (solvers.py:1070-1086) commutes with that
+    column scaling. The constants must give the same observed factor and coefficient std as the oracle's full
+    Bayes rule, for any step size and prior scale."""
+    from oracle import linalg as o_linalg
+    from probdiffeq_b200 import _iwp
+
+    for nu, order in ((4, 1), (3, 1), (5, 1), (4, 2)):
+        n = nu + 1
+        a, q, facts = _iwp.system_matrices(nu)
+        consts = _iwp.error_constants(nu, order)
+        for dt, lam in ((0.37, 1.0), (1e-3, 2.5), (4.2, 0.1)):
+            k = np.arange(n)
+            p = dt ** (nu - k) / facts[nu - k]  # Taylor preconditioner (utilities.py:74-84)
+            L = np.abs(p)[:, None] * (np.sqrt(dt) * lam * q)  # zero-error extrapolation: noise only
+            h = np.zeros((1, n))
+            h[0, order] = 1.0
+            r_obs, (r_cor, _gain) = o_linalg.revert_conditional(R_X_F=(h @ L).T, R_X=L.T, R_YX=np.zeros((1, 1)))
+            assert np.isclose(abs(r_obs[0, 0]), abs(consts[0]) * abs(p[order]) * np.sqrt(dt) * lam, rtol=1e-12)
+            std = np.sqrt(np.sum(r_cor**2, axis=0))  # std of every coefficient after the update
+            for i in range(n):
+                # (the observed coefficient itself comes out as an exact zero up to rounding)
+                assert np.isclose(std[i], consts[1 + i] * abs(p[i]) * np.sqrt(dt) * lam, rtol=1e-10,
+                                  atol=1e-13 * np.max(np.abs(L))), (nu, i)  # fmt: skip
+
+
+def test_problem_constants_and_posterior_default():
+    from probdiffeq_b200 import ivpsolve, problems
+
+    params, u0 = problems.lotka_volterra_ensemble(5, seed=0)
+    assert params.shape == (5, 4) and u0.shape == (5, 2) and np.all(params > 0)
+    assert problems.PLEIADES_U0.shape == (28,) and problems.HIRES_U0.shape == (8,)
+    assert problems.burgers_u0(7).shape == (7,) and abs(problems.burgers_u0(7)[0]) > 0
+
+    class _S:  # the posterior is returned by default only while the conditionals stay below POSTERIOR_AUTO_BYTES
+        class strategy:
+            kind = "fixedpoint"
+
+    class _P:
+        factorisation = "blockdiag"
+
+        def __init__(self, B):
+            import torch
+
+            self.tcoeffs = torch.empty((B, 6, 28), device="meta")
+
+    assert ivpsolve._want_posterior(None, _S, _P(64), 33, True) is True
+    assert ivpsolve._want_posterior(None, _S, _P(65536), 33, True) is False
+    assert ivpsolve._want_posterior(True, _S, _P(65536), 33, True) is True
+    _S.strategy.kind = "filter"
+    assert ivpsolve._want_posterior(None, _S, _P(64), 33, True) is False
