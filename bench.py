@@ -351,7 +351,7 @@ def run_ours(args) -> None:
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this workload, from the ncu --set full
                 # capture summarised in profiles/r1_k1_loop_lv_nu4_iso_ts0.ncu.txt (229.7 MB + 715.5 MB)
                 "traffic": 947.3e6 if B == B_DEFAULT else None, "traffic_unit": "bytes per launch (ncu)",
-                "kernel": "k1_loop_kernel<LotkaVolterra,4,isotropic,2,ts0>",
+                "kernel": f"k1_loop_kernel<LotkaVolterra,4,isotropic,2,ts0,SPEC={lib.pdeq_k1_spec_choice()}>",
                 "flops_per_attempt": fl, "attempts_per_launch": attempts_pass,
                 "peak_source": "pdeq_fp64_peak_probe (FP64 FMA, measured in this run; MEASURED_PEAKS.json has no FP64 figure)",
                 "hbm": {"algorithmic_bytes_per_launch": bytes_algo, "achieved_gbs": bytes_algo / kernel_s / 1e9,

@@ -247,6 +247,13 @@ int pdeq_allreduce_sum_f64(void* nccl_comm, double* buf, int64_t n, void* stream
    FMA chains on every SM and returns the elapsed milliseconds in *ms and the FLOP count in *flops. */
 int pdeq_fp64_peak_probe(int32_t iters, double* ms, double* flops, void* stream);
 
+/* Which build of the thread-per-instance loop kernel the launcher uses when a configuration matches the
+   compile-time specialised combination (adaptive + clip_dt, `solver`, error_state_std on coefficient 0, ts0,
+   damp = 0, unit prior scale): 0 = the general kernel, 1..5 = the specialised builds (csrc/pdeq_loop_thread.cuh).
+   The library's default can be overridden per launch through the environment variable PDEQ_K1_SPEC; every build
+   returns bitwise the same results. */
+int pdeq_k1_spec_choice(void);
+
 #ifdef __cplusplus
 }
 #endif

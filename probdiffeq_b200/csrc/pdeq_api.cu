@@ -151,6 +151,8 @@ using namespace pdeq;
 extern "C" {
 
 int pdeq_version(void) { return PDEQ_VERSION; }
+
+int pdeq_k1_spec_choice(void) { return k1_spec_choice(); }
 const char* pdeq_last_error(void) { return g_err; }
 
 int pdeq_vf_id(const char* name) {

@@ -42,12 +42,13 @@ int device_sm_count();
 // ---------------------------------------------------------------------------------------------------
 // K1 launcher
 // ---------------------------------------------------------------------------------------------------
-template <class VF, int NU, int FACT, int D, bool TS0>
-cudaError_t k1_launch(const LoopArgs& a, void*, size_t, cudaStream_t stream) {
-  using TL = ThreadLoop<VF, NU, FACT, D, TS0>;
-  auto kern = k1_loop_kernel<VF, NU, FACT, D, TS0>;
+template <class VF, int NU, int FACT, int D, bool TS0, int SPEC>
+cudaError_t k1_launch_impl(const LoopArgs& a, cudaStream_t stream) {
+  using TL = ThreadLoop<VF, NU, FACT, D, TS0, SPEC>;
+  auto kern = k1_loop_kernel<VF, NU, FACT, D, TS0, SPEC>;
   const bool needs_interp = a.fixed_grid == 0 && a.cfg.clip_dt == 0;
-  const size_t smem = needs_interp ? size_t(TL::IF_SLOTS) * K1_THREADS * sizeof(double) : 0;
+  const size_t smem = TL::SMS ? size_t(TL::ST_SLOTS) * K1_THREADS * sizeof(double)
+                              : (needs_interp ? size_t(TL::IF_SLOTS) * K1_THREADS * sizeof(double) : 0);
   cudaError_t err;
   if (smem > 48 * 1024) {
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -64,13 +65,47 @@ cudaError_t k1_launch(const LoopArgs& a, void*, size_t, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-template <class VF, int NU, int FACT, int D, bool TS0>
+// Which specialised loop to use when the configuration matches: PDEQ_K1_SPEC=0 in the environment forces the
+// general kernel (A/B measurements, bitwise comparison tests), 1 / 2 pick the 3- / 4-CTAs-per-SM build, 3 / 4 the
+// builds with the accepted state in shared memory (ThreadLoop).
+#ifndef PDEQ_K1_SPEC_DEFAULT
+#define PDEQ_K1_SPEC_DEFAULT 1
+#endif
+inline int k1_spec_choice() {
+  const char* e = std::getenv("PDEQ_K1_SPEC");
+  const int c = e == nullptr ? PDEQ_K1_SPEC_DEFAULT : std::atoi(e);
+  return (c >= 0 && c <= 5) ? c : PDEQ_K1_SPEC_DEFAULT;
+}
+
+template <class VF, int NU, int FACT, int D, bool TS0, bool HAS_SPEC = false>
+cudaError_t k1_launch(const LoopArgs& a, void*, size_t, cudaStream_t stream) {
+  if constexpr (HAS_SPEC && TS0) {
+    if (k1_spec_matches(a, TS0)) {
+      const int spec = k1_spec_choice();
+      if (spec == 1) return k1_launch_impl<VF, NU, FACT, D, TS0, 1>(a, stream);
+      if (spec == 2) return k1_launch_impl<VF, NU, FACT, D, TS0, 2>(a, stream);
+      if (spec == 3) return k1_launch_impl<VF, NU, FACT, D, TS0, 3>(a, stream);
+      if (spec == 4) return k1_launch_impl<VF, NU, FACT, D, TS0, 4>(a, stream);
+      if (spec == 5) return k1_launch_impl<VF, NU, FACT, D, TS0, 5>(a, stream);
+    }
+  }
+  return k1_launch_impl<VF, NU, FACT, D, TS0, 0>(a, stream);
+}
+
+template <class VF, int NU, int FACT, int D, bool TS0, bool HAS_SPEC = false>
 struct K1Registrar {
   static size_t ws(const pdeq_config&, int64_t, int32_t) { return 256; }
   explicit K1Registrar(int vf_id = VF::id) {
-    register_loop({{vf_id, NU, FACT, D, TS0 ? 1 : 0, 0}, &k1_launch<VF, NU, FACT, D, TS0>, &ws, "thread"});
+    register_loop({{vf_id, NU, FACT, D, TS0 ? 1 : 0, 0}, &k1_launch<VF, NU, FACT, D, TS0, HAS_SPEC>, &ws, "thread"});
   }
 };
+
+// As PDEQ_INSTANTIATE_K1, with the compile-time specialised loop (ThreadLoop SPEC = 1) behind the isotropic ts0 entry.
+#define PDEQ_INSTANTIATE_K1_WITH_SPEC(VF, NU, D)                                          \
+  static K1Registrar<VF, NU, PDEQ_FACT_ISOTROPIC, D, true, true> _k1_iso0_##VF##_##NU##_##D; \
+  static K1Registrar<VF, NU, PDEQ_FACT_ISOTROPIC, D, false> _k1_iso1_##VF##_##NU##_##D;      \
+  static K1Registrar<VF, NU, PDEQ_FACT_BLOCKDIAG, D, true> _k1_bd0_##VF##_##NU##_##D;        \
+  static K1Registrar<VF, NU, PDEQ_FACT_BLOCKDIAG, D, false> _k1_bd1_##VF##_##NU##_##D;
 
 #define PDEQ_INSTANTIATE_K1(VF, NU, D)                                              \
   static K1Registrar<VF, NU, PDEQ_FACT_ISOTROPIC, D, true> _k1_iso0_##VF##_##NU##_##D; \

@@ -47,6 +47,8 @@ constexpr int K1_THREADS = 128;
 #define PDEQ_K1_MIN_BLOCKS(FACT) ((FACT) == PDEQ_FACT_ISOTROPIC ? 3 : 2)
 #endif
 
+#define PDEQ_K1_SPEC_MIN_BLOCKS(SPEC) ((SPEC) == 5 ? 6 : ((SPEC) == 4 ? 5 : ((SPEC) >= 2 ? 4 : 3)))
+
 template <int n>
 PDEQ_DI double ipow_small(double x, int k) {
   double r = 1.0;
@@ -57,15 +59,37 @@ PDEQ_DI double ipow_small(double x, int k) {
   return r;
 }
 
-PDEQ_DI double safe_sqrt(double x) { return x > 0.0 ? fast_sqrt(x) : 0.0; }
+// sqrt(x) for x > 0, else 0 -- in select form (no branch: the attempt body stays one basic block, which lets the
+// scheduler overlap the error estimate with the triangularisations); same value as `x > 0 ? fast_sqrt(x) : 0`.
+PDEQ_DI double safe_sqrt(double x) {
+  const bool pos = x > 0.0;
+  const double r = fast_sqrt(pos ? x : 1.0);
+  return pos ? r : 0.0;
+}
 
-template <class VF, int NU, int FACT, int D, bool TS0>
+// SPEC = 0: every solver / error / control option is a run-time (warp-uniform) branch on pdeq_config.
+// SPEC = 1: the headline combination is fixed at compile time -- adaptive with clip_dt, `solver` (no calibration),
+//           error_state_std on coefficient 0 through the constant-matrix shortcut (ts0, damp = 0), scale-then-rms
+//           norm, unit prior scale. The arithmetic that remains is the SPEC = 0 arithmetic
+//           operation for operation (bitwise the same results); what goes away are the values the run-time
+//           branches keep alive (the noise-only factor Lq, calibration state), i.e. registers and spills.
+//           The launcher checks the conditions on the host (k1_spec_matches).
+// SPEC = 2: the same loop compiled for four resident CTAs per SM (128 registers) instead of three (168).
+// SPEC = 3: as 2, with the accepted state (mean and factor) resident in shared memory, one column per thread: it is
+//           read at the start of an attempt and written when the attempt is accepted, so the 25 doubles do not
+//           occupy registers during the triangularisations and the accept is 25 predicated stores instead of 50
+//           register moves. SPEC = 4 / 5: as 3, five (96 registers) / six (80) resident CTAs.
+template <class VF, int NU, int FACT, int D, bool TS0, int SPEC = 0>
 struct ThreadLoop {
+  static constexpr bool SP = SPEC != 0;
+  static constexpr bool SMS = SPEC >= 3;  // accepted state in shared memory
+  static_assert(!SP || TS0, "the specialised loop is ts0 only");
   static constexpr int n = NU + 1;
   static constexpr int q = VF::order;
   static constexpr int NB = (FACT == PDEQ_FACT_BLOCKDIAG) ? D : 1;
   static constexpr int P = VF::num_params > 0 ? VF::num_params : 1;
   static constexpr int IF_SLOTS = n * D + NB * n * n + 1;  // interp_from: mean, chol, t
+  static constexpr int ST_SLOTS = n * D + NB * (n * (n + 1)) / 2;
   static_assert(q < n, "need more Taylor coefficients than the ODE order");
 
   PDEQ_DI static constexpr int blk(int j) { return FACT == PDEQ_FACT_BLOCKDIAG ? j : 0; }
@@ -151,6 +175,42 @@ struct ThreadLoop {
     t = sm[(IF_SLOTS - 1) * nthreads + tid];
   }
 
+  // Accepted state in shared memory (SPEC >= 3), one column per thread (conflict-free).
+  PDEQ_DI static void st_store(double* __restrict__ sm, int nthreads, int tid, const double (&m)[n][D],
+                               const double (&L)[NB][n][n]) {
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) sm[(s++) * nthreads + tid] = m[i][j];
+    }
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+#pragma unroll
+        for (int j = 0; j <= i; ++j) sm[(s++) * nthreads + tid] = L[k][i][j];
+      }
+    }
+  }
+  PDEQ_DI static void st_load(const double* __restrict__ sm, int nthreads, int tid, double (&m)[n][D],
+                              double (&L)[NB][n][n]) {
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) m[i][j] = sm[(s++) * nthreads + tid];
+    }
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+#pragma unroll
+        for (int j = 0; j <= i; ++j) L[k][i][j] = sm[(s++) * nthreads + tid];
+      }
+    }
+  }
+
   // Whitened RMS of the observation residual per block (IsotropicNormal.residual_whitened_rms_flat,
   // ssm_impl_isotropic.py:203-207; BlockDiagNormal..., ssm_impl_blockdiag.py:285-292) for 1x1 factors r[k].
   PDEQ_DI static void whitened_rms(const double (&mobs)[D], const double (&r)[NB], double (&out)[NB]) {
@@ -175,8 +235,12 @@ struct ThreadLoop {
     const double(*__restrict__ Q)[PDEQ_MAX_COEFFS] = cfg.sys_q;
     const double* __restrict__ fact = cfg.factorials;
     const double* __restrict__ ifact = cfg.inv_factorials;
-    const bool adaptive = a.fixed_grid == 0;
-    const bool clip = cfg.clip_dt != 0;
+    const bool adaptive = SP ? true : a.fixed_grid == 0;
+    const bool clip = SP ? true : cfg.clip_dt != 0;
+    const int cfg_solver = SP ? (int)PDEQ_SOLVER_PLAIN : cfg.solver;
+    const int cfg_error = SP ? (int)PDEQ_ERROR_STATE_STD : cfg.error;
+    const int cfg_norm = SP ? (int)PDEQ_NORM_SCALE_THEN_RMS : cfg.error_norm;
+    const double damp = SP ? 0.0 : a.damp;
     const bool needs_interp = adaptive && !clip;
     const int T = a.T;
     const long B = a.prob.num_instances;
@@ -223,7 +287,7 @@ struct ThreadLoop {
         }
 #pragma unroll
         for (int k = 0; k < NB; ++k) {
-          prior[k] = a.prob.prior_scale != nullptr ? a.prob.prior_scale[b * a.prob.prior_scale_stride + k] : 1.0;
+          prior[k] = (!SP && a.prob.prior_scale != nullptr) ? a.prob.prior_scale[b * a.prob.prior_scale_stride + k] : 1.0;
           sig[k] = 1.0;
           run_scale[k] = 0.0;
         }
@@ -241,7 +305,9 @@ struct ThreadLoop {
         ck = 1;
         t_next = (T > 1) ? a.grid[1] : t;
         if (needs_interp) if_store(smem_if, nthreads, tid, m, L, t);
+        if (SMS) st_store(smem_if, nthreads, tid, m, L);
       }
+      if (SMS) st_load(smem_if, nthreads, tid, m, L);
 
       // ------------------------------------------------------------------ checkpoint reached?
       // adaptive: RejectionLoop.loop's interpolation switch (solvers_via_adaptive_steps.py:241-247)
@@ -278,7 +344,7 @@ struct ThreadLoop {
         }
         if (ck >= T) {
           // -------------------------------------------------------------- finish the instance
-          if (cfg.solver == PDEQ_SOLVER_MLE) {
+          if (cfg_solver == PDEQ_SOLVER_MLE) {
             // solver_mle.userfriendly_output (solvers.py:439-480): rescale everything by the calibrated scale
             double fin[NB];
 #pragma unroll
@@ -389,19 +455,19 @@ struct ThreadLoop {
       // Cholesky factor of the zero-error extrapolation (process noise only), shared by solver_dynamic and
       // the error estimators
       double Lq[NB][n][n], robs[NB];
-      const bool need_robs = adaptive ? (cfg.solver == PDEQ_SOLVER_DYNAMIC || cfg.error == PDEQ_ERROR_RESIDUAL_STD)
-                                      : (cfg.solver == PDEQ_SOLVER_DYNAMIC);
+      const bool need_robs = adaptive ? (cfg_solver == PDEQ_SOLVER_DYNAMIC || cfg_error == PDEQ_ERROR_RESIDUAL_STD)
+                                      : (cfg_solver == PDEQ_SOLVER_DYNAMIC);
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
         noise_chol<n>(p, sq * prior[k], Q, Lq[k]);
-        robs[k] = need_robs ? obs_marginal_chol<n, q, TS0>(Lq[k], h[k], a.damp) : 1.0;
+        robs[k] = need_robs ? obs_marginal_chol<n, q, TS0>(Lq[k], h[k], damp) : 1.0;
       }
 
       // solver_dynamic: calibrate the output scale before extrapolating (solvers.py:552-573)
       double sig_new[NB];
 #pragma unroll
       for (int k = 0; k < NB; ++k) sig_new[k] = 1.0;
-      if (cfg.solver == PDEQ_SOLVER_DYNAMIC) whitened_rms(mobs, robs, sig_new);
+      if (cfg_solver == PDEQ_SOLVER_DYNAMIC) whitened_rms(mobs, robs, sig_new);
 
       // extrapolate the Cholesky factor and correct (strategy_filter.predict + bayes_rule)
       double Ln[NB][n][n], gain[NB][n], ry[NB];
@@ -409,7 +475,7 @@ struct ThreadLoop {
       for (int k = 0; k < NB; ++k) {
         double Lp[n][n];
         predict_chol<n>(L[k], p, pinv, sq * prior[k] * sig_new[k], A, Q, Lp);
-        revert_obs<n, q, TS0>(Lp, h[k], a.damp, ry[k], gain[k], Ln[k]);
+        revert_obs<n, q, TS0>(Lp, h[k], damp, ry[k], gain[k], Ln[k]);
       }
       double mn[n][D];
 #pragma unroll
@@ -422,7 +488,7 @@ struct ThreadLoop {
       double run_new[NB];
 #pragma unroll
       for (int k = 0; k < NB; ++k) run_new[k] = run_scale[k];
-      if (cfg.solver == PDEQ_SOLVER_MLE) {
+      if (cfg_solver == PDEQ_SOLVER_MLE) {
         const double w1 = sqrt(ndata / (ndata + 1.0)), w2 = sqrt(1.0 / (ndata + 1.0));
         double term[NB];
         whitened_rms(mobs, ry, term);
@@ -439,7 +505,7 @@ struct ThreadLoop {
       if (adaptive) {
         double err[D], ref[D];
         int kpow;
-        if (cfg.error == PDEQ_ERROR_RESIDUAL_STD) {
+        if (cfg_error == PDEQ_ERROR_RESIDUAL_STD) {
           // solvers.py:955-968,978-991
           double se[NB];
           whitened_rms(mobs, robs, se);
@@ -450,9 +516,9 @@ struct ThreadLoop {
           kpow = q;
         } else {
           // solvers.py:1070-1086: Bayes rule on the zero-error extrapolation, std of one coefficient
-          const int idx = cfg.derivative_idx;
+          const int idx = SP ? 0 : cfg.derivative_idx;
           double rye[NB], sd[NB];
-          if (TS0 && a.damp == 0.0 && cfg.err_const[0] != 0.0) {
+          if (SP || (TS0 && damp == 0.0 && cfg.err_const[0] != 0.0)) {
             // The zero-error extrapolation's factor is a constant matrix with scaled columns, and column scalings
             // commute with the triangularisation (pdeq_config.err_const): no reflector is needed at all.
             double pq = 0.0, pi = 0.0, ci = 0.0;
@@ -475,7 +541,7 @@ struct ThreadLoop {
             for (int k = 0; k < NB; ++k) {
               double Lc[n][n], g_unused[n];
               Lc[0][0] = 0.0;
-              revert_obs<n, q, TS0, 0>(Lq[k], h[k], a.damp, rye[k], g_unused, Lc);
+              revert_obs<n, q, TS0, 0>(Lq[k], h[k], damp, rye[k], g_unused, Lc);
               sd[k] = fabs(Lc[0][0]);
             }
           } else {
@@ -487,7 +553,7 @@ struct ThreadLoop {
 #pragma unroll
                 for (int j = 0; j <= i; ++j) Lc[i][j] = 0.0;
               }
-              revert_obs<n, q, TS0>(Lq[k], h[k], a.damp, rye[k], g_unused, Lc);
+              revert_obs<n, q, TS0>(Lq[k], h[k], damp, rye[k], g_unused, Lc);
               sd[k] = row_norm<n>(Lc, idx);
             }
           }
@@ -509,14 +575,14 @@ struct ThreadLoop {
           }
           kpow = idx;
         }
-        if (cfg.error_per_unit_step) kpow += 1;
+        if (!SP && cfg.error_per_unit_step) kpow += 1;
         double escale = ipow_small<n>(dtc, kpow);  // dt^k / k!
 #pragma unroll
         for (int e = 0; e <= n; ++e) {
           if (e == kpow) escale *= ifact[e];
         }
         double norm;
-        if (cfg.error_norm == PDEQ_NORM_SCALE_THEN_RMS) {
+        if (cfg_norm == PDEQ_NORM_SCALE_THEN_RMS) {
           double ss = 0.0;
 #pragma unroll
           for (int j = 0; j < D; ++j) {
@@ -537,7 +603,7 @@ struct ThreadLoop {
           norm = (safe_sqrt(se2) * rsqrt((double)ne)) * fast_rcp(fma(a.rtol, safe_sqrt(sr2) * inv_sqrt_d, a.atol));
         }
         // error_power = norm^(-1/n) (solvers.py:995); accept iff !(error_power < 1) (solvers_via_adaptive_steps.py:256-258)
-        const double lep = neg_inv_n * log2(norm);
+        const double lep = neg_inv_n * (SP ? log2_select(norm) : log2(norm));
         accept = !(lep < 0.0);
 
         double lratio;  // log2 of the unclipped step ratio / safety
@@ -547,7 +613,7 @@ struct ThreadLoop {
         } else {
           lratio = lep;
         }
-        const double ratio = cfg.safety * exp2(lratio);
+        const double ratio = cfg.safety * (SP ? exp2_select(lratio) : exp2(lratio));
         const double sc = fmax(cfg.factor_min, fmin(ratio, cfg.factor_max));
         dt_next = sc * dtc;
         if (a.sol.trace != nullptr && nattempts <= a.sol.trace_capacity) {
@@ -568,19 +634,25 @@ struct ThreadLoop {
       dt = dt_next;
       if (accept) {
         if (needs_interp) if_store(smem_if, nthreads, tid, m, L, t);  // interp_from <- step_from (:330-338)
+        if (SMS) {
+          st_store(smem_if, nthreads, tid, mn, Ln);
+        } else {
 #pragma unroll
-        for (int i = 0; i < n; ++i) {
+          for (int i = 0; i < n; ++i) {
 #pragma unroll
-          for (int j = 0; j < D; ++j) m[i][j] = mn[i][j];
+            for (int j = 0; j < D; ++j) m[i][j] = mn[i][j];
+          }
         }
 #pragma unroll
         for (int k = 0; k < NB; ++k) {
 #pragma unroll
           for (int i = 0; i < n; ++i) {
 #pragma unroll
-            for (int j = 0; j <= i; ++j) L[k][i][j] = Ln[k][i][j];
+            for (int j = 0; j <= i; ++j) {
+              if (!SMS) L[k][i][j] = Ln[k][i][j];
+            }
           }
-          if (cfg.solver == PDEQ_SOLVER_DYNAMIC) sig[k] = sig_new[k];
+          if (cfg_solver == PDEQ_SOLVER_DYNAMIC) sig[k] = sig_new[k];
           run_scale[k] = run_new[k];
         }
         ndata += 1.0;
@@ -595,10 +667,19 @@ struct ThreadLoop {
   }
 };
 
-template <class VF, int NU, int FACT, int D, bool TS0>
-__global__ void __launch_bounds__(K1_THREADS, PDEQ_K1_MIN_BLOCKS(FACT)) k1_loop_kernel(const __grid_constant__ LoopArgs a) {
+template <class VF, int NU, int FACT, int D, bool TS0, int SPEC = 0>
+__global__ void __launch_bounds__(K1_THREADS, SPEC != 0 ? PDEQ_K1_SPEC_MIN_BLOCKS(SPEC) : PDEQ_K1_MIN_BLOCKS(FACT)) k1_loop_kernel(const __grid_constant__ LoopArgs a) {
   extern __shared__ double smem_if[];
-  ThreadLoop<VF, NU, FACT, D, TS0>::run(a, smem_if);
+  ThreadLoop<VF, NU, FACT, D, TS0, SPEC>::run(a, smem_if);
+}
+
+// Host-side test for SPEC = 1 (see ThreadLoop).
+inline bool k1_spec_matches(const LoopArgs& a, bool ts0) {
+  const pdeq_config& c = a.cfg;
+  return ts0 && a.fixed_grid == 0 && c.clip_dt != 0 && c.solver == PDEQ_SOLVER_PLAIN &&
+         c.error == PDEQ_ERROR_STATE_STD && c.derivative_idx == 0 && c.error_per_unit_step == 0 &&
+         c.error_norm == PDEQ_NORM_SCALE_THEN_RMS && a.damp == 0.0 && c.err_const[0] != 0.0 &&
+         a.prob.prior_scale == nullptr;
 }
 
 }  // namespace pdeq

@@ -1,0 +1,101 @@
+"""A/B sweep of the headline kernel's builds (PDEQ_K1_SPEC = 0..5, see csrc/pdeq_loop_thread.cuh) on one GPU.
+
+For every build: the BASELINE configs[1] ensemble (2^20 Lotka-Volterra instances unless --instances is given),
+W warm-up passes, K timed passes with an L2 flush in between (CUDA events on the launching stream), and a BITWISE
+comparison of every output (means, Cholesky factors, times, step and attempt counts) with the general kernel
+(PDEQ_K1_SPEC=0). Prints one JSON line per build and a last line naming the fastest bitwise-identical build.
+
+usage: python scripts/sweep_k1_spec.py [--instances B] [--steps K] [--warmup W] [--out FILE]
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import sys
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--instances", type=int, default=1 << 20)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--specs", default="0,1,2,3,4,5")
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+
+    import torch
+
+    from probdiffeq_b200 import ivpsolve, probdiffeq, problems
+
+    assert torch.cuda.is_available(), "needs a CUDA device"
+    dev = torch.device("cuda", 0)
+    B = args.instances
+    params_np, u0_np = problems.lotka_volterra_ensemble(B, seed=0)
+    params = torch.from_numpy(params_np).to(dev)
+    u0 = torch.from_numpy(u0_np).to(dev)
+    ssm = probdiffeq.state_space_model_isotropic()
+    vf = probdiffeq.ode("lotka_volterra", params=params)
+    tcoeffs, _ = probdiffeq.jetexpand_ode_padded_scan(num=4)(vf, (u0,), t=0.0)
+    prior = ssm.prior_wiener_integrated(tcoeffs)
+    ts0 = ssm.constraint_ode_ts0(vf)
+    solver = probdiffeq.solver(strategy=probdiffeq.strategy_filter(), constraint=ts0)
+    error = probdiffeq.error_state_std(constraint=ts0)
+    control = ivpsolve.control_proportional_integral()
+    solve = ivpsolve.solve_adaptive_terminal_values(solver=solver, error=error, control=control)
+
+    def one_pass():
+        return solve(prior, t0=0.0, t1=50.0, atol=1e-8, rtol=1e-6)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def outputs(sol):
+        return [sol.t, sol.u.mean_flat, sol.u.cholesky_flat, sol.num_steps, sol.num_attempts, sol.status]
+
+    results, ref = [], None
+    for spec in [int(s) for s in args.specs.split(",")]:
+        os.environ["PDEQ_K1_SPEC"] = str(spec)  # read by the launcher on every launch
+        for _ in range(args.warmup):
+            one_pass()
+            flush.fill_(1)
+        torch.cuda.synchronize()
+        evs, sol = [], None
+        for _ in range(args.steps):
+            flush.fill_(0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sol = one_pass()
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        ms = [a.elapsed_time(b) for a, b in evs]
+        outs = [o.clone() for o in outputs(sol)]
+        if ref is None:
+            ref = outs
+        # bitwise: compare the raw bytes (NaNs, signed zeros included)
+        same = all(torch.equal(a.contiguous().view(torch.uint8), b.contiguous().view(torch.uint8)) for a, b in zip(outs, ref))
+        steps = int(sol.num_steps.sum().item())
+        line = {
+            "spec": spec, "instances": B, "ms_mean": float(np.mean(ms)), "ms_min": float(np.min(ms)),
+            "ms": [round(x, 3) for x in ms], "accepted_steps": steps, "attempts": int(sol.num_attempts.sum().item()),
+            "steps_per_s": steps / (float(np.mean(ms)) * 1e-3), "failed": int((sol.status != 0).sum().item()),
+            "bitwise_equal_to_first": bool(same),
+        }  # fmt: skip
+        results.append(line)
+        print(json.dumps(line), flush=True)
+    ok = [r for r in results if r["bitwise_equal_to_first"]]
+    best = min(ok, key=lambda r: r["ms_mean"])
+    print(json.dumps({"best_spec": best["spec"], "ms_mean": best["ms_mean"]}), flush=True)
+    if args.out:
+        pathlib.Path(args.out).write_text(str(best["spec"]))
+
+
+if __name__ == "__main__":
+    main()
