@@ -69,7 +69,7 @@ cudaError_t k1_launch_impl(const LoopArgs& a, cudaStream_t stream) {
 // general kernel (A/B measurements, bitwise comparison tests), 1 / 2 pick the 3- / 4-CTAs-per-SM build, 3 / 4 the
 // builds with the accepted state in shared memory (ThreadLoop).
 #ifndef PDEQ_K1_SPEC_DEFAULT
-#define PDEQ_K1_SPEC_DEFAULT 1
+#define PDEQ_K1_SPEC_DEFAULT 2
 #endif
 inline int k1_spec_choice() {
   const char* e = std::getenv("PDEQ_K1_SPEC");
