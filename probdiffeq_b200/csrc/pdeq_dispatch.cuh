@@ -123,7 +123,13 @@ struct K2Plan {
   size_t smem_bytes, ring_bytes_per_group;
 };
 
-template <class VF, int NU, int FACT, bool TS0, bool FP>
+// PDEQ_K2_SPEC=0 in the environment forces the general kernel where a specialised build exists (GroupLoop SPEC).
+inline bool k2_spec_enabled() {
+  const char* e = std::getenv("PDEQ_K2_SPEC");
+  return e == nullptr || std::atoi(e) != 0;
+}
+
+template <class VF, int NU, int FACT, bool TS0, bool FP, int SPEC = 0>
 cudaError_t k2_plan(const pdeq_config& cfg, int64_t B, int32_t T, bool needs_interp, K2Plan* plan) {
   using GL = GroupLoop<VF, NU, FACT, TS0, FP, 0>;
   const int d = cfg.ode_dim;
@@ -157,7 +163,7 @@ cudaError_t k2_plan(const pdeq_config& cfg, int64_t B, int32_t T, bool needs_int
     if (err != cudaSuccess) return err;
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, plan->threads, plan->smem_bytes);
   } else {
-    auto kern = k2_loop_kernel<VF, NU, FACT, TS0, FP, 0>;
+    auto kern = k2_loop_kernel<VF, NU, FACT, TS0, FP, 0, SPEC>;
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
     if (err != cudaSuccess) return err;
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, plan->threads, plan->smem_bytes);
@@ -184,11 +190,19 @@ size_t k2_workspace(const pdeq_config& cfg, int64_t B, int32_t T) {
   return 256 + groups * plan.ring_bytes_per_group;
 }
 
-template <class VF, int NU, int FACT, bool TS0, bool FP>
+template <class VF, int NU, int FACT, bool TS0, bool FP, bool HAS_SPEC = false>
 cudaError_t k2_launch(const LoopArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   const bool needs_interp = a.fixed_grid == 0 && a.cfg.clip_dt == 0;
   K2Plan plan;
-  cudaError_t err = k2_plan<VF, NU, FACT, TS0, FP>(a.cfg, a.prob.num_instances, a.T, needs_interp, &plan);
+  // the specialised build exists for the warp-per-instance mode only (d <= 32)
+  const bool spec = HAS_SPEC && a.cfg.ode_dim <= 32 && k2_spec_matches(a) && k2_spec_enabled();
+  cudaError_t err = cudaSuccess;
+  if constexpr (HAS_SPEC) {
+    err = spec ? k2_plan<VF, NU, FACT, TS0, FP, 1>(a.cfg, a.prob.num_instances, a.T, needs_interp, &plan)
+               : k2_plan<VF, NU, FACT, TS0, FP, 0>(a.cfg, a.prob.num_instances, a.T, needs_interp, &plan);
+  } else {
+    err = k2_plan<VF, NU, FACT, TS0, FP>(a.cfg, a.prob.num_instances, a.T, needs_interp, &plan);
+  }
   if (err != cudaSuccess) return err;
   GroupLaunchInfo info;
   info.groups_per_cta = plan.groups_per_cta;
@@ -207,15 +221,18 @@ cudaError_t k2_launch(const LoopArgs& a, void* workspace, size_t workspace_bytes
     k2_loop_kernel<VF, NU, FACT, TS0, FP, 2><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);
   else if (plan.mode == 1)
     k2_loop_kernel<VF, NU, FACT, TS0, FP, 1><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);
-  else
+  else if (spec) {
+    if constexpr (HAS_SPEC)
+      k2_loop_kernel<VF, NU, FACT, TS0, FP, 0, 1><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);
+  } else
     k2_loop_kernel<VF, NU, FACT, TS0, FP, 0><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);
   return cudaGetLastError();
 }
 
-template <class VF, int NU, int FACT, bool TS0, bool FP>
+template <class VF, int NU, int FACT, bool TS0, bool FP, bool HAS_SPEC = false>
 struct K2Registrar {
   explicit K2Registrar(int vf_id = VF::id) {
-    register_loop({{vf_id, NU, FACT, 0, TS0 ? 1 : 0, FP ? 1 : 0}, &k2_launch<VF, NU, FACT, TS0, FP>,
+    register_loop({{vf_id, NU, FACT, 0, TS0 ? 1 : 0, FP ? 1 : 0}, &k2_launch<VF, NU, FACT, TS0, FP, HAS_SPEC>,
                    &k2_workspace<VF, NU, FACT, TS0, FP>, "group"});
   }
 };
@@ -251,6 +268,13 @@ struct K3Registrar {
   }
 };
 #define PDEQ_INSTANTIATE_K3(VF, NU) static K3Registrar<VF, NU> _k3_##VF##_##NU;
+
+// as PDEQ_INSTANTIATE_K2, with the specialised warp-mode builds (GroupLoop SPEC = 1) behind the two ts0 entries
+#define PDEQ_INSTANTIATE_K2_WITH_SPEC(VF, NU, FACT, TAG)                      \
+  static K2Registrar<VF, NU, FACT, true, false, true> _k2_f0_##VF##_##NU##_##TAG;  \
+  static K2Registrar<VF, NU, FACT, false, false> _k2_f1_##VF##_##NU##_##TAG;       \
+  static K2Registrar<VF, NU, FACT, true, true, true> _k2_s0_##VF##_##NU##_##TAG;   \
+  static K2Registrar<VF, NU, FACT, false, true> _k2_s1_##VF##_##NU##_##TAG;
 
 // filter + fixed-point smoother, ts0 + ts1, for one factorisation
 #define PDEQ_INSTANTIATE_K2(VF, NU, FACT, TAG)                        \

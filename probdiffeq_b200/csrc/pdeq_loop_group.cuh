@@ -33,8 +33,15 @@ constexpr int K2_CTA_THREADS = 256;  // upper bound of a CTA-mode block
 // MODE 0: a warp per instance (d <= 32). MODE 1: a CTA per instance, one dimension per lane (d <= 256).
 // MODE 2: a CTA per instance, up to K2_MAX_DPL dimensions per lane (d <= 1024); its proposal arrays cost ~160
 // registers, which is why the one-dimension-per-lane case has its own instantiation (two CTAs per SM instead of one).
-template <class VF, int NU, int FACT, bool TS0, bool FP, int MODE>
+//
+// SPEC = 0: solver / error estimator are run-time (group-uniform) branches on pdeq_config.
+// SPEC = 1: `solver_dynamic` + `error_residual_std` (BASELINE configs 3 and 4a's combination) fixed at compile time.
+//           Same arithmetic, operation for operation; what goes away is what the run-time branches keep alive across
+//           the extrapolation -- above all the full noise-only factor Lq (n (n+1) / 2 doubles per lane) that only
+//           error_state_std's general path reads -- and the code of the unused estimators (instruction cache).
+template <class VF, int NU, int FACT, bool TS0, bool FP, int MODE, int SPEC = 0>
 struct GroupLoop {
+  static constexpr bool SPD = SPEC == 1;
   static constexpr bool CTA = MODE != 0;
   static constexpr int n = NU + 1;
   static constexpr int q = VF::order;
@@ -296,6 +303,9 @@ struct GroupLoop {
     const bool adaptive = a.fixed_grid == 0;
     const bool clip = cfg.clip_dt != 0;
     const bool needs_interp = adaptive && !clip;
+    const int cfg_solver = SPD ? (int)PDEQ_SOLVER_DYNAMIC : cfg.solver;
+    const int cfg_error = SPD ? (int)PDEQ_ERROR_RESIDUAL_STD : cfg.error;
+    const bool per_unit_step = SPD ? false : cfg.error_per_unit_step != 0;
     const int T = a.T;
     const int d = cfg.ode_dim;
     const long B = a.prob.num_instances;
@@ -450,7 +460,7 @@ struct GroupLoop {
 #pragma unroll
             for (int i = 0; i < n; ++i) bad += isfinite(m[i]) ? 0.0 : 1.0;
             double fin = 1.0;
-            if (cfg.solver == PDEQ_SOLVER_MLE) {
+            if (cfg_solver == PDEQ_SOLVER_MLE) {
               // solver_mle.userfriendly_output (solvers.py:439-480)
               fin = st_from[F_RUN * d + j];
               if (cfg.correct_asymptotic_underconfidence) fin = fin / sqrt((double)nsteps);
@@ -486,14 +496,14 @@ struct GroupLoop {
                   cond_marginalise<n>(c, m, L, mo, Lo);
                 }
               }
-            } else if (cfg.solver == PDEQ_SOLVER_MLE && a.sol.chol != nullptr && (!ISO || j == 0)) {
+            } else if (cfg_solver == PDEQ_SOLVER_MLE && a.sol.chol != nullptr && (!ISO || j == 0)) {
               for (int k = 0; k < T; ++k) {
                 const long bt = b * T + k;
                 double* co = ISO ? a.sol.chol + bt * (long)(n * n) : a.sol.chol + (bt * d + j) * (long)(n * n);
                 for (int e = 0; e < n * n; ++e) co[e] = fin * co[e];
               }
             }
-            if (cfg.solver == PDEQ_SOLVER_MLE && a.sol.output_scale != nullptr) {
+            if (cfg_solver == PDEQ_SOLVER_MLE && a.sol.output_scale != nullptr) {
               for (int k = 0; k < T; ++k) {
                 if (ISO) {
                   if (j == 0) a.sol.output_scale[b * T + k] = fin;
@@ -543,10 +553,10 @@ struct GroupLoop {
       g.sync();
 
       // phase B: per dimension -- linearise, calibrate, extrapolate, correct, local error
-      const bool need_robs = adaptive ? (cfg.solver == PDEQ_SOLVER_DYNAMIC || cfg.error == PDEQ_ERROR_RESIDUAL_STD)
-                                      : (cfg.solver == PDEQ_SOLVER_DYNAMIC);
-      int kpow = (cfg.error == PDEQ_ERROR_RESIDUAL_STD) ? q : cfg.derivative_idx;
-      if (cfg.error_per_unit_step) kpow += 1;
+      const bool need_robs = adaptive ? (cfg_solver == PDEQ_SOLVER_DYNAMIC || cfg_error == PDEQ_ERROR_RESIDUAL_STD)
+                                      : (cfg_solver == PDEQ_SOLVER_DYNAMIC);
+      int kpow = (cfg_error == PDEQ_ERROR_RESIDUAL_STD) ? q : cfg.derivative_idx;
+      if (per_unit_step) kpow += 1;
       double escale = ipow_small<n>(dtc, kpow);
 #pragma unroll
       for (int e = 0; e <= n; ++e) {
@@ -591,7 +601,7 @@ struct GroupLoop {
         noise_chol<n>(p, sq * prior, Q, Lq);
         const double robs = need_robs ? obs_marginal_chol<n, q, TS0>(Lq, h, a.damp) : 1.0;
         double sig_new = 1.0;
-        if (cfg.solver == PDEQ_SOLVER_DYNAMIC) sig_new = whitened(g, mobs * fast_rcp(robs), active, inv_sqrt_d);
+        if (cfg_solver == PDEQ_SOLVER_DYNAMIC) sig_new = whitened(g, mobs * fast_rcp(robs), active, inv_sqrt_d);
 
         double Lp[n][n], Ln[n][n], gain[n], ry, mn[n];
         if (FP) {
@@ -605,7 +615,7 @@ struct GroupLoop {
         for (int i = 0; i < n; ++i) mn[i] = fma(-gain[i], mobs, mp[i]);
 
         double run_new = run_scale;
-        if (cfg.solver == PDEQ_SOLVER_MLE) {
+        if (cfg_solver == PDEQ_SOLVER_MLE) {
           const double w1 = sqrt(ndata / (ndata + 1.0)), w2 = sqrt(1.0 / (ndata + 1.0));
           const double term = whitened(g, mobs * fast_rcp(ry), active, inv_sqrt_d);
           const double x1 = w1 * run_scale, x2 = w2 * term;
@@ -614,8 +624,9 @@ struct GroupLoop {
 
         if (adaptive) {
           double err, ref;
-          if (cfg.error == PDEQ_ERROR_RESIDUAL_STD) {
-            err = whitened(g, mobs * fast_rcp(robs), active, inv_sqrt_d) * fabs(robs);
+          if (cfg_error == PDEQ_ERROR_RESIDUAL_STD) {
+            // (SPEC = 1: the calibration above already holds this very quantity)
+            err = (SPD ? sig_new : whitened(g, mobs * fast_rcp(robs), active, inv_sqrt_d)) * fabs(robs);
             ref = fmax(fabs(m[0]), fabs(mn[0]));
           } else {
             const int idx = cfg.derivative_idx;
@@ -736,7 +747,7 @@ struct GroupLoop {
               cond_copy(st_from + F_G * d, pending, d, j);
             }
           }
-          if (cfg.solver == PDEQ_SOLVER_DYNAMIC) st_from[F_SIG * d + j] = psig[r];
+          if (cfg_solver == PDEQ_SOLVER_DYNAMIC) st_from[F_SIG * d + j] = psig[r];
           st_from[F_RUN * d + j] = prun[r];
           if (!adaptive) emit(a, b, ck, d, j, t_new, pm[r], pL[r], st_from[F_SIG * d + j], nsteps + 1);
         }
@@ -756,11 +767,16 @@ struct GroupLaunchInfo {
   int groups_per_cta;
 };
 
-template <class VF, int NU, int FACT, bool TS0, bool FP, int MODE>
+template <class VF, int NU, int FACT, bool TS0, bool FP, int MODE, int SPEC = 0>
 __global__ void __launch_bounds__(MODE != 0 ? K2_CTA_THREADS : 128, MODE == 1 ? 2 : ((MODE == 0 && !FP) ? PDEQ_K2_WARP_FILTER_BLOCKS : 1))
     k2_loop_kernel(const __grid_constant__ LoopArgs a, const __grid_constant__ GroupLaunchInfo info) {
   extern __shared__ double smem_k2[];
-  GroupLoop<VF, NU, FACT, TS0, FP, MODE>::run(a, smem_k2, info.cond_ring, info.if_scratch, info.groups_per_cta);
+  GroupLoop<VF, NU, FACT, TS0, FP, MODE, SPEC>::run(a, smem_k2, info.cond_ring, info.if_scratch, info.groups_per_cta);
+}
+
+// Host-side test for GroupLoop SPEC = 1.
+inline bool k2_spec_matches(const LoopArgs& a) {
+  return a.cfg.solver == PDEQ_SOLVER_DYNAMIC && a.cfg.error == PDEQ_ERROR_RESIDUAL_STD && a.cfg.error_per_unit_step == 0;
 }
 
 }  // namespace pdeq

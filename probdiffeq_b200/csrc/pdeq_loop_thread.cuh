@@ -581,7 +581,9 @@ struct ThreadLoop {
         for (int e = 0; e <= n; ++e) {
           if (e == kpow) escale *= ifact[e];
         }
-        double norm;
+        // log2 of the error norm. scale-then-rms: norm = sqrt(sum w^2 / d), so log2(norm) = log2(sum w^2 / d) / 2 and
+        // the square root is never taken.
+        double l2norm;
         if (cfg_norm == PDEQ_NORM_SCALE_THEN_RMS) {
           double ss = 0.0;
 #pragma unroll
@@ -589,7 +591,8 @@ struct ThreadLoop {
             const double w = (err[j] * escale) * fast_rcp(fma(a.rtol, ref[j], a.atol));
             ss = fma(w, w, ss);
           }
-          norm = safe_sqrt(ss) * inv_sqrt_d;
+          const double ms = ss * (1.0 / (double)D);
+          l2norm = 0.5 * (SP ? log2_select(ms) : log2(ms));
         } else {
           // rms(error_abs) / (atol + rtol * rms(reference)); the isotropic error has size 1
           double se2 = 0.0, sr2 = 0.0;
@@ -600,10 +603,11 @@ struct ThreadLoop {
             if (j < ne) se2 = fma(ea, ea, se2);
             sr2 = fma(ref[j], ref[j], sr2);
           }
-          norm = (safe_sqrt(se2) * rsqrt((double)ne)) * fast_rcp(fma(a.rtol, safe_sqrt(sr2) * inv_sqrt_d, a.atol));
+          const double norm = (safe_sqrt(se2) * rsqrt((double)ne)) * fast_rcp(fma(a.rtol, safe_sqrt(sr2) * inv_sqrt_d, a.atol));
+          l2norm = SP ? log2_select(norm) : log2(norm);
         }
         // error_power = norm^(-1/n) (solvers.py:995); accept iff !(error_power < 1) (solvers_via_adaptive_steps.py:256-258)
-        const double lep = neg_inv_n * (SP ? log2_select(norm) : log2(norm));
+        const double lep = neg_inv_n * l2norm;
         accept = !(lep < 0.0);
 
         double lratio;  // log2 of the unclipped step ratio / safety

@@ -1,0 +1,27 @@
+#!/usr/bin/env bash
+# Second GPU-box visit of the round: validates the third-order rcp/rsqrt refinements and the group kernel's
+# specialised build (bitwise A/B), re-runs the GPU suite (minus the one 2-minute full-size Burgers test),
+# the bench line and the ncu captures of the headline kernel. Outputs under gpurun_out/v2/.
+set -u
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+O=gpurun_out/v2
+mkdir -p $O
+timeout 240 python scripts/sweep_k1_spec.py --specs 0,1,2,3 --out $O/best_spec.txt > $O/sweep_k1_spec.jsonl 2> $O/sweep_k1.err
+echo "sweep_k1 rc=$?" >> $O/stages.txt
+timeout 240 python scripts/sweep_k2_spec.py 8192 > $O/sweep_k2_spec.jsonl 2> $O/sweep_k2.err
+echo "sweep_k2 rc=$?" >> $O/stages.txt
+timeout 420 python -m pytest tests -q -m gpu --durations=8 \
+  --deselect tests/test_gpu_group_and_smoother.py::test_burgers_d1024_ts1_full_size_dimension > $O/pytest_gpu.log 2>&1
+echo "pytest rc=$?" >> $O/stages.txt
+timeout 240 python bench.py --steps 10 --warmup 3 > $O/bench_n1.json 2> $O/bench_n1.err
+echo "bench rc=$?" >> $O/stages.txt
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k1_loop_kernel --launch-skip 1 -c 1 \
+  -o $O/prof_k1 -f python scripts/sweep_k1_spec.py --specs 2 --steps 2 --warmup 1 > $O/ncu_full.log 2>&1
+echo "ncu_full rc=$?" >> $O/stages.txt
+[ -f $O/prof_k1.ncu-rep ] && python scripts/summarise_ncu.py $O/prof_k1.ncu-rep $O/k1.ncu.txt > /dev/null 2>> $O/ncu_full.log
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_bench.csv \
+  python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/bench_under_ncu.log 2>&1
+echo "ncu_launches rc=$?" >> $O/stages.txt
+cat $O/stages.txt
+tail -n 12 $O/pytest_gpu.log
+cut -c1-220 $O/sweep_k1_spec.jsonl $O/sweep_k2_spec.jsonl
