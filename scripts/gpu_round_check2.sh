@@ -4,10 +4,12 @@
 # the bench line and the ncu captures of the headline kernel. Outputs under gpurun_out/v2/.
 set -u
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
-O=gpurun_out/v2
+O=gpurun_out/${VISIT:-v2}
 mkdir -p $O
-timeout 240 python scripts/sweep_k1_spec.py --specs 0,1,2,3 --out $O/best_spec.txt > $O/sweep_k1_spec.jsonl 2> $O/sweep_k1.err
+timeout 240 python scripts/sweep_k1_spec.py --specs ${K1_SPECS:-0,1,2,3} --out $O/best_spec.txt > $O/sweep_k1_spec.jsonl 2> $O/sweep_k1.err
 echo "sweep_k1 rc=$?" >> $O/stages.txt
+if [ -n "${USE_BEST:-}" ] && [ -s $O/best_spec.txt ]; then export PDEQ_K1_SPEC=$(cat $O/best_spec.txt); fi
+echo "PDEQ_K1_SPEC=${PDEQ_K1_SPEC:-library default}" >> $O/stages.txt
 timeout 240 python scripts/sweep_k2_spec.py 8192 > $O/sweep_k2_spec.jsonl 2> $O/sweep_k2.err
 echo "sweep_k2 rc=$?" >> $O/stages.txt
 timeout 420 python -m pytest tests -q -m gpu --durations=8 \
@@ -16,7 +18,7 @@ echo "pytest rc=$?" >> $O/stages.txt
 timeout 240 python bench.py --steps 10 --warmup 3 > $O/bench_n1.json 2> $O/bench_n1.err
 echo "bench rc=$?" >> $O/stages.txt
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k1_loop_kernel --launch-skip 1 -c 1 \
-  -o $O/prof_k1 -f python scripts/sweep_k1_spec.py --specs 2 --steps 2 --warmup 1 > $O/ncu_full.log 2>&1
+  -o $O/prof_k1 -f python scripts/sweep_k1_spec.py --specs ${PDEQ_K1_SPEC:-2} --steps 2 --warmup 1 > $O/ncu_full.log 2>&1
 echo "ncu_full rc=$?" >> $O/stages.txt
 [ -f $O/prof_k1.ncu-rep ] && python scripts/summarise_ncu.py $O/prof_k1.ncu-rep $O/k1.ncu.txt > /dev/null 2>> $O/ncu_full.log
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_bench.csv \
