@@ -74,7 +74,7 @@ cudaError_t k1_launch_impl(const LoopArgs& a, cudaStream_t stream) {
 inline int k1_spec_choice() {
   const char* e = std::getenv("PDEQ_K1_SPEC");
   const int c = e == nullptr ? PDEQ_K1_SPEC_DEFAULT : std::atoi(e);
-  return (c >= 0 && c <= 5) ? c : PDEQ_K1_SPEC_DEFAULT;
+  return (c >= 0 && c <= 7) ? c : PDEQ_K1_SPEC_DEFAULT;
 }
 
 template <class VF, int NU, int FACT, int D, bool TS0, bool HAS_SPEC = false>
@@ -87,6 +87,8 @@ cudaError_t k1_launch(const LoopArgs& a, void*, size_t, cudaStream_t stream) {
       if (spec == 3) return k1_launch_impl<VF, NU, FACT, D, TS0, 3>(a, stream);
       if (spec == 4) return k1_launch_impl<VF, NU, FACT, D, TS0, 4>(a, stream);
       if (spec == 5) return k1_launch_impl<VF, NU, FACT, D, TS0, 5>(a, stream);
+      if (spec == 6) return k1_launch_impl<VF, NU, FACT, D, TS0, 6>(a, stream);
+      if (spec == 7) return k1_launch_impl<VF, NU, FACT, D, TS0, 7>(a, stream);
     }
   }
   return k1_launch_impl<VF, NU, FACT, D, TS0, 0>(a, stream);

@@ -24,6 +24,10 @@ echo "ncu_full rc=$?" >> $O/stages.txt
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_bench.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/bench_under_ncu.log 2>&1
 echo "ncu_launches rc=$?" >> $O/stages.txt
+if [ -n "${RUN_CONFIGS:-}" ]; then
+  timeout 240 python scripts/bench_configs.py 30 ${RUN_CONFIGS} > $O/bench_configs.log 2>&1
+  echo "bench_configs rc=$?" >> $O/stages.txt
+fi
 cat $O/stages.txt
 tail -n 12 $O/pytest_gpu.log
 cut -c1-220 $O/sweep_k1_spec.jsonl $O/sweep_k2_spec.jsonl
