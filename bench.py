@@ -380,14 +380,14 @@ def run_ours(args) -> None:
                 "serial": {"value": e2e_steps_all / (ms_e2e_serial * 1e-3), "ms_per_step": ms_e2e_serial,
                            "how": "the same steps one after the other on one stream, L2 flushed in between"},
             },
-            "gpu_launches": args.steps * 1,
-            "gpu_launches_note": "1 loop kernel per step in the resident arm; the e2e arm adds 4 Taylor-pass kernels per step",
+            "gpu_launches": args.steps * 1 + 2 * args.steps * 5,
+            "gpu_launches_note": "1 loop kernel per step in the resident arm; each of the two e2e arms (serial, pipelined) launches 1 loop kernel + 4 Taylor-pass kernels per step",
             "roofline": {
                 "bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
                 "frac": achieved_tflops / fp64_peak_tflops,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this workload, from the ncu --set full
-                # capture summarised in profiles/r1b_k1_loop_lv_nu4_iso_ts0_spec2.ncu.txt (263.5 MB + 758.7 MB)
-                "traffic": 1022.2e6 if B == B_DEFAULT else None, "traffic_unit": "bytes per launch (ncu)",
+                # capture summarised in profiles/r1e_k1_loop_lv_nu4_iso_ts0.ncu.txt (261.0 MB + 746.1 MB)
+                "traffic": 1007.2e6 if B == B_DEFAULT else None, "traffic_unit": "bytes per launch (ncu)",
                 "kernel": f"k1_loop_kernel<LotkaVolterra,4,isotropic,2,ts0,SPEC={lib.pdeq_k1_spec_choice()}>",
                 "flops_per_attempt": fl, "attempts_per_launch": attempts_pass,
                 "peak_source": "pdeq_fp64_peak_probe (FP64 FMA, measured in this run; MEASURED_PEAKS.json has no FP64 figure)",

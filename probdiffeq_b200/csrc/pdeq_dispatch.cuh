@@ -47,34 +47,34 @@ cudaError_t k1_launch_impl(const LoopArgs& a, cudaStream_t stream) {
   using TL = ThreadLoop<VF, NU, FACT, D, TS0, SPEC>;
   auto kern = k1_loop_kernel<VF, NU, FACT, D, TS0, SPEC>;
   const bool needs_interp = a.fixed_grid == 0 && a.cfg.clip_dt == 0;
-  const size_t smem = TL::SMS ? size_t(TL::ST_SLOTS) * K1_THREADS * sizeof(double)
-                              : (needs_interp ? size_t(TL::IF_SLOTS) * K1_THREADS * sizeof(double) : 0);
+  const size_t smem = TL::SMS ? size_t(TL::ST_SLOTS) * TL::THREADS * sizeof(double)
+                              : (needs_interp ? size_t(TL::IF_SLOTS) * TL::THREADS * sizeof(double) : 0);
   cudaError_t err;
   if (smem > 48 * 1024) {
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
   }
   int per_sm = 0;
-  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K1_THREADS, smem);
+  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TL::THREADS, smem);
   if (err != cudaSuccess) return err;
   if (per_sm < 1) per_sm = 1;
-  const long want = (a.prob.num_instances + K1_THREADS - 1) / K1_THREADS;
+  const long want = (a.prob.num_instances + TL::THREADS - 1) / TL::THREADS;
   const long cap = (long)per_sm * device_sm_count();
   const int grid = (int)std::max(1L, std::min(want, cap));
-  kern<<<grid, K1_THREADS, smem, stream>>>(a);
+  kern<<<grid, TL::THREADS, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
 // Which specialised loop to use when the configuration matches: PDEQ_K1_SPEC=0 in the environment forces the
-// general kernel (A/B measurements, bitwise comparison tests), 1 / 2 pick the 3- / 4-CTAs-per-SM build, 3 / 4 the
-// builds with the accepted state in shared memory (ThreadLoop).
+// general kernel (A/B measurements, bitwise comparison tests), 1..5 pick a specialised build (ThreadLoop: register
+// budget / resident CTAs / CTA size / where the accepted state lives).
 #ifndef PDEQ_K1_SPEC_DEFAULT
 #define PDEQ_K1_SPEC_DEFAULT 2
 #endif
 inline int k1_spec_choice() {
   const char* e = std::getenv("PDEQ_K1_SPEC");
   const int c = e == nullptr ? PDEQ_K1_SPEC_DEFAULT : std::atoi(e);
-  return (c >= 0 && c <= 7) ? c : PDEQ_K1_SPEC_DEFAULT;
+  return (c >= 0 && c <= 5) ? c : PDEQ_K1_SPEC_DEFAULT;
 }
 
 template <class VF, int NU, int FACT, int D, bool TS0, bool HAS_SPEC = false>
@@ -87,8 +87,6 @@ cudaError_t k1_launch(const LoopArgs& a, void*, size_t, cudaStream_t stream) {
       if (spec == 3) return k1_launch_impl<VF, NU, FACT, D, TS0, 3>(a, stream);
       if (spec == 4) return k1_launch_impl<VF, NU, FACT, D, TS0, 4>(a, stream);
       if (spec == 5) return k1_launch_impl<VF, NU, FACT, D, TS0, 5>(a, stream);
-      if (spec == 6) return k1_launch_impl<VF, NU, FACT, D, TS0, 6>(a, stream);
-      if (spec == 7) return k1_launch_impl<VF, NU, FACT, D, TS0, 7>(a, stream);
     }
   }
   return k1_launch_impl<VF, NU, FACT, D, TS0, 0>(a, stream);

@@ -47,7 +47,10 @@ constexpr int K1_THREADS = 128;
 #define PDEQ_K1_MIN_BLOCKS(FACT) ((FACT) == PDEQ_FACT_ISOTROPIC ? 3 : 2)
 #endif
 
-#define PDEQ_K1_SPEC_MIN_BLOCKS(SPEC) ((SPEC) == 5 ? 6 : ((SPEC) == 4 ? 5 : ((SPEC) >= 2 ? 4 : 3)))  // 6, 7: as 2
+// Resident CTAs per SM of the specialised builds (SPEC = 1..4, see ThreadLoop). Registers are per SM sub-partition
+// (16 K each), so 13..16 resident warps all mean <= 128 registers and 9..12 mean <= 168: there is no build "between"
+// 2 and 1, whatever the CTA size.
+#define PDEQ_K1_SPEC_MIN_BLOCKS(SPEC) ((SPEC) == 4 ? 5 : ((SPEC) >= 2 ? 4 : 3))  // 5: as 2
 
 template <int n>
 PDEQ_DI double ipow_small(double x, int k) {
@@ -78,14 +81,15 @@ PDEQ_DI double safe_sqrt(double x) {
 // SPEC = 3: as 2, with the accepted state (mean and factor) resident in shared memory, one column per thread: it is
 //           read at the start of an attempt and written when the attempt is accepted, so the 25 doubles do not
 //           occupy registers during the triangularisations and the accept is 25 predicated stores instead of 50
-//           register moves. SPEC = 4 / 5: as 3, five (96 registers) / six (80) resident CTAs.
-//           SPEC = 6 / 7: A/B builds of 2 (see ISETUP / CB below); bitwise the same results as well.
+//           register moves. SPEC = 4: as 3, five resident CTAs (96 registers).
+// SPEC = 5: as 2, but the vector field's parameters are re-read from global memory (an L1 hit) at the start of every
+//           attempt instead of occupying 2 P registers across the triangularisations.
 template <class VF, int NU, int FACT, int D, bool TS0, int SPEC = 0>
 struct ThreadLoop {
   static constexpr bool SP = SPEC != 0;
-  static constexpr bool SMS = SPEC >= 3 && SPEC <= 5;  // accepted state in shared memory
-  static constexpr bool ISETUP = SPEC != 6;             // A/B: reflector set-up with integer sign/zero tests
-  static constexpr bool CB = SPEC == 7;                 // A/B: log2/exp2 coefficients from constant memory
+  static constexpr bool SMS = SPEC == 3 || SPEC == 4;  // accepted state in shared memory
+  static constexpr bool PGL = SPEC == 5;               // parameters re-read (L1) per attempt instead of held in registers
+  static constexpr int THREADS = K1_THREADS;
   static_assert(!SP || TS0, "the specialised loop is ts0 only");
   static constexpr int n = NU + 1;
   static constexpr int q = VF::order;
@@ -311,6 +315,10 @@ struct ThreadLoop {
         if (SMS) st_store(smem_if, nthreads, tid, m, L);
       }
       if (SMS) st_load(smem_if, nthreads, tid, m, L);
+      if (PGL && VF::num_params > 0) {
+#pragma unroll
+        for (int k = 0; k < P; ++k) params[k] = a.prob.params[b * a.prob.params_stride + k];
+      }
 
       // ------------------------------------------------------------------ checkpoint reached?
       // adaptive: RejectionLoop.loop's interpolation switch (solvers_via_adaptive_steps.py:241-247)
@@ -477,8 +485,8 @@ struct ThreadLoop {
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
         double Lp[n][n];
-        predict_chol<n, ISETUP>(L[k], p, pinv, sq * prior[k] * sig_new[k], A, Q, Lp);
-        revert_obs<n, q, TS0, -1, ISETUP>(Lp, h[k], damp, ry[k], gain[k], Ln[k]);
+        predict_chol<n>(L[k], p, pinv, sq * prior[k] * sig_new[k], A, Q, Lp);
+        revert_obs<n, q, TS0>(Lp, h[k], damp, ry[k], gain[k], Ln[k]);
       }
       double mn[n][D];
 #pragma unroll
@@ -595,7 +603,7 @@ struct ThreadLoop {
             ss = fma(w, w, ss);
           }
           const double ms = ss * (1.0 / (double)D);
-          l2norm = 0.5 * (SP ? log2_select<CB>(ms) : log2(ms));
+          l2norm = 0.5 * (SP ? log2_select(ms) : log2(ms));
         } else {
           // rms(error_abs) / (atol + rtol * rms(reference)); the isotropic error has size 1
           double se2 = 0.0, sr2 = 0.0;
@@ -607,7 +615,7 @@ struct ThreadLoop {
             sr2 = fma(ref[j], ref[j], sr2);
           }
           const double norm = (safe_sqrt(se2) * rsqrt((double)ne)) * fast_rcp(fma(a.rtol, safe_sqrt(sr2) * inv_sqrt_d, a.atol));
-          l2norm = SP ? log2_select<CB>(norm) : log2(norm);
+          l2norm = SP ? log2_select(norm) : log2(norm);
         }
         // error_power = norm^(-1/n) (solvers.py:995); accept iff !(error_power < 1) (solvers_via_adaptive_steps.py:256-258)
         const double lep = neg_inv_n * l2norm;
@@ -620,7 +628,7 @@ struct ThreadLoop {
         } else {
           lratio = lep;
         }
-        const double ratio = cfg.safety * (SP ? exp2_select<CB>(lratio) : exp2(lratio));
+        const double ratio = cfg.safety * (SP ? exp2_select(lratio) : exp2(lratio));
         const double sc = fmax(cfg.factor_min, fmin(ratio, cfg.factor_max));
         dt_next = sc * dtc;
         if (a.sol.trace != nullptr && nattempts <= a.sol.trace_capacity) {
