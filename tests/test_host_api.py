@@ -44,6 +44,21 @@ def test_vector_field_registry():
     assert lib.pdeq_vf_id(b"no_such_problem") == -1
 
 
+def test_k1_spec_choice_follows_the_environment(monkeypatch):
+    """pdeq_k1_spec_choice: the library default (a specialised build, not the general kernel) unless PDEQ_K1_SPEC
+    names another build; values outside the known builds fall back to the default. Host-only, no launch."""
+    lib = _lib.load()
+    monkeypatch.delenv("PDEQ_K1_SPEC", raising=False)
+    default = lib.pdeq_k1_spec_choice()
+    assert 1 <= default <= 5
+    for spec in range(0, 6):
+        monkeypatch.setenv("PDEQ_K1_SPEC", str(spec))
+        assert lib.pdeq_k1_spec_choice() == spec
+    for bad in ("-1", "99"):
+        monkeypatch.setenv("PDEQ_K1_SPEC", bad)
+        assert lib.pdeq_k1_spec_choice() == default
+
+
 def _cfg(**kw):
     cfg = _lib.Config()
     cfg.factorisation, cfg.num_derivatives, cfg.ode_dim = 0, 4, 2
