@@ -69,7 +69,7 @@ cudaError_t k1_launch_impl(const LoopArgs& a, cudaStream_t stream) {
 // general kernel (A/B measurements, bitwise comparison tests), 1..5 pick a specialised build (ThreadLoop: register
 // budget / resident CTAs / CTA size / where the accepted state lives).
 #ifndef PDEQ_K1_SPEC_DEFAULT
-#define PDEQ_K1_SPEC_DEFAULT 2
+#define PDEQ_K1_SPEC_DEFAULT 1
 #endif
 inline int k1_spec_choice() {
   const char* e = std::getenv("PDEQ_K1_SPEC");
