@@ -386,8 +386,8 @@ def run_ours(args) -> None:
                 "bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
                 "frac": achieved_tflops / fp64_peak_tflops,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this workload, from the ncu --set full
-                # capture summarised in profiles/r1e_k1_loop_lv_nu4_iso_ts0.ncu.txt (261.0 MB + 746.1 MB)
-                "traffic": 1007.2e6 if B == B_DEFAULT else None, "traffic_unit": "bytes per launch (ncu)",
+                # capture summarised in profiles/r1e_k1_loop_lv_nu4_iso_ts0.ncu.txt (221.0 MB + 684.1 MB)
+                "traffic": 905.1e6 if B == B_DEFAULT else None, "traffic_unit": "bytes per launch (ncu)",
                 "kernel": f"k1_loop_kernel<LotkaVolterra,4,isotropic,2,ts0,SPEC={lib.pdeq_k1_spec_choice()}>",
                 "flops_per_attempt": fl, "attempts_per_launch": attempts_pass,
                 "peak_source": "pdeq_fp64_peak_probe (FP64 FMA, measured in this run; MEASURED_PEAKS.json has no FP64 figure)",
