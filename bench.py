@@ -65,7 +65,7 @@ def config_dict(B: int, n_gpus: int) -> dict:
         "instances_total": B * n_gpus,
         "sharding": "by instance index, no collective",
         "l2": "256 MiB L2 flush between timed steps; per-step inputs+outputs (0.4 GB) exceed the 126 MB L2",
-        "spinup": "untimed passes for >= 0.75 s before the W warm-up steps (clock ramp of a fresh process)",
+        "spinup": "untimed passes for >= 0.75 s and until three consecutive passes agree within 3 % before the W warm-up steps (clock ramp of a fresh process)",
     }
 
 
@@ -267,9 +267,15 @@ def run_ours(args) -> None:
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
+        # Warm-up holds the previous step's result while the next one is produced, exactly as the timed loop below does
+        # (`last`): both sets of output buffers then sit in torch's caching allocator, and no timed step pays for a
+        # cudaMalloc (which would stall the launch behind it for tens of milliseconds).
+        held = None
+        for _ in range(max(warmup, 2)):
+            cur = fn()
             flush.fill_(1)
+            held = cur
+        del held, cur
         barrier()
         evs = []
         last = None
@@ -315,14 +321,22 @@ def run_ours(args) -> None:
 
     # Untimed spin-up on top of the W warm-up steps: a fresh process finds the GPU at idle clocks, and W = 3 passes
     # (~80 ms) can end before the clocks have ramped -- a whole run then reads ~30 % slow. Keep the device busy for
-    # at least 0.75 s (at most 40 passes) before anything is timed.
+    # at least 0.75 s and until three consecutive passes agree within 3 % (at most 80 passes) before anything is timed.
     import time as _time
 
-    spin_t0, spinup = _time.perf_counter(), 0
-    while _time.perf_counter() - spin_t0 < 0.75 and spinup < 40:
+    spin_t0, spinup, spin_ms = _time.perf_counter(), 0, []
+    while spinup < 80:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         step_resident()
+        e1.record()
         torch.cuda.synchronize()
+        spin_ms.append(e0.elapsed_time(e1))
         spinup += 1
+        # stop once the device has been busy for 0.75 s AND the last three passes agree within 3 % (clocks settled)
+        settled = len(spin_ms) >= 3 and max(spin_ms[-3:]) <= 1.03 * min(spin_ms[-3:])
+        if _time.perf_counter() - spin_t0 >= 0.75 and settled:
+            break
 
     sampler = ClockSampler(local_rank)
     sampler.start()
