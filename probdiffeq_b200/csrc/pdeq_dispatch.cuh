@@ -123,10 +123,12 @@ struct K2Plan {
   size_t smem_bytes, ring_bytes_per_group;
 };
 
-// PDEQ_K2_SPEC=0 in the environment forces the general kernel where a specialised build exists (GroupLoop SPEC).
-inline bool k2_spec_enabled() {
+// PDEQ_K2_SPEC=0 in the environment forces the general kernel where a specialised build exists (GroupLoop SPEC);
+// 2 selects the smoother build that defers the backward conditional to accepted steps.
+inline int k2_spec_choice() {
   const char* e = std::getenv("PDEQ_K2_SPEC");
-  return e == nullptr || std::atoi(e) != 0;
+  const int c = e == nullptr ? 1 : std::atoi(e);
+  return (c >= 0 && c <= 2) ? c : 1;
 }
 
 template <class VF, int NU, int FACT, bool TS0, bool FP, int SPEC = 0>
@@ -195,7 +197,9 @@ cudaError_t k2_launch(const LoopArgs& a, void* workspace, size_t workspace_bytes
   const bool needs_interp = a.fixed_grid == 0 && a.cfg.clip_dt == 0;
   K2Plan plan;
   // the specialised build exists for the warp-per-instance mode only (d <= 32)
-  const bool spec = HAS_SPEC && a.cfg.ode_dim <= 32 && k2_spec_matches(a) && k2_spec_enabled();
+  const int choice = k2_spec_choice();
+  const bool spec = HAS_SPEC && a.cfg.ode_dim <= 32 && k2_spec_matches(a) && choice != 0;
+  const bool defer = spec && FP && choice == 2 && a.fixed_grid == 0;
   cudaError_t err = cudaSuccess;
   if constexpr (HAS_SPEC) {
     err = spec ? k2_plan<VF, NU, FACT, TS0, FP, 1>(a.cfg, a.prob.num_instances, a.T, needs_interp, &plan)
@@ -222,8 +226,18 @@ cudaError_t k2_launch(const LoopArgs& a, void* workspace, size_t workspace_bytes
   else if (plan.mode == 1)
     k2_loop_kernel<VF, NU, FACT, TS0, FP, 1><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);
   else if (spec) {
-    if constexpr (HAS_SPEC)
-      k2_loop_kernel<VF, NU, FACT, TS0, FP, 0, 1><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);
+    if constexpr (HAS_SPEC) {
+      if (defer) {
+        if constexpr (FP) {
+          auto kern = k2_loop_kernel<VF, NU, FACT, TS0, FP, 0, 2>;
+          err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);
+          if (err != cudaSuccess) return err;
+          kern<<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);
+        }
+      } else {
+        k2_loop_kernel<VF, NU, FACT, TS0, FP, 0, 1><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);
+      }
+    }
   } else
     k2_loop_kernel<VF, NU, FACT, TS0, FP, 0><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);
   return cudaGetLastError();

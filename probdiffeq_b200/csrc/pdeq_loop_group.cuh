@@ -41,7 +41,14 @@ constexpr int K2_CTA_THREADS = 256;  // upper bound of a CTA-mode block
 //           error_state_std's general path reads -- and the code of the unused estimators (instruction cache).
 template <class VF, int NU, int FACT, bool TS0, bool FP, int MODE, int SPEC = 0>
 struct GroupLoop {
-  static constexpr bool SPD = SPEC == 1;
+  static constexpr bool SPD = SPEC >= 1;
+  // SPEC = 2 (smoother only): the backward conditional of a step -- the gain rows and backward noise of the reverted
+  // transition and their merge into the carried conditional -- is computed when the step is ACCEPTED instead of with
+  // every attempt (acceptance is uniform across the lanes of an instance). An attempt then costs what a filter
+  // attempt costs; an accepted step pays one extra prediction triangularisation. Same operations on the same
+  // values for every accepted step, hence bitwise the same results. (dt > 0, where the filter's and the smoother's
+  // prediction stacks coincide: |p^-1| = p^-1.)
+  static constexpr bool DEFER = FP && SPEC == 2;
   static constexpr bool CTA = MODE != 0;
   static constexpr int n = NU + 1;
   static constexpr int q = VF::order;
@@ -604,7 +611,7 @@ struct GroupLoop {
         if (cfg_solver == PDEQ_SOLVER_DYNAMIC) sig_new = whitened(g, mobs * fast_rcp(robs), active, inv_sqrt_d);
 
         double Lp[n][n], Ln[n][n], gain[n], ry, mn[n];
-        if (FP) {
+        if (FP && !DEFER) {
           const CondFields carried{st_from + F_G * d, d, jj};
           extrapolate_smoother(L, m, p, pinv, sq * prior * sig_new, A, Q, carried, Lp, pending, d, jj);
         } else {
@@ -735,6 +742,13 @@ struct GroupLoop {
             st_load(st_from, d, j, m, L);
             st_store(st_if, d, j, m, L);
             if (FP) cond_copy(st_if + F_G * d, st_from + F_G * d, d, j);
+          }
+          if (DEFER) {  // the accepted step's backward conditional, from the state it started from
+            double m0[n], L0[n][n], Lp_again[n][n];
+            st_load(st_from, d, j, m0, L0);
+            const CondFields carried{st_from + F_G * d, d, j};
+            extrapolate_smoother(L0, m0, p, pinv, sq * st_from[F_PRIOR * d + j] * psig[r], A, Q, carried, Lp_again,
+                                 pending, d, j);
           }
           st_store(st_from, d, j, pm[r], pL[r]);
           if (FP) {

@@ -1,6 +1,7 @@
 """A/B of the group kernel's specialised build (PDEQ_K2_SPEC=0/1, GroupLoop SPEC in csrc/pdeq_loop_group.cuh) on
 BASELINE config 3 (Pleiades, fixed-point smoother) and on the Pleiades filter: time per pass and a BITWISE
-comparison of all outputs with the general kernel. usage: python scripts/sweep_k2_spec.py [instances]"""
+comparison of all outputs with the general kernel. usage: python scripts/sweep_k2_spec.py [instances] [specs, e.g. 0,1,2]
+(PDEQ_K2_SPEC=2: the smoother build that computes the backward conditional for accepted steps only.)"""
 
 import json
 import os
@@ -37,11 +38,12 @@ def outputs(sol):
 
 if __name__ == "__main__":
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+    specs = tuple(int(x) for x in sys.argv[2].split(",")) if len(sys.argv) > 2 else (0, 1, 0, 1)
     torch.cuda.set_device(0)
     for name, make in (("3:pleiades-bd-fixedpoint", bc.config3), ("pleiades-bd-filter", pleiades_filter)):
         run = make(B)
         ref = None
-        for spec in (0, 1, 0, 1):
+        for spec in specs:
             os.environ["PDEQ_K2_SPEC"] = str(spec)
             run()
             secs, (sol, _) = bc.timed(run)

@@ -1,6 +1,7 @@
-"""The specialised build of the group kernel (GroupLoop SPEC = 1: solver_dynamic + error_residual_std fixed at
-compile time, csrc/pdeq_loop_group.cuh) against the general kernel, which the oracle parity tests pin: the
-specialisation does not change a floating-point operation, so every output must agree BITWISE.
+"""The specialised builds of the group kernel (GroupLoop SPEC = 1: solver_dynamic + error_residual_std fixed at
+compile time; SPEC = 2: in addition the smoother's backward conditional is computed for accepted steps only --
+csrc/pdeq_loop_group.cuh) against the general kernel, which the oracle parity tests pin: neither changes a floating-
+point operation on an accepted step, so every output must agree BITWISE.
 The launcher reads PDEQ_K2_SPEC on every launch."""
 
 import os
@@ -41,11 +42,12 @@ def test_specialised_group_kernel_is_bitwise_the_general_kernel(cuda, strategy):
         os.environ["PDEQ_K2_SPEC"] = "0"
         ref = _solve(1500, strategy)
         assert int(np.abs(ref[-1]).max()) == 0
-        os.environ["PDEQ_K2_SPEC"] = "1"
-        got = _solve(1500, strategy)
-        assert len(got) == len(ref)
-        for a, b in zip(got, ref):
-            assert a.shape == b.shape and a.tobytes() == b.tobytes()
+        for spec in ("1", "2"):
+            os.environ["PDEQ_K2_SPEC"] = spec
+            got = _solve(1500, strategy)
+            assert len(got) == len(ref)
+            for a, b in zip(got, ref):
+                assert a.shape == b.shape and a.tobytes() == b.tobytes(), f"PDEQ_K2_SPEC={spec}"
     finally:
         if old is None:
             os.environ.pop("PDEQ_K2_SPEC", None)
