@@ -383,3 +383,32 @@ def test_posterior_sample_with_zero_draws_is_the_smoothing_mean_and_has_the_righ
 
 def test_unused_import_guard():
     assert ssm.Normal is not None
+
+
+@pytest.mark.parametrize("nu", [1, 2, 3, 4, 5, 7])
+@pytest.mark.parametrize("dt", [1.234, 0.037, -0.5])
+def test_preconditioned_iwp_mean_transition_is_the_taylor_shift(nu, dt):
+    """The identity the kernels' `predict_mean` rests on (csrc/pdeq_blockops.cuh): with A = flipped Pascal
+    (utilities.py:59-61) and p_k = dt^(nu-k)/(nu-k)! (utilities.py:74-84),  p_i A_ik / p_k = dt^(k-i)/(k-i)!  for
+    k >= i, so p * (A (p^-1 * m)) -- LatentCond.marginalise's mean, ssm_impl_isotropic.py:81-89 -- is the Taylor
+    shift  m_i + sum_{k>i} p[nu-(k-i)] m_k.  Checked against the oracle's own system matrices and preconditioner."""
+    from oracle import linalg as ol
+
+    n = nu + 1
+    A, _ = ol.system_matrices_1d_iwp(nu)
+    p, pinv = ol.preconditioner_taylor(nu)(dt)
+    rng = np.random.Generator(np.random.PCG64(nu))
+    m = rng.normal(size=(n, 3)) * 10.0 ** rng.integers(-3, 4, size=(n, 1))
+    reference = p[:, None] * (A @ (pinv[:, None] * m))
+    shifted = m.copy()
+    for i in range(n):
+        for k in range(i + 1, n):
+            shifted[i] += p[n - 1 - (k - i)] * m[k]
+    scale = np.abs(p[:, None] * (np.abs(A) @ np.abs(pinv[:, None] * m)))  # size of the terms that are summed
+    assert np.all(np.abs(shifted - reference) <= 1e-14 * scale)
+    # the coefficient form of the same statement
+    M = p[:, None] * A * pinv[None, :]
+    for i in range(n):
+        for k in range(n):
+            expect = 0.0 if k < i else dt ** (k - i) / float(ol.factorial(k - i))
+            assert abs(M[i, k] - expect) <= 1e-13 * max(abs(expect), 1e-300) or (k < i and M[i, k] == 0.0)
