@@ -497,9 +497,19 @@ class solver_dynamic(_Solver):
     kind = "solver_dynamic"
 
     def __init__(self, *, strategy, constraint, constraint_init=None, re_linearize_after_calibration=False):
-        if re_linearize_after_calibration:
-            raise NotImplementedError("re_linearize_after_calibration=True is outside the accelerated path.")
-        super().__init__(strategy=strategy, constraint=constraint, constraint_init=constraint_init)
+        # reference: solvers.py:578-582. The re-linearisation happens at the MEAN of the re-extrapolated state
+        # (taylor_point_prior, taylor_points.py:150-156), and the calibrated output scale changes the covariance of
+        # that state, not its mean: for the ts0 / ts1 constraints built here the second linearisation is the first
+        # one. The kernels therefore run the same step for both values of the flag. (In the reference the isotropic
+        # model's two extrapolation code paths differ by an ulp in the mean, which the adaptive loop turns into
+        # ~1e-10 differences; block-diagonal and dense are bitwise identical -- tests/test_oracle_kats.py.)
+        self.re_linearize_after_calibration = bool(re_linearize_after_calibration)
+        super().__init__(
+            strategy=strategy,
+            constraint=constraint,
+            constraint_init=constraint_init,
+            re_linearize_after_calibration=int(bool(re_linearize_after_calibration)),  # carried in pdeq_config
+        )
 
 
 def error_norm_scale_then_rms(*, norm_order=None):
@@ -519,8 +529,11 @@ class _ErrorEstimator:
 
     def __init__(self, *, constraint, error_norm=None, re_linearize_before_error=False, derivative_idx=0,
                  error_per_unit_step=False):  # fmt: skip
-        if re_linearize_before_error:
-            raise NotImplementedError("re_linearize_before_error=True is outside the accelerated path.")
+        # reference: solvers.py:946-952, 1061-1067. Re-linearising at the zero-error extrapolation of the previous mean
+        # reproduces the step's cached linearisation exactly (same point, same time) for the ts0 / ts1 constraints
+        # built here, in every factorisation (bitwise in the oracle, tests/test_oracle_kats.py): the flag is accepted
+        # and changes nothing.
+        self.re_linearize_before_error = bool(re_linearize_before_error)
         self.constraint = constraint
         self.error_norm = "scale_then_rms" if error_norm is None else error_norm
         if self.error_norm not in _lib.NORM:

@@ -143,6 +143,27 @@ def test_constructors_mirror_the_reference_error_behaviour():
         probdiffeq.strategy_smoother_fixedinterval(terminal="nonsense")
 
 
+def test_re_linearize_flags_are_accepted_and_carried_into_the_config():
+    """reference: solvers.py:496, 911, 1021. Both flags are no-ops for the prior Taylor point (shown on the oracle in
+    tests/test_oracle_kats.py), so the product accepts them; the solver's flag travels in pdeq_config."""
+    from probdiffeq_b200 import ivpsolve, probdiffeq
+
+    vf = probdiffeq.ode("lotka_volterra", params=np.asarray([[0.5, 0.05, 0.5, 0.05]]))
+    ssm = probdiffeq.state_space_model_blockdiag()
+    ts1 = ssm.constraint_ode_ts1(vf)
+    for flag in (False, True):
+        solver = probdiffeq.solver_dynamic(strategy=probdiffeq.strategy_filter(), constraint=ts1,
+                                           re_linearize_after_calibration=flag)  # fmt: skip
+        assert solver.re_linearize_after_calibration is flag
+        assert solver.options["re_linearize_after_calibration"] == int(flag)
+        for est in (probdiffeq.error_residual_std, probdiffeq.error_state_std):
+            assert est(constraint=ts1, re_linearize_before_error=flag).re_linearize_before_error is flag
+    prior = type("P", (), {"factorisation": "blockdiag", "num_derivatives": 4, "ode_dim": 2})()
+    cfg = ivpsolve._lower(prior, solver, probdiffeq.error_residual_std(constraint=ts1, re_linearize_before_error=True),
+                          ivpsolve.control_integral(), clip_dt=False)  # fmt: skip
+    assert cfg.re_linearize_after_calibration == 1 and cfg.solver == 2
+
+
 def test_error_constants_reproduce_the_full_bayes_rule():
     """pdeq_config.err_const (probdiffeq_b200/_iwp.py): for ts0 and damp = 0 the zero-error extrapolation's factor is
     diag(|p|) sqrt(dt) lambda q, and error_state_std's triangularisation (solvers.py:1070-1086) commutes with that

@@ -412,3 +412,52 @@ def test_preconditioned_iwp_mean_transition_is_the_taylor_shift(nu, dt):
         for k in range(n):
             expect = 0.0 if k < i else dt ** (k - i) / float(ol.factorial(k - i))
             assert abs(M[i, k] - expect) <= 1e-13 * max(abs(expect), 1e-300) or (k < i and M[i, k] == 0.0)
+
+
+def _relinearize_case(fact, constraint, strategy, error_name, relin_solver, relin_error):
+    draw = np.random.Generator(np.random.PCG64(3)).uniform(0.8, 1.2, size=(1, 6))
+    params, u0 = np.asarray([0.5, 0.05, 0.5, 0.05])[None, :] * draw[:, :4], 20.0 * draw[:, 4:]
+    vf = pdq.ode("lotka_volterra", params[0])
+    tc = pdq.jetexpand_ode_padded_scan(num=4)(vf, (u0[0],), t=0.0)[0]
+    ssm = getattr(pdq, "state_space_model_" + fact)()
+    cons = getattr(ssm, "constraint_ode_" + constraint)(vf)
+    strat = {"filter": pdq.strategy_filter, "fixedpoint": pdq.strategy_smoother_fixedpoint}[strategy]()
+    solver = pdq.solver_dynamic(strategy=strat, constraint=cons, re_linearize_after_calibration=relin_solver)
+    err = getattr(pdq, "error_" + error_name)(constraint=cons, re_linearize_before_error=relin_error)
+    prior = ssm.prior_wiener_integrated(np.asarray(tc))
+    solve = ivpsolve.solve_adaptive_save_at(solver=solver, error=err, control=ivpsolve.control_integral(), clip_dt=False, warn=False)
+    return solve(prior, save_at=np.linspace(0.0, 3.0, 4), atol=1e-8, rtol=1e-6, dt0=0.1)
+
+
+def _fields(sol):
+    return [np.asarray(x) for x in (sol.t, sol.u_mean, sol.u_chol, sol.num_steps, sol.output_scale)]
+
+
+@pytest.mark.parametrize("fact", ["isotropic", "blockdiag", "dense"])
+@pytest.mark.parametrize("constraint", ["ts0", "ts1"])
+@pytest.mark.parametrize("strategy", ["filter", "fixedpoint"])
+@pytest.mark.parametrize("error_name", ["state_std", "residual_std"])
+def test_re_linearize_flags_change_nothing_for_prior_taylor_points(fact, constraint, strategy, error_name):
+    """Why the product accepts `re_linearize_before_error` / `re_linearize_after_calibration` and runs the same
+    kernels (reference: solvers.py:578-582, 946-952, 1061-1067): the second linearisation is taken at the mean of a
+    state whose mean the first linearisation already used, so with the prior Taylor point (taylor_points.py:150-156)
+    it reproduces the first. In the oracle this is bitwise for the error estimators in every factorisation and for
+    solver_dynamic in the block-diagonal and dense models; the isotropic model extrapolates the mean through two code
+    paths that differ by an ulp (ssm_impl_isotropic.py:75-79 vs :81-89), which the adaptive loop turns into ~1e-10 --
+    the same accepted steps, values far inside the 1e-8 tolerance."""
+    base = _fields(_relinearize_case(fact, constraint, strategy, error_name, False, False))
+    with_error_flag = _fields(_relinearize_case(fact, constraint, strategy, error_name, False, True))
+    for a, b in zip(base, with_error_flag):
+        assert np.array_equal(a, b)
+    with_solver_flag = _fields(_relinearize_case(fact, constraint, strategy, error_name, True, False))
+    if fact == "isotropic":
+        t0, m0, L0, n0, s0 = base
+        t1, m1, L1, n1, s1 = with_solver_flag
+        assert np.array_equal(n0, n1)  # accepted steps per checkpoint
+        rel = lambda a, b: np.max(np.abs(a - b)) / max(np.max(np.abs(a)), 1e-300)  # noqa: E731
+        assert rel(t0, t1) <= 1e-12 and rel(m0, m1) <= 1e-8
+        cov = lambda L: L @ np.swapaxes(L, -1, -2)  # noqa: E731  (factor signs are not unique)
+        assert rel(cov(L0), cov(L1)) <= 1e-6 and rel(s0, s1) <= 1e-6
+    else:
+        for a, b in zip(base, with_solver_flag):
+            assert np.array_equal(a, b)
