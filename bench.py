@@ -4,18 +4,27 @@
   python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repository)
   python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host cores
 
-Workload (N = 1): BASELINE.json configs[1] -- a Lotka-Volterra ensemble of 2^20 instances with randomised
+Headline workload: BASELINE.json configs[1] -- ONE Lotka-Volterra ensemble of 2^20 instances with randomised
 parameters / initial values (seed 0), nu = 4, isotropic ts0 filter, `solver` +
 `error_state_std` + PI control, terminal values on t in [0, 50], rtol 1e-6, atol 1e-8, float64.
-One "step" is one solve of the whole ensemble.  For N > 1 every rank solves its own 2^20-instance shard
-(seed = rank; instances are independent, there is no data-path collective): weak scaling.
+One "step" is one solve of the whole ensemble.  For N > 1 the SAME ensemble is permuted
+(`sharding.permutation`) and cut into N contiguous shards (`sharding.shard_bounds`), one rank per GPU, no
+data-path collective: strong scaling (`"scaling": "strong"`).  The weak-scaling number of round 1 (every rank
+solves its own 2^20-instance ensemble, seed = rank) is kept under the key `weak`.
 
-`value`    accepted solver steps / second with the inputs resident in HBM (CUDA events around the solve).
+`value`    accepted solver steps / second of the whole job with the inputs resident in HBM (CUDA events around
+           the solve on the launching stream, max over ranks).
 `e2e`      the same metric through the public API with pinned HOST inputs: H2D copy of parameters and initial
-           values, on-device Taylor initialisation, the solve, D2H copy of terminal values and step counts.
-`roofline` FP64: algorithmic FLOPs of the loop kernel / its measured duration against the FP64 FMA peak measured
-           in the same run (MEASURED_PEAKS.json carries no FP64 number); HBM traffic is reported beside it.
-`cpu_baseline` the plain-C restatement of the reference's algorithm (oracle/c) on the host cores, bounded sample.
+           values, on-device Taylor initialisation, the solve, D2H copy of terminal means and step counts.
+`roofline` FP64: FLOPs of the algorithm the kernel executes (SURVEY.md section 8(d) model without the terms the
+           kernel provably skips) / measured duration against the FP64 FMA peak measured in the same run
+           (MEASURED_PEAKS.json carries no FP64 number); instruction-level fractions from the committed ncu
+           profile are reported beside it and labelled as such.
+`configs`  BASELINE configs 3, 4a, 4b and the config-5 variant at their full ensemble sizes (sharded the same way
+           for N > 1): steps/s, attempts/s, roofline, e2e; the config-5 variant sums the ensemble
+           log-marginal-likelihood over the ranks with `pdeq_allreduce_sum_f64` (ncclAllReduce through the C ABI).
+`cpu_baseline` the plain-C restatement of the reference's algorithm (oracle/c) on the host cores, bounded sample:
+           a PORT, not JAX (jax is not installable here).
 """
 
 from __future__ import annotations
@@ -43,6 +52,15 @@ T0, T1, RTOL, ATOL = 0.0, 50.0, 1e-6, 1e-8
 BASE_LV = np.asarray([0.5, 0.05, 0.5, 0.05])
 CPU_SAMPLE = 1 << 19  # cpu_baseline: ~10-30 s of host work
 REF_SAMPLE = 1 << 17  # --impl reference: instances per step
+PERM_SEED = 0
+
+# Instruction mix of the headline kernel per attempted step, from the committed ncu capture named below
+# (profile-derived constants, NOT measured in this run): executed FP64 FLOPs = 2 DFMA + DMUL + DADD.
+K1_PROFILE = {
+    "file": "profiles/r1e_k1_loop_lv_nu4_iso_ts0.ncu.txt",
+    "dfma": 368, "dmul": 163, "dadd": 30, "fp64_instructions": 579, "instructions": 943,
+    "fp64_pipe_active": 0.713, "dram_bytes_per_launch_2p20": 905.1e6,
+}  # fmt: skip
 
 
 def lv_ensemble(B: int, seed: int):
@@ -51,21 +69,29 @@ def lv_ensemble(B: int, seed: int):
     return BASE_LV[None, :] * draw[:, :4], 20.0 * draw[:, 4:]
 
 
-def flops_per_attempt(n: int, d: int) -> float:
-    """SURVEY.md section 8(d), isotropic ts0 `solver` + `error_state_std` (dense Householder model)."""
+def flops_per_attempt(n: int, d: int, error_qr: bool = True) -> float:
+    """SURVEY.md section 8(d), isotropic ts0 `solver` + `error_state_std` (dense Householder model):
+    prediction 2n^3 + 10n^3/3, two (n+1)^2 triangularisations (correction, error estimate), 4n^2 d, vector field.
+    `error_qr=False` drops the error estimate's triangularisation: the benchmarked kernel replaces it by host
+    constants (pdeq_config.err_const; ts0, damp = 0), so it is not work the kernel does."""
     c_vf = 10.0  # Lotka-Volterra right-hand side
-    return 2 * n**3 + 10 * n**3 / 3 + 2 * 4 * (n + 1) ** 3 / 3 + 4 * n**2 * d + c_vf
+    qr = 4 * (n + 1) ** 3 / 3
+    return 2 * n**3 + 10 * n**3 / 3 + (2 if error_qr else 1) * qr + 4 * n**2 * d + c_vf
 
 
-def config_dict(B: int, n_gpus: int) -> dict:
+def config_dict(B_total: int, n_gpus: int) -> dict:
     return {
-        "workload": "BASELINE configs[1]: Lotka-Volterra ensemble, nu=4, isotropic ts0 filter, solver + "
-        "error_state_std + PI control, terminal values t in [0,50], rtol=1e-6, atol=1e-8",
-        "instances_per_gpu": B,
-        "instances_total": B * n_gpus,
-        "sharding": "by instance index, no collective",
-        "l2": "256 MiB L2 flush between timed steps; per-step inputs+outputs (0.4 GB) exceed the 126 MB L2",
-        "spinup": "untimed passes for >= 0.75 s and until three consecutive passes agree within 3 % before the W warm-up steps (clock ramp of a fresh process)",
+        "workload": "BASELINE configs[1]: ONE Lotka-Volterra ensemble of 2^20 instances, nu=4, isotropic ts0 filter, "
+        "solver + error_state_std + PI control, terminal values t in [0,50], rtol=1e-6, atol=1e-8",
+        "instances_total": B_total,
+        "instances_per_gpu": B_total // n_gpus,
+        "sharding": "permuted instance index (sharding.permutation, seed 0), contiguous shards (sharding.shard_bounds), "
+        "no data-path collective",
+        "l2": "256 MiB L2 flush between timed steps",
+        "spinup": "untimed passes for >= 0.75 s and until three consecutive passes agree within 3 % before the W "
+        "warm-up steps (clock ramp of a fresh process)",
+        "e2e_returns": "terminal means (B, 2) and accepted-step counts only; Cholesky factors are not computed into "
+        "an output buffer nor copied back (want_cholesky=False) -- less than the reference's solution object holds",
     }
 
 
@@ -161,7 +187,8 @@ def cpu_baseline_block(sample: int) -> dict:
         "cores": threads,
         "kind": "port",
         "sample": f"first {sample} instances of the same ensemble, one pass, {dt:.1f} s; plain-C restatement of the "
-        "reference algorithm (oracle/c), OpenMP over instances; JAX is not installable here so the reference itself cannot run",
+        "reference algorithm (oracle/c: dense unblocked Householder, libm pow, -O3 -march=x86-64-v3), OpenMP over "
+        "instances; NOT JAX -- jax is not installable here so the reference itself cannot run",
         "attempts_per_s": float(res["num_attempts"].sum()) / dt,
     }
 
@@ -185,10 +212,11 @@ def run_reference(args) -> None:
     line = {
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong" if args.gpus > 1 else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{args.cpu_sample} instances per step"},
+                         "sample": f"{args.cpu_sample} instances per step; plain-C port of the reference algorithm, not JAX"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }  # fmt: skip
@@ -196,13 +224,172 @@ def run_reference(args) -> None:
 
 
 # ---------------------------------------------------------------------------------------------------
+# The other BASELINE configs (3, 4a, 4b, 5-variant): problem builders for the CUDA arm
+# ---------------------------------------------------------------------------------------------------
+CONFIG5_D = 64  # see DESIGN.md section 7: the largest power of two for which the ORACLE completes every instance
+CONFIG5_CONSTRAINT = "ts0"
+
+
+def other_configs():
+    """name -> dict(host=fn(B) -> dict of host arrays with the ensemble axis leading, B, make=fn(dev inputs) -> run,
+    flops=..., note=...). `run()` returns (solution, extras)."""
+    import torch
+
+    from probdiffeq_b200 import ivpsolve, probdiffeq
+    from probdiffeq_b200 import problems as pb
+
+    def c3_host(B):
+        return dict(u0=pb.pleiades_ensemble(B, seed=1))
+
+    def c3_make(dev_in):
+        vf = probdiffeq.ode("pleiades")
+        ssm = probdiffeq.state_space_model_blockdiag()
+        ts0 = ssm.constraint_ode_ts0(vf)
+        solver = probdiffeq.solver_dynamic(strategy=probdiffeq.strategy_smoother_fixedpoint(), constraint=ts0)
+        error = probdiffeq.error_residual_std(constraint=ts0)
+        solve = ivpsolve.solve_adaptive_save_at(solver=solver, error=error, control=ivpsolve.control_integral())
+        save_at = torch.linspace(0.0, 3.0, 33, dtype=torch.float64, device=dev_in["u0"].device)
+
+        def run():
+            u0 = dev_in["u0"]
+            tcoeffs, _ = probdiffeq.jetexpand_ode_padded_scan(num=5)(vf, (u0,), t=0.0)
+            dt0 = ivpsolve.dt0(vf, (u0,), t=0.0)
+            sol = solve(ssm.prior_wiener_integrated(tcoeffs), save_at=save_at, atol=1e-9, rtol=1e-6, dt0=dt0,
+                        want_posterior=False)
+            return sol, {}
+
+        return run
+
+    def c4a_host(B):
+        rng = np.random.Generator(np.random.PCG64(2))
+        u0 = np.repeat(pb.HIRES_U0[None, :], B, axis=0)
+        sc = rng.uniform(0.9, 1.1, size=(B, 2))
+        u0[:, 0] *= sc[:, 0]
+        u0[:, 7] *= sc[:, 1]
+        return dict(u0=u0)
+
+    def c4a_make(dev_in):
+        vf = probdiffeq.ode("hires")
+        ssm = probdiffeq.state_space_model_dense()
+        ts1 = ssm.constraint_ode_ts1(vf)
+        solver = probdiffeq.solver_dynamic(strategy=probdiffeq.strategy_filter(), constraint=ts1)
+        error = probdiffeq.error_residual_std(constraint=ts1)
+        solve = ivpsolve.solve_adaptive_terminal_values(solver=solver, error=error,
+                                                        control=ivpsolve.control_proportional_integral())
+
+        def run():
+            u0 = dev_in["u0"]
+            tcoeffs, _ = probdiffeq.jetexpand_ode_padded_scan(num=5)(vf, (u0,), t=0.0)
+            dt0 = ivpsolve.dt0(vf, (u0,), t=0.0)
+            sol = solve(ssm.prior_wiener_integrated(tcoeffs), t0=0.0, t1=321.8122, atol=1e-11, rtol=1e-8, dt0=dt0,
+                        want_cholesky=False)
+            return sol, {}
+
+        return run
+
+    def c4b_host(B):
+        rng = np.random.Generator(np.random.PCG64(2))
+        rng.uniform(0.9, 1.1, size=(16384, 2))  # continue the stream of config 4a
+        return dict(u0=2.0 * rng.uniform(0.9, 1.1, size=(B, 1)), du0=np.zeros((B, 1)), params=np.full((B, 1), 1e3))
+
+    def c4b_make(dev_in):
+        ssm = probdiffeq.state_space_model_dense()
+
+        def run():
+            vf = probdiffeq.ode("vanderpol", params=dev_in["params"])
+            ts1 = ssm.constraint_ode_ts1(vf)
+            solver = probdiffeq.solver_dynamic(strategy=probdiffeq.strategy_filter(), constraint=ts1)
+            error = probdiffeq.error_state_std(constraint=ts1)
+            solve = ivpsolve.solve_adaptive_terminal_values(solver=solver, error=error, control=ivpsolve.control_integral())
+            tcoeffs, _ = probdiffeq.jetexpand_ode_padded_scan(num=3)(vf, (dev_in["u0"], dev_in["du0"]), t=0.0)
+            sol = solve(ssm.prior_wiener_integrated(tcoeffs), t0=0.0, t1=6.3, atol=1e-11, rtol=1e-8, want_cholesky=False)
+            return sol, {}
+
+        return run
+
+    d5 = CONFIG5_D
+
+    def c5_host(B):
+        rng = np.random.Generator(np.random.PCG64(3))
+        nu = 0.01 * rng.uniform(0.5, 2.0, size=(B, 1))
+        return dict(params=nu, u0=np.repeat(pb.burgers_u0(d5)[None, :], B, axis=0))
+
+    def c5_make(dev_in):
+        ssm = probdiffeq.state_space_model_blockdiag()
+        lml = probdiffeq.loss_lml_terminal_values()
+        dev = dev_in["u0"].device
+
+        def solve_for(params, u0):
+            vf = probdiffeq.ode("burgers", params=params)
+            cons = ssm.constraint_ode_ts0(vf) if CONFIG5_CONSTRAINT == "ts0" else ssm.constraint_ode_ts1(vf)
+            solver = probdiffeq.solver(strategy=probdiffeq.strategy_filter(), constraint=cons)
+            error = probdiffeq.error_state_std(constraint=cons)
+            solve = ivpsolve.solve_adaptive_terminal_values(solver=solver, error=error,
+                                                            control=ivpsolve.control_proportional_integral())
+            tcoeffs, _ = probdiffeq.jetexpand_ode_padded_scan(num=3)(vf, (u0,), t=0.0)
+            dt0 = ivpsolve.dt0(vf, (u0,), t=0.0)
+            return solve(ssm.prior_wiener_integrated(tcoeffs), t0=0.0, t1=1.0, atol=1e-7, rtol=1e-4, dt0=dt0)
+
+        # data: terminal mean of the viscosity-0.01 instance (solved by this same path) + 1e-2 N(0, 1), std = 1e-2
+        ref = solve_for(torch.full((1, 1), 0.01, dtype=torch.float64, device=dev), dev_in["u0"][:1])
+        noise = np.random.Generator(np.random.PCG64(33)).normal(size=(1, d5))
+        data = ref.u.mean[0][:1] + 1e-2 * torch.from_numpy(noise).to(dev)
+        std = torch.full((1, d5), 1e-2, dtype=torch.float64, device=dev)
+
+        def run():
+            sol = solve_for(dev_in["params"], dev_in["u0"])
+            ll = lml(data, marginals=sol.u, std=std)
+            return sol, {"lml_local": ll.sum().reshape(1)}
+
+        return run
+
+    n3, n4, n5 = 6, 6, 4
+    N4 = n4 * 8
+    f3 = 28 * (4 * (2 * n3) ** 3 / 3 + n3**3 + 4 * n3**3 + 10 * n3**3 / 3 + 4 * (n3 + 1) ** 3 / 3) + 1.1e3
+    f4a = 2 * N4**3 + 10 * N4**3 / 3 + 2 * 8 * N4**2 + 4 * (N4 + 8) ** 3 / 3 + 8**2 * N4
+    f4b = flops_per_attempt(5, 1)
+    err_qr5 = CONFIG5_CONSTRAINT != "ts0"  # ts0, damp = 0: the error estimate's triangularisation is host constants
+    f5 = d5 * (2 * n5**3 + 10 * n5**3 / 3 + (2 if err_qr5 else 1) * 4 * (n5 + 1) ** 3 / 3 + 4 * n5**2) + 6.0 * d5
+    io5 = 8.0 * (n5 * d5 + 1) + 2 * 8.0 * (1 + n5 * d5 + d5 * n5 * n5 + d5) + 4 * 4.0  # per instance: in + 2 checkpoints out
+    return {
+        "3": dict(B=65536, host=c3_host, make=c3_make, flops_per_attempt=f3, kernel="k2_loop_kernel<Pleiades,5,blockdiag,ts0,fixedpoint>",
+                  launches=5 + 1 + 1,
+                  workload="BASELINE configs[2]: Pleiades d=28, nu=5, blockdiag ts0, fixed-point smoother, solver_dynamic + "
+                           "error_residual_std + I control, save_at = linspace(0,3,33), rtol=1e-6, atol=1e-9, dt0 from dt0()",
+                  flops_model="SURVEY 8(d): d * (4(2n)^3/3 + n^3 + 4n^3 + 10n^3/3 + 4(n+1)^3/3) + c_vf, n=6, d=28"),
+        "4a": dict(B=16384, host=c4a_host, make=c4a_make, flops_per_attempt=f4a, kernel="k3_loop_kernel<Hires,5,ts1>",
+                   launches=5 + 1 + 1,
+                   workload="BASELINE configs[3] (a): HIRES d=8, nu=5, dense ts1 (analytic Jacobian), filter, solver_dynamic + "
+                            "error_residual_std + PI control, terminal values t1=321.8122, rtol=1e-8, atol=1e-11",
+                   flops_model="SURVEY 8(d): 2N^3 + 10N^3/3 + 2dN^2 + 4(N+d)^3/3 + d^2 N, N=48, d=8"),
+        "4b": dict(B=16384, host=c4b_host, make=c4b_make, flops_per_attempt=f4b, kernel="k1_loop_kernel<VanDerPol,4,isotropic,1,ts1>",
+                   launches=3 + 1,
+                   workload="BASELINE configs[3] (b): Van der Pol, second-order form, stiffness 1e3, nu=4, dense ts1 (d=1), "
+                            "solver_dynamic + error_state_std + I control, terminal values t1=6.3, rtol=1e-8, atol=1e-11",
+                   flops_model="isotropic model of SURVEY 8(d) with n=5, d=1 (16384 instances fill 29 % of the resident "
+                               "lanes: this config measures the latency of the slowest instance, not throughput)"),
+        "5": dict(B=4096, host=c5_host, make=c5_make, flops_per_attempt=f5, kernel="k2_loop_kernel<Burgers,3,blockdiag,%s,filter>" % CONFIG5_CONSTRAINT,
+                  launches=3 + 1 + 1 + 1, io_bytes_per_instance=io5, lml=True,
+                  workload="BASELINE configs[4] VARIANT: Burgers semi-discretisation with d=%d instead of 1024 (the specified "
+                           "d=1024 blockdiag ts0 solve does not complete in the reference algorithm: DESIGN.md section 7), nu=3, "
+                           "blockdiag %s filter, solver + error_state_std + PI control, terminal values t1=1, rtol=1e-4, atol=1e-7, "
+                           "viscosity 0.01 U(0.5,2); ensemble log-marginal-likelihood (loss_lml_terminal_values, std 1e-2) "
+                           "summed over GPUs with ncclAllReduce" % (d5, CONFIG5_CONSTRAINT),
+                  flops_model="SURVEY 8(d): d * (2n^3 + 10n^3/3 + %s 4(n+1)^3/3 + 4n^2) + c_vf, n=4, d=%d"
+                              % ("2 *" if err_qr5 else "", d5)),
+    }  # fmt: skip
+
+
+# ---------------------------------------------------------------------------------------------------
 # The CUDA arm
 # ---------------------------------------------------------------------------------------------------
 def run_ours(args) -> None:
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
 
-    from probdiffeq_b200 import _lib, ivpsolve, probdiffeq
+    from probdiffeq_b200 import _lib, ivpsolve, probdiffeq, sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -214,68 +401,27 @@ def run_ours(args) -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-    B = args.instances
-
-    params_np, u0_np = lv_ensemble(B, seed=rank)
-    params_h = torch.from_numpy(params_np).pin_memory()
-    u0_h = torch.from_numpy(u0_np).pin_memory()
-    mean_h = torch.empty((B, D), dtype=torch.float64).pin_memory()
-    steps_h = torch.empty((B,), dtype=torch.int32).pin_memory()
-
-    ssm = probdiffeq.state_space_model_isotropic()
-    jetexpand = probdiffeq.jetexpand_ode_padded_scan(num=NU)
-
-    def build_solver(vf):
-        ts0 = ssm.constraint_ode_ts0(vf)
-        solver = probdiffeq.solver(strategy=probdiffeq.strategy_filter(), constraint=ts0)
-        error = probdiffeq.error_state_std(constraint=ts0)
-        control = ivpsolve.control_proportional_integral()
-        return ivpsolve.solve_adaptive_terminal_values(solver=solver, error=error, control=control)
-
-    # ---- device-resident arm: inputs already in HBM ----
-    params_d = params_h.to(dev)
-    u0_d = u0_h.to(dev)
-    vf_d = probdiffeq.ode("lotka_volterra", params=params_d)
-    tcoeffs_d, _ = jetexpand(vf_d, (u0_d,), t=T0)
-    prior_d = ssm.prior_wiener_integrated(tcoeffs_d)
-    solve_d = build_solver(vf_d)
-
-    def step_resident():
-        return solve_d(prior_d, t0=T0, t1=T1, atol=ATOL, rtol=RTOL)
-
-    # ---- end-to-end arm: pinned host inputs -> public API -> host results ----
-    # Two sets of pinned result buffers: the pipelined arm below has two steps in flight.
-    mean_hs = [mean_h, torch.empty((B, D), dtype=torch.float64).pin_memory()]
-    steps_hs = [steps_h, torch.empty((B,), dtype=torch.int32).pin_memory()]
-
-    def step_e2e(slot: int = 0):
-        p = params_h.to(dev, non_blocking=True)
-        u = u0_h.to(dev, non_blocking=True)
-        vf = probdiffeq.ode("lotka_volterra", params=p)
-        tc, _ = jetexpand(vf, (u,), t=T0)
-        prior = ssm.prior_wiener_integrated(tc)
-        sol = build_solver(vf)(prior, t0=T0, t1=T1, atol=ATOL, rtol=RTOL, want_cholesky=False)
-        mean_hs[slot].copy_(sol.u.mean[0], non_blocking=True)
-        steps_hs[slot].copy_(sol.num_steps, non_blocking=True)
-        return sol
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    B_total = args.instances
+    launches = 0  # kernels of this library launched inside timed regions (counted where they are issued)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    per_step = {}
+
+    def timed(fn, steps, warmup, tag=None):
         # Warm-up holds the previous step's result while the next one is produced, exactly as the timed loop below does
         # (`last`): both sets of output buffers then sit in torch's caching allocator, and no timed step pays for a
         # cudaMalloc (which would stall the launch behind it for tens of milliseconds).
         held = None
-        for _ in range(max(warmup, 2)):
+        for _ in range(max(warmup, 2) if tag != "cfg" else warmup):
             cur = fn()
             flush.fill_(1)
             held = cur
-        del held, cur
+        del held
         barrier()
         evs = []
         last = None
@@ -288,10 +434,9 @@ def run_ours(args) -> None:
             evs.append((e0, e1))
         barrier()
         ms = [a.elapsed_time(b) for a, b in evs]
-        per_step.append([round(x, 3) for x in ms])
+        if tag and tag != "cfg":
+            per_step[tag] = [round(x, 3) for x in ms]
         return sum(ms) / len(ms), last
-
-    per_step = []
 
     def timed_pipelined(fn, steps, warmup):
         """The same K end-to-end steps issued on two alternating CUDA streams (the public API runs on torch's
@@ -319,13 +464,77 @@ def run_ours(args) -> None:
         barrier()
         return e0.elapsed_time(e1) / steps
 
-    # Untimed spin-up on top of the W warm-up steps: a fresh process finds the GPU at idle clocks, and W = 3 passes
-    # (~80 ms) can end before the clocks have ramped -- a whole run then reads ~30 % slow. Keep the device busy for
-    # at least 0.75 s and until three consecutive passes agree within 3 % (at most 80 passes) before anything is timed.
-    import time as _time
+    def reduce_max(*vals):
+        if world == 1:
+            return list(vals)
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
 
-    spin_t0, spinup, spin_ms = _time.perf_counter(), 0, []
-    while spinup < 80:
+    def reduce_sum(*vals):
+        if world == 1:
+            return [int(v) for v in vals]
+        t = torch.tensor(vals, dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.tolist()
+
+    # =============================================================================================
+    # headline: BASELINE configs[1], ONE ensemble split over the ranks
+    # =============================================================================================
+    ssm = probdiffeq.state_space_model_isotropic()
+    jetexpand = probdiffeq.jetexpand_ode_padded_scan(num=NU)
+
+    def build_solver(vf):
+        ts0 = ssm.constraint_ode_ts0(vf)
+        solver = probdiffeq.solver(strategy=probdiffeq.strategy_filter(), constraint=ts0)
+        error = probdiffeq.error_state_std(constraint=ts0)
+        control = ivpsolve.control_proportional_integral()
+        return ivpsolve.solve_adaptive_terminal_values(solver=solver, error=error, control=control)
+
+    def lv_arms(params_np, u0_np):
+        """Resident and end-to-end step functions for one shard."""
+        Bs = params_np.shape[0]
+        params_h = torch.from_numpy(np.ascontiguousarray(params_np)).pin_memory()
+        u0_h = torch.from_numpy(np.ascontiguousarray(u0_np)).pin_memory()
+        mean_hs = [torch.empty((Bs, D), dtype=torch.float64).pin_memory() for _ in range(2)]
+        steps_hs = [torch.empty((Bs,), dtype=torch.int32).pin_memory() for _ in range(2)]
+        params_d, u0_d = params_h.to(dev), u0_h.to(dev)
+        vf_d = probdiffeq.ode("lotka_volterra", params=params_d)
+        tcoeffs_d, _ = jetexpand(vf_d, (u0_d,), t=T0)
+        prior_d = ssm.prior_wiener_integrated(tcoeffs_d)
+        solve_d = build_solver(vf_d)
+
+        def step_resident():
+            return solve_d(prior_d, t0=T0, t1=T1, atol=ATOL, rtol=RTOL)
+
+        def step_e2e(slot: int = 0):
+            p = params_h.to(dev, non_blocking=True)
+            u = u0_h.to(dev, non_blocking=True)
+            vf = probdiffeq.ode("lotka_volterra", params=p)
+            tc, _ = jetexpand(vf, (u,), t=T0)
+            prior = ssm.prior_wiener_integrated(tc)
+            sol = build_solver(vf)(prior, t0=T0, t1=T1, atol=ATOL, rtol=RTOL, want_cholesky=False)
+            mean_hs[slot].copy_(sol.u.mean[0], non_blocking=True)
+            steps_hs[slot].copy_(sol.num_steps, non_blocking=True)
+            return sol
+
+        h2d = int(params_h.numel() * 8 + u0_h.numel() * 8)
+        d2h = int(mean_hs[0].numel() * 8 + steps_hs[0].numel() * 4)
+        return step_resident, step_e2e, steps_hs, h2d, d2h
+
+    params_all, u0_all = lv_ensemble(B_total, seed=0)
+    if world > 1:
+        (params_np, u0_np), _idx = sharding.shard((params_all, u0_all), rank, world, seed=PERM_SEED)
+    else:
+        params_np, u0_np = params_all, u0_all
+    B = params_np.shape[0]
+    step_resident, step_e2e, steps_hs, h2d_bytes, d2h_bytes = lv_arms(params_np, u0_np)
+
+    # Untimed spin-up on top of the W warm-up steps: a fresh process finds the GPU at idle clocks, and W = 3 passes
+    # can end before the clocks have ramped -- a whole run then reads ~30 % slow. Keep the device busy for at least
+    # 0.75 s and until three consecutive passes agree within 3 % (at most 400 passes) before anything is timed.
+    spin_t0, spinup, spin_ms = time.perf_counter(), 0, []
+    while spinup < 400:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         step_resident()
@@ -333,91 +542,219 @@ def run_ours(args) -> None:
         torch.cuda.synchronize()
         spin_ms.append(e0.elapsed_time(e1))
         spinup += 1
-        # stop once the device has been busy for 0.75 s AND the last three passes agree within 3 % (clocks settled)
         settled = len(spin_ms) >= 3 and max(spin_ms[-3:]) <= 1.03 * min(spin_ms[-3:])
-        if _time.perf_counter() - spin_t0 >= 0.75 and settled:
+        if time.perf_counter() - spin_t0 >= 0.75 and settled:
             break
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms_res, sol = timed(step_resident, args.steps, args.warmup)
+    ms_res, sol = timed(step_resident, args.steps, args.warmup, "resident")
+    launches += args.steps * 1
     steps_pass = int(sol.num_steps.sum().item())
     attempts_pass = int(sol.num_attempts.sum().item())
     bad = int((sol.status != 0).sum().item())
-    ms_e2e_serial, _ = timed(step_e2e, args.steps, max(args.warmup, 1))
-    e2e_steps_pass = int(steps_h.to(torch.int64).sum().item())
+    ms_e2e_serial, _ = timed(step_e2e, args.steps, max(args.warmup, 1), "e2e_serial")
+    e2e_steps_pass = int(steps_hs[0].to(torch.int64).sum().item())
     ms_e2e = timed_pipelined(step_e2e, args.steps, max(args.warmup, 1))
+    launches += 2 * args.steps * (1 + NU)
     clocks = sampler.stop()
     assert int(steps_hs[1].to(torch.int64).sum().item()) == e2e_steps_pass == int(steps_hs[0].to(torch.int64).sum().item())
+    del sol
 
     # FP64 FMA peak, measured now on this GPU
-    import ctypes as C
-
     pms, pfl = C.c_double(0), C.c_double(0)
     _lib.check(lib.pdeq_fp64_peak_probe(1 << 17, C.byref(pms), C.byref(pfl), None), "fp64 probe")
     fp64_peak_tflops = pfl.value / (pms.value * 1e-3) / 1e12
 
-    # max over ranks / sums over ranks
-    if world > 1:
-        t = torch.tensor([ms_res, ms_e2e, ms_e2e_serial], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_res, ms_e2e, ms_e2e_serial = t.tolist()
-        c = torch.tensor([steps_pass, attempts_pass, e2e_steps_pass, bad], dtype=torch.int64, device=dev)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        steps_all, attempts_all, e2e_steps_all, bad = c.tolist()
-    else:
-        steps_all, attempts_all, e2e_steps_all = steps_pass, attempts_pass, e2e_steps_pass
+    ms_rank = ms_res
+    ms_res, ms_e2e, ms_e2e_serial = reduce_max(ms_res, ms_e2e, ms_e2e_serial)
+    steps_all, attempts_all, e2e_steps_all, bad = reduce_sum(steps_pass, attempts_pass, e2e_steps_pass, bad)
+
+    # ---- the weak-scaling number of round 1 (N > 1 only): every rank its own 2^20-instance ensemble, seed = rank
+    weak = None
+    if world > 1 and not args.no_weak:
+        wp, wu = lv_ensemble(B_total, seed=rank)
+        w_resident, _w_e2e, _sh, _a, _b = lv_arms(wp, wu)
+        ms_w, wsol = timed(w_resident, max(2, args.steps // 2), 2, "weak")
+        launches += max(2, args.steps // 2)
+        (ms_w,) = reduce_max(ms_w)
+        (w_steps,) = reduce_sum(int(wsol.num_steps.sum().item()))
+        weak = {"value": w_steps / (ms_w * 1e-3), "unit": UNIT, "ms_per_step": ms_w,
+                "instances_per_gpu": B_total, "what": "every rank solves its own 2^20-instance ensemble (seed = rank)"}  # fmt: skip
+        del wsol, w_resident
+
+    # =============================================================================================
+    # the other configs
+    # =============================================================================================
+    comm = None
+    configs_out = {}
+    wanted = [c for c in args.configs.split(",") if c]
+    if wanted:
+        table = other_configs()
+        for name in wanted:
+            spec = table[name]
+            Bc = spec["B"] if args.config_instances <= 0 else min(spec["B"], args.config_instances)
+            try:
+                host_all = spec["host"](Bc)
+                keys = list(host_all)
+                if world > 1:
+                    shards, _ = sharding.shard([host_all[k] for k in keys], rank, world, seed=PERM_SEED)
+                    host = dict(zip(keys, shards))
+                else:
+                    host = host_all
+                pinned = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in host.items()}
+                dev_in = {k: v.to(dev) for k, v in pinned.items()}
+                run = spec["make"](dev_in)
+                ms_c, (csol, extra) = timed(run, args.config_steps, 1, "cfg")
+                launches += args.config_steps * spec["launches"]
+                Bl = csol.num_steps.shape[0]
+                c_steps = int(csol.num_steps.reshape(Bl, -1)[:, -1].sum().item())
+                c_att = int(csol.num_attempts.sum().item())
+                c_bad = int((csol.status != 0).sum().item())
+
+                # end to end: pinned host inputs -> device -> Taylor init, dt0, solve (, lml) -> host
+                mean_h = torch.empty(csol.u.mean[0].reshape(Bl, -1, csol.u.mean[0].shape[-1])[:, -1].shape, dtype=torch.float64).pin_memory()
+                nsteps_h = torch.empty((Bl,), dtype=torch.int32).pin_memory()
+                lml_h = torch.empty((1,), dtype=torch.float64).pin_memory()
+
+                def run_e2e(spec=spec, pinned=pinned, mean_h=mean_h, nsteps_h=nsteps_h, lml_h=lml_h, Bl=Bl):
+                    d_in = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+                    s2, ex = spec["make"](d_in)()
+                    m0 = s2.u.mean[0]
+                    mean_h.copy_(m0.reshape(Bl, -1, m0.shape[-1])[:, -1], non_blocking=True)
+                    nsteps_h.copy_(s2.num_steps.reshape(Bl, -1)[:, -1], non_blocking=True)
+                    if "lml_local" in ex:
+                        lml_h.copy_(ex["lml_local"], non_blocking=True)
+                    return s2
+
+                ms_ce, _ = timed(run_e2e, max(1, args.config_steps // 2), 1, "cfg")
+                launches += max(1, args.config_steps // 2) * spec["launches"]
+                ms_c_rank = ms_c
+                ms_c, ms_ce = reduce_max(ms_c, ms_ce)
+                c_steps, c_att, c_bad = reduce_sum(c_steps, c_att, c_bad)
+                fl = spec["flops_per_attempt"]
+                tfl = fl * c_att / (ms_c * 1e-3) / 1e12 / world  # per GPU
+                block = {
+                    "workload": spec["workload"], "instances_total": Bc, "kernel": spec["kernel"],
+                    "ms_per_pass": ms_c, "value": c_steps / (ms_c * 1e-3), "unit": UNIT,
+                    "attempts_per_s": c_att / (ms_c * 1e-3), "accepted_steps_per_pass": c_steps,
+                    "attempts_per_pass": c_att, "rejection_ratio": 1.0 - c_steps / max(c_att, 1),
+                    "failed_instances": c_bad, "timed_passes": args.config_steps,
+                    "timed_region": "H2D-resident u0/params -> Taylor init, dt0, solve" + (", lml" if spec.get("lml") else ""),
+                    "roofline": {"bound": "fp64", "achieved": tfl, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
+                                 "frac": tfl / fp64_peak_tflops, "flops_per_attempt": fl, "flops_model": spec["flops_model"],
+                                 "per": "GPU", "traffic": None,
+                                 "peak_source": "pdeq_fp64_peak_probe (FP64 FMA, measured in this run)"},
+                    "e2e": {"value": c_steps / (ms_ce * 1e-3), "unit": UNIT, "ms_per_step": ms_ce,
+                            "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in pinned.values())),
+                            "d2h_bytes_per_step": int(mean_h.numel() * 8 + nsteps_h.numel() * 4 + (8 if spec.get("lml") else 0))},
+                }  # fmt: skip
+                if "io_bytes_per_instance" in spec:
+                    peaks_path = ROOT / "MEASURED_PEAKS.json"
+                    hbm_peak = json.load(open(peaks_path))["hbm_gbs"] if peaks_path.exists() else 6650.0
+                    gbs = spec["io_bytes_per_instance"] * Bl / (ms_c_rank * 1e-3) / 1e9
+                    block["roofline"]["hbm"] = {
+                        "algorithmic_bytes_per_launch": spec["io_bytes_per_instance"] * Bl, "achieved_gbs": gbs,
+                        "peak_gbs": hbm_peak, "frac": gbs / hbm_peak,
+                        "note": "the carried state stays in shared memory for the whole solve: only inputs and the two "
+                                "checkpoints cross HBM, so the FP64 pipe binds, not HBM",
+                        "peak_source": "MEASURED_PEAKS.json" if peaks_path.exists() else "fallback 6.65 TB/s"}  # fmt: skip
+                if spec.get("lml"):
+                    # the one collective on the path: sum the per-rank log-marginal-likelihoods with ncclAllReduce
+                    # issued through the C ABI, on a communicator created through the C ABI
+                    if comm is None:
+                        comm = sharding.Communicator.from_torch_distributed(dev)
+                    local = extra["lml_local"].clone()
+                    via_abi = comm.allreduce_sum(local.clone())
+                    via_torch = sharding.allreduce_sum(local.clone())
+                    torch.cuda.synchronize()
+                    block["ensemble_lml"] = float(via_abi.item())
+                    block["lml_allreduce"] = {
+                        "via": "pdeq_allreduce_sum_f64 -> ncclAllReduce(sum, f64) on a pdeq_nccl_comm_init_rank communicator",
+                        "comm_nranks": comm.count(), "torch_all_reduce": float(via_torch.item()),
+                        "abs_diff_vs_torch": abs(float(via_abi.item()) - float(via_torch.item())),
+                        "local_lml_rank0": float(local.item())}  # fmt: skip
+                configs_out[name] = block
+                del csol, run, dev_in
+            except Exception as exc:  # one config failing must not hide the headline
+                configs_out[name] = {"error": repr(exc)[:400]}
+            torch.cuda.empty_cache()
 
     if rank == 0:
         n = NU + 1
-        fl = flops_per_attempt(n, D)
+        spec_id = lib.pdeq_k1_spec_choice()
+        shortcut = spec_id != 0  # the specialised builds never triangularise for the error estimate
+        fl_model = flops_per_attempt(n, D, error_qr=True)
+        fl = flops_per_attempt(n, D, error_qr=not shortcut)
         kernel_s = ms_res * 1e-3
-        achieved_tflops = fl * attempts_pass / kernel_s / 1e12
+        achieved_tflops = fl * attempts_all / kernel_s / 1e12 / world  # per GPU
+        fl_exec = 2 * K1_PROFILE["dfma"] + K1_PROFILE["dmul"] + K1_PROFILE["dadd"]
+        exec_tflops = fl_exec * attempts_all / kernel_s / 1e12 / world
         peaks_path = ROOT / "MEASURED_PEAKS.json"
         hbm_peak = json.load(open(peaks_path))["hbm_gbs"] if peaks_path.exists() else 6650.0
-        bytes_algo = B * 8.0 * (n * D + 4 + (2 * (1 + n * D + n * n + 1)) ) + B * 4.0 * (2 + 2)
+        bytes_algo = B * 8.0 * (n * D + 4 + (2 * (1 + n * D + n * n + 1))) + B * 4.0 * (2 + 2)
         line = {
-            "metric": METRIC, "value": steps_all / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": steps_all / kernel_s, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(B, world),
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(B_total, world),
             "accepted_steps_per_pass": steps_all, "attempts_per_pass": attempts_all,
             "rejection_ratio": 1.0 - steps_all / max(attempts_all, 1), "failed_instances": bad,
-            "attempts_per_s": attempts_all / (ms_res * 1e-3),
+            "attempts_per_s": attempts_all / kernel_s,
+            "tail_compaction": {"enabled": os.environ.get("PDEQ_K1_POOL", "1") != "0",
+                                "segment": int(os.environ.get("PDEQ_K1_SEG", "32"))},
             "e2e": {
                 "value": e2e_steps_all / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(params_h.numel() * 8 + u0_h.numel() * 8),
-                "d2h_bytes_per_step": int(mean_h.numel() * 8 + steps_h.numel() * 4),
+                "h2d_bytes_per_step": h2d_bytes * world if world > 1 else h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes * world if world > 1 else d2h_bytes,
+                "returns": "terminal means and accepted-step counts (no Cholesky factors: want_cholesky=False)",
                 "how": "K public-API steps on two alternating CUDA streams (double-buffered pinned result buffers): "
                        "each step copies its inputs host->device, runs the Taylor pass and the loop kernel, and reads "
                        "its terminal values and step counts back; device time over the K steps / K",
                 "serial": {"value": e2e_steps_all / (ms_e2e_serial * 1e-3), "ms_per_step": ms_e2e_serial,
                            "how": "the same steps one after the other on one stream, L2 flushed in between"},
             },
-            "gpu_launches": args.steps * 1 + 2 * args.steps * 5,
-            "gpu_launches_note": "1 loop kernel per step in the resident arm; each of the two e2e arms (serial, pipelined) launches 1 loop kernel + 4 Taylor-pass kernels per step",
+            "gpu_launches": launches,
+            "gpu_launches_note": "kernels of this library issued inside timed regions on rank 0: 1 loop kernel per "
+                                 "resident step; 1 loop + 4 Taylor-pass kernels per e2e step (two e2e arms); per "
+                                 "config pass: Taylor passes + dt0 + loop (+ lml)",
             "roofline": {
                 "bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
-                "frac": achieved_tflops / fp64_peak_tflops,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this workload, from the ncu --set full
-                # capture summarised in profiles/r1e_k1_loop_lv_nu4_iso_ts0.ncu.txt (221.0 MB + 684.1 MB)
-                "traffic": 905.1e6 if B == B_DEFAULT else None, "traffic_unit": "bytes per launch (ncu)",
-                "kernel": f"k1_loop_kernel<LotkaVolterra,4,isotropic,2,ts0,SPEC={lib.pdeq_k1_spec_choice()}>",
-                "flops_per_attempt": fl, "attempts_per_launch": attempts_pass,
+                "frac": achieved_tflops / fp64_peak_tflops, "per": "GPU",
+                "flops_per_attempt": fl, "attempts_per_launch": attempts_all // world,
+                "flops_model": "SURVEY 8(d) dense-Householder model of the executed algorithm: prediction 2n^3 + 10n^3/3, "
+                               "ONE (n+1)^2 triangularisation (the correction), 4n^2 d, vector field"
+                               + ("; the error estimate's triangularisation is NOT counted -- the kernel replaces it by host constants"
+                                  if shortcut else "; plus the error estimate's triangularisation (general kernel)"),
+                "frac_survey_model_incl_skipped_qr": fl_model * attempts_all / kernel_s / 1e12 / world / fp64_peak_tflops,
+                "frac_executed": exec_tflops / fp64_peak_tflops,
+                "frac_executed_note": "executed FP64 FLOPs per attempt (2 DFMA + DMUL + DADD = %d) from the ncu capture %s "
+                                      "(profile-derived, not measured in this run); FP64 pipe active there: %.3f"
+                                      % (fl_exec, K1_PROFILE["file"], K1_PROFILE["fp64_pipe_active"]),
+                "traffic": None,
+                "traffic_note": "not measurable inside this run; the ncu capture %s reports %.1f MB per 2^20-instance launch "
+                                "(dram__bytes_read.sum + dram__bytes_write.sum)" % (K1_PROFILE["file"], K1_PROFILE["dram_bytes_per_launch_2p20"] / 1e6),
+                "kernel": f"k1_loop_kernel<LotkaVolterra,4,isotropic,2,ts0,SPEC={spec_id}>",
                 "peak_source": "pdeq_fp64_peak_probe (FP64 FMA, measured in this run; MEASURED_PEAKS.json has no FP64 figure)",
-                "hbm": {"algorithmic_bytes_per_launch": bytes_algo, "achieved_gbs": bytes_algo / kernel_s / 1e9,
-                        "peak_gbs": hbm_peak, "frac": bytes_algo / kernel_s / 1e9 / hbm_peak,
+                "hbm": {"algorithmic_bytes_per_launch": bytes_algo, "achieved_gbs": bytes_algo / (ms_rank * 1e-3) / 1e9,
+                        "peak_gbs": hbm_peak, "frac": bytes_algo / (ms_rank * 1e-3) / 1e9 / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks_path.exists() else "fallback 6.65 TB/s"},
             },
             "clocks": clocks,
-            "ms_steps": {"resident": per_step[0], "e2e_serial": per_step[1]},
+            "ms_steps": per_step,
         }  # fmt: skip
+        if weak is not None:
+            line["weak"] = weak
+        if configs_out:
+            line["configs"] = configs_out
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline_block(args.cpu_sample)
             except Exception as exc:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {exc!r}"}
         print(json.dumps(line))
+    if comm is not None:
+        comm.destroy()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -429,9 +766,13 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--instances", type=int, default=B_DEFAULT, help="instances per GPU")
+    ap.add_argument("--instances", type=int, default=B_DEFAULT, help="instances of the WHOLE ensemble (split over the GPUs)")
     ap.add_argument("--cpu-sample", type=int, default=None, help="instances in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-weak", action="store_true", help="skip the extra weak-scaling pass for N > 1")
+    ap.add_argument("--configs", default="3,4a,4b,5", help="other BASELINE configs to time ('' = none)")
+    ap.add_argument("--config-steps", type=int, default=2, help="timed passes per other config")
+    ap.add_argument("--config-instances", type=int, default=0, help="cap the other configs' ensembles (0 = full size)")
     args = ap.parse_args()
     if args.cpu_sample is None:
         args.cpu_sample = REF_SAMPLE if args.impl == "reference" else CPU_SAMPLE

@@ -240,8 +240,21 @@ int pdeq_offgrid_marginals(const pdeq_config* cfg, int64_t num_instances, int32_
                            double* out_chol, void* stream);
 
 /* Sum `n` doubles in place across the ranks of an NCCL communicator (ncclComm_t passed as void*):
-   the ensemble log-marginal-likelihood reduction. The only collective on this path. */
+   the ensemble log-marginal-likelihood reduction, i.e. the sum over instances of the per-instance term of
+   loss_lml_terminal_values (probdiffeq/_probdiffeq/estimators_and_losses.py:20-50) when the instances live on several
+   GPUs. The only collective on this path; the reference has none (its only batching is jax.vmap,
+   probdiffeq/backend/func.py:9-10). */
 int pdeq_allreduce_sum_f64(void* nccl_comm, double* buf, int64_t n, void* stream);
+
+/* Communicator plumbing for hosts that do not own an ncclComm_t (a ctypes / jax.ffi host): NCCL is resolved from the
+   process (dlopen of libnccl.so.2, the copy already loaded if there is one). Rank 0 calls pdeq_nccl_unique_id, the
+   128-byte id travels to the other ranks by whatever side channel the host has (torch.distributed, MPI, a file), and
+   every rank calls pdeq_nccl_comm_init_rank with its CUDA device current. pdeq_nccl_comm_count returns the number
+   of ranks of a communicator (-1 on error). */
+int pdeq_nccl_unique_id(void* id128);
+int pdeq_nccl_comm_init_rank(void** nccl_comm, int32_t nranks, const void* id128, int32_t rank);
+int pdeq_nccl_comm_count(void* nccl_comm);
+int pdeq_nccl_comm_destroy(void* nccl_comm);
 
 /* Device-side FP64 FMA throughput probe used for the roofline denominator: runs `iters` dependent
    FMA chains on every SM and returns the elapsed milliseconds in *ms and the FLOP count in *flops. */

@@ -140,6 +140,10 @@ SYMBOLS = {
          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
     ),  # fmt: skip
     "pdeq_allreduce_sum_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pdeq_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "pdeq_nccl_comm_init_rank": (C.c_int, [_P(C.c_void_p), C.c_int32, C.c_void_p, C.c_int32]),
+    "pdeq_nccl_comm_count": (C.c_int, [C.c_void_p]),
+    "pdeq_nccl_comm_destroy": (C.c_int, [C.c_void_p]),
     "pdeq_fp64_peak_probe": (C.c_int, [C.c_int32, _P(C.c_double), _P(C.c_double), C.c_void_p]),
     "pdeq_k1_spec_choice": (C.c_int, []),
 }

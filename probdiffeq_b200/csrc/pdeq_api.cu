@@ -29,7 +29,16 @@ static std::vector<LoopEntry>& loop_table() {
   static std::vector<LoopEntry> t;
   return t;
 }
-void register_loop(const LoopEntry& e) { loop_table().push_back(e); }
+// A second registration under the same key REPLACES the first (a plug-in rebuilt with a changed right-hand side must
+// not leave the old step-loop kernel behind the new Taylor / dt0 kernels), exactly as register_aux does.
+void register_loop(const LoopEntry& e) {
+  for (auto& x : loop_table())
+    if (x.key == e.key) {
+      x = e;
+      return;
+    }
+  loop_table().push_back(e);
+}
 const LoopEntry* find_loop(const KernelKey& key) {
   for (const auto& e : loop_table())
     if (e.key == key) return &e;
@@ -234,6 +243,11 @@ static int run_loop(const pdeq_config* cfg, const pdeq_problem* pr, const pdeq_s
   a.dt0 = dt0;
   a.dt0_stride = dt0_stride;
   a.work_counter = (unsigned long long*)ws;
+  a.pool_ring = nullptr;
+  a.pool_ring_mask = 0;
+  a.pool_slots = nullptr;
+  a.pool_num_slots = 0;
+  a.pool_seg_len = 0;
   cudaError_t e = cudaMemsetAsync(ws, 0, 256, s);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
   const LoopEntry* entry = select_loop(cfg);
@@ -318,20 +332,88 @@ int pdeq_fp64_peak_probe(int32_t iters, double* ms, double* flops, void* stream)
 // NCCL all-reduce of the ensemble log-marginal-likelihood. NCCL is resolved from the process (the copy
 // that created the communicator) so that no second NCCL is loaded.
 // ---------------------------------------------------------------------------------------------------
-int pdeq_allreduce_sum_f64(void* nccl_comm, double* buf, int64_t n, void* stream) {
-  typedef int (*allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
-  static allreduce_fn fn = nullptr;
-  if (fn == nullptr) {
+// NCCL entry points resolved once from the copy of libnccl.so.2 already in the process (torch's), else loaded.
+struct NcclApi {
+  struct UniqueId {
+    char internal[128];  // NCCL_UNIQUE_ID_BYTES
+  };
+  int (*all_reduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*get_unique_id)(UniqueId*) = nullptr;
+  int (*comm_init_rank)(void**, int, UniqueId, int) = nullptr;
+  int (*comm_destroy)(void*) = nullptr;
+  int (*comm_count)(void*, int*) = nullptr;
+  const char* (*get_error_string)(int) = nullptr;
+  bool ok = false;
+};
+static const NcclApi* nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
     void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
     if (h == nullptr) h = dlopen("libnccl.so.2", RTLD_NOW);
-    if (h == nullptr) return fail(-30, "libnccl.so.2 not found: %s", dlerror());
-    fn = (allreduce_fn)dlsym(h, "ncclAllReduce");
-    if (fn == nullptr) return fail(-30, "ncclAllReduce not found");
-  }
+    if (h == nullptr) return;
+    api.all_reduce = (decltype(api.all_reduce))dlsym(h, "ncclAllReduce");
+    api.get_unique_id = (decltype(api.get_unique_id))dlsym(h, "ncclGetUniqueId");
+    api.comm_init_rank = (decltype(api.comm_init_rank))dlsym(h, "ncclCommInitRank");
+    api.comm_destroy = (decltype(api.comm_destroy))dlsym(h, "ncclCommDestroy");
+    api.comm_count = (decltype(api.comm_count))dlsym(h, "ncclCommCount");
+    api.get_error_string = (decltype(api.get_error_string))dlsym(h, "ncclGetErrorString");
+    api.ok = api.all_reduce && api.get_unique_id && api.comm_init_rank && api.comm_destroy && api.comm_count;
+  });
+  return api.ok ? &api : nullptr;
+}
+static int nccl_fail(const NcclApi* api, int rc, const char* where) {
+  return fail(100 + rc, "%s failed: %s (ncclResult %d)", where,
+              api->get_error_string ? api->get_error_string(rc) : "?", rc);
+}
+
+int pdeq_nccl_unique_id(void* id128) {
+  const NcclApi* api = nccl_api();
+  if (api == nullptr) return fail(-30, "libnccl.so.2 not found: %s", dlerror());
+  if (id128 == nullptr) return fail(-31, "id buffer is NULL");
+  NcclApi::UniqueId id;
+  int rc = api->get_unique_id(&id);
+  if (rc != 0) return nccl_fail(api, rc, "ncclGetUniqueId");
+  std::memcpy(id128, id.internal, sizeof(id.internal));
+  return 0;
+}
+
+int pdeq_nccl_comm_init_rank(void** comm, int32_t nranks, const void* id128, int32_t rank) {
+  const NcclApi* api = nccl_api();
+  if (api == nullptr) return fail(-30, "libnccl.so.2 not found: %s", dlerror());
+  if (comm == nullptr || id128 == nullptr) return fail(-31, "comm/id is NULL");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(-31, "bad rank %d of %d", rank, nranks);
+  NcclApi::UniqueId id;
+  std::memcpy(id.internal, id128, sizeof(id.internal));
+  int rc = api->comm_init_rank(comm, nranks, id, rank);
+  if (rc != 0) return nccl_fail(api, rc, "ncclCommInitRank");
+  return 0;
+}
+
+int pdeq_nccl_comm_count(void* nccl_comm) {
+  const NcclApi* api = nccl_api();
+  if (api == nullptr || nccl_comm == nullptr) return -1;
+  int n = -1;
+  return api->comm_count(nccl_comm, &n) == 0 ? n : -1;
+}
+
+int pdeq_nccl_comm_destroy(void* nccl_comm) {
+  const NcclApi* api = nccl_api();
+  if (api == nullptr) return fail(-30, "libnccl.so.2 not found");
+  if (nccl_comm == nullptr) return 0;
+  int rc = api->comm_destroy(nccl_comm);
+  if (rc != 0) return nccl_fail(api, rc, "ncclCommDestroy");
+  return 0;
+}
+
+int pdeq_allreduce_sum_f64(void* nccl_comm, double* buf, int64_t n, void* stream) {
+  const NcclApi* api = nccl_api();
+  if (api == nullptr) return fail(-30, "libnccl.so.2 not found: %s", dlerror());
   if (nccl_comm == nullptr || buf == nullptr) return fail(-31, "comm/buf is NULL");
+  if (n < 0) return fail(-31, "negative count");
   // ncclFloat64 = 8, ncclSum = 0
-  int rc = fn(buf, buf, (size_t)n, 8, 0, nccl_comm, (cudaStream_t)stream);
-  if (rc != 0) return fail(100 + rc, "ncclAllReduce failed with %d", rc);
+  int rc = api->all_reduce(buf, buf, (size_t)n, 8, 0, nccl_comm, (cudaStream_t)stream);
+  if (rc != 0) return nccl_fail(api, rc, "ncclAllReduce");
   return 0;
 }
 

@@ -42,13 +42,38 @@ int device_sm_count();
 // ---------------------------------------------------------------------------------------------------
 // K1 launcher
 // ---------------------------------------------------------------------------------------------------
+// Tail compaction (ThreadLoop::run): PDEQ_K1_POOL=0 in the environment switches it off (A/B measurements),
+// PDEQ_K1_SEG sets how many loop iterations a warp runs between two visits to the pool.
+inline bool k1_pool_enabled() {
+  const char* e = std::getenv("PDEQ_K1_POOL");
+  return e == nullptr || std::atoi(e) != 0;
+}
+inline int k1_pool_seg_len() {
+  const char* e = std::getenv("PDEQ_K1_SEG");
+  const int c = e == nullptr ? 32 : std::atoi(e);
+  return (c >= 1 && c <= 4096) ? c : 32;
+}
+constexpr int K1_MAX_CTAS_PER_SM = 6;
+inline size_t k1_pool_ring_entries(long lanes) {
+  size_t cap = 1024;
+  while ((long)cap < lanes) cap <<= 1;
+  return cap;
+}
+inline long k1_max_lanes(int64_t num_instances) {
+  const long want = (num_instances + K1_THREADS - 1) / K1_THREADS;
+  return std::max(1L, std::min(want, (long)K1_MAX_CTAS_PER_SM * device_sm_count())) * K1_THREADS;
+}
+inline size_t k1_pool_bytes(long lanes, int park_slots) {
+  return k1_pool_ring_entries(lanes) * sizeof(unsigned int) + (size_t)lanes * park_slots * sizeof(double);
+}
+
 template <class VF, int NU, int FACT, int D, bool TS0, int SPEC>
-cudaError_t k1_launch_impl(const LoopArgs& a, cudaStream_t stream) {
+cudaError_t k1_launch_impl(const LoopArgs& a_in, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   using TL = ThreadLoop<VF, NU, FACT, D, TS0, SPEC>;
   auto kern = k1_loop_kernel<VF, NU, FACT, D, TS0, SPEC>;
+  LoopArgs a = a_in;
   const bool needs_interp = a.fixed_grid == 0 && a.cfg.clip_dt == 0;
-  const size_t smem = TL::SMS ? size_t(TL::ST_SLOTS) * TL::THREADS * sizeof(double)
-                              : (needs_interp ? size_t(TL::IF_SLOTS) * TL::THREADS * sizeof(double) : 0);
+  const size_t smem = needs_interp ? size_t(TL::IF_SLOTS) * TL::THREADS * sizeof(double) : 0;
   cudaError_t err;
   if (smem > 48 * 1024) {
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -61,40 +86,57 @@ cudaError_t k1_launch_impl(const LoopArgs& a, cudaStream_t stream) {
   const long want = (a.prob.num_instances + TL::THREADS - 1) / TL::THREADS;
   const long cap = (long)per_sm * device_sm_count();
   const int grid = (int)std::max(1L, std::min(want, cap));
+  // the pool of parked instances lives behind the 256-byte header of the workspace
+  const long lanes = (long)grid * TL::THREADS;
+  const int park = TL::PARK_BASE + (needs_interp ? TL::IF_SLOTS : 0);
+  a.pool_ring = nullptr;
+  a.pool_slots = nullptr;
+  a.pool_ring_mask = 0;
+  a.pool_num_slots = 0;
+  a.pool_seg_len = k1_pool_seg_len();
+  if (k1_pool_enabled() && workspace != nullptr && workspace_bytes >= 256 + k1_pool_bytes(lanes, park)) {
+    const size_t ring = k1_pool_ring_entries(lanes);
+    a.pool_ring = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + 256);
+    a.pool_ring_mask = (unsigned int)(ring - 1);
+    a.pool_slots = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256 + ring * sizeof(unsigned int));
+    a.pool_num_slots = lanes;
+    err = cudaMemsetAsync(a.pool_ring, 0, ring * sizeof(unsigned int), stream);
+    if (err != cudaSuccess) return err;
+  }
   kern<<<grid, TL::THREADS, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
 // Which specialised loop to use when the configuration matches: PDEQ_K1_SPEC=0 in the environment forces the
-// general kernel (A/B measurements, bitwise comparison tests), 1..5 pick a specialised build (ThreadLoop: register
-// budget / resident CTAs / CTA size / where the accepted state lives).
+// general kernel (A/B measurements, bitwise comparison tests), 1..2 pick a specialised build (ThreadLoop: register
+// budget / resident CTAs).
 #ifndef PDEQ_K1_SPEC_DEFAULT
 #define PDEQ_K1_SPEC_DEFAULT 1
 #endif
 inline int k1_spec_choice() {
   const char* e = std::getenv("PDEQ_K1_SPEC");
   const int c = e == nullptr ? PDEQ_K1_SPEC_DEFAULT : std::atoi(e);
-  return (c >= 0 && c <= 5) ? c : PDEQ_K1_SPEC_DEFAULT;
+  return (c >= 0 && c <= 2) ? c : PDEQ_K1_SPEC_DEFAULT;
 }
 
 template <class VF, int NU, int FACT, int D, bool TS0, bool HAS_SPEC = false>
-cudaError_t k1_launch(const LoopArgs& a, void*, size_t, cudaStream_t stream) {
+cudaError_t k1_launch(const LoopArgs& a, void* ws, size_t ws_bytes, cudaStream_t stream) {
   if constexpr (HAS_SPEC && TS0) {
     if (k1_spec_matches(a, TS0)) {
       const int spec = k1_spec_choice();
-      if (spec == 1) return k1_launch_impl<VF, NU, FACT, D, TS0, 1>(a, stream);
-      if (spec == 2) return k1_launch_impl<VF, NU, FACT, D, TS0, 2>(a, stream);
-      if (spec == 3) return k1_launch_impl<VF, NU, FACT, D, TS0, 3>(a, stream);
-      if (spec == 4) return k1_launch_impl<VF, NU, FACT, D, TS0, 4>(a, stream);
-      if (spec == 5) return k1_launch_impl<VF, NU, FACT, D, TS0, 5>(a, stream);
+      if (spec == 1) return k1_launch_impl<VF, NU, FACT, D, TS0, 1>(a, ws, ws_bytes, stream);
+      if (spec == 2) return k1_launch_impl<VF, NU, FACT, D, TS0, 2>(a, ws, ws_bytes, stream);
     }
   }
-  return k1_launch_impl<VF, NU, FACT, D, TS0, 0>(a, stream);
+  return k1_launch_impl<VF, NU, FACT, D, TS0, 0>(a, ws, ws_bytes, stream);
 }
 
 template <class VF, int NU, int FACT, int D, bool TS0, bool HAS_SPEC = false>
 struct K1Registrar {
-  static size_t ws(const pdeq_config&, int64_t, int32_t) { return 256; }
+  static size_t ws(const pdeq_config&, int64_t num_instances, int32_t) {
+    using TL = ThreadLoop<VF, NU, FACT, D, TS0, 0>;
+    return 256 + k1_pool_bytes(k1_max_lanes(num_instances), TL::PARK_SLOTS_MAX);
+  }
   explicit K1Registrar(int vf_id = VF::id) {
     register_loop({{vf_id, NU, FACT, D, TS0 ? 1 : 0, 0}, &k1_launch<VF, NU, FACT, D, TS0, HAS_SPEC>, &ws, "thread"});
   }

@@ -36,6 +36,16 @@ struct LoopArgs {
   const double* dt0;
   int64_t dt0_stride;
   unsigned long long* work_counter;  // zero-initialised by the host wrapper
+  // Tail compaction of the thread-per-instance kernel (K1, see ThreadLoop::run): once the queue of fresh instances
+  // is empty, warps that are no longer full park their unfinished instances in a pool and re-form as full warps.
+  // ctl = work_counter: [0] fresh-instance counter, [1] pool head, [2] pool tail, [3] finished instances (all zeroed
+  // by the host wrapper). ring: zero-initialised tickets (slot + 1). slots: [field][num_slots] parked states.
+  // slots == nullptr switches the compaction off.
+  unsigned int* pool_ring;
+  unsigned int pool_ring_mask;
+  double* pool_slots;
+  int64_t pool_num_slots;
+  int32_t pool_seg_len;
 };
 
 constexpr int K1_THREADS = 128;
@@ -50,7 +60,7 @@ constexpr int K1_THREADS = 128;
 // Resident CTAs per SM of the specialised builds (SPEC = 1..4, see ThreadLoop). Registers are per SM sub-partition
 // (16 K each), so 13..16 resident warps all mean <= 128 registers and 9..12 mean <= 168: there is no build "between"
 // 2 and 1, whatever the CTA size.
-#define PDEQ_K1_SPEC_MIN_BLOCKS(SPEC) ((SPEC) == 4 ? 5 : ((SPEC) >= 2 ? 4 : 3))  // 5: as 2
+#define PDEQ_K1_SPEC_MIN_BLOCKS(SPEC) ((SPEC) >= 2 ? 4 : 3)
 
 template <int n>
 PDEQ_DI double ipow_small(double x, int k) {
@@ -78,17 +88,11 @@ PDEQ_DI double safe_sqrt(double x) {
 //           branches keep alive (the noise-only factor Lq, calibration state), i.e. registers and spills.
 //           The launcher checks the conditions on the host (k1_spec_matches).
 // SPEC = 2: the same loop compiled for four resident CTAs per SM (128 registers) instead of three (168).
-// SPEC = 3: as 2, with the accepted state (mean and factor) resident in shared memory, one column per thread: it is
-//           read at the start of an attempt and written when the attempt is accepted, so the 25 doubles do not
-//           occupy registers during the triangularisations and the accept is 25 predicated stores instead of 50
-//           register moves. SPEC = 4: as 3, five resident CTAs (96 registers).
-// SPEC = 5: as 2, but the vector field's parameters are re-read from global memory (an L1 hit) at the start of every
-//           attempt instead of occupying 2 P registers across the triangularisations.
+// (Round 1 also measured builds with the accepted state in shared memory, five resident CTAs, and parameters re-read
+// per attempt -- all slower, profiles/r1e_sweep_k1_spec.jsonl -- they are gone.)
 template <class VF, int NU, int FACT, int D, bool TS0, int SPEC = 0>
 struct ThreadLoop {
   static constexpr bool SP = SPEC != 0;
-  static constexpr bool SMS = SPEC == 3 || SPEC == 4;  // accepted state in shared memory
-  static constexpr bool PGL = SPEC == 5;               // parameters re-read (L1) per attempt instead of held in registers
   static constexpr int THREADS = K1_THREADS;
   static_assert(!SP || TS0, "the specialised loop is ts0 only");
   static constexpr int n = NU + 1;
@@ -96,7 +100,10 @@ struct ThreadLoop {
   static constexpr int NB = (FACT == PDEQ_FACT_BLOCKDIAG) ? D : 1;
   static constexpr int P = VF::num_params > 0 ? VF::num_params : 1;
   static constexpr int IF_SLOTS = n * D + NB * n * n + 1;  // interp_from: mean, chol, t
-  static constexpr int ST_SLOTS = n * D + NB * (n * (n + 1)) / 2;
+  static constexpr int NLOW = NB * (n * (n + 1)) / 2;
+  // a parked instance (tail compaction): mean, packed factor, calibration state, 4 scalars, 3 packed integers
+  static constexpr int PARK_BASE = n * D + NLOW + 2 * NB + 7;
+  static constexpr int PARK_SLOTS_MAX = PARK_BASE + IF_SLOTS;
   static_assert(q < n, "need more Taylor coefficients than the ODE order");
 
   PDEQ_DI static constexpr int blk(int j) { return FACT == PDEQ_FACT_BLOCKDIAG ? j : 0; }
@@ -145,6 +152,21 @@ struct ThreadLoop {
     }
   }
 
+  // A checkpoint the instance never reached (max_attempts bail-out).
+  PDEQ_DI static void emit_nan(const LoopArgs& a, long b, int ck, int nsteps) {
+    const long bt = b * a.T + ck;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    a.sol.t[bt] = nan;
+    a.sol.num_steps[bt] = nsteps;
+    for (int e = 0; e < n * D; ++e) a.sol.mean[bt * (n * D) + e] = nan;
+    if (a.sol.chol != nullptr) {
+      for (int e = 0; e < NB * n * n; ++e) a.sol.chol[bt * (NB * n * n) + e] = nan;
+    }
+    if (a.sol.output_scale != nullptr) {
+      for (int k = 0; k < NB; ++k) a.sol.output_scale[bt * NB + k] = nan;
+    }
+  }
+
   // interp_from lives in shared memory (one column per thread): it is written on every accepted step but read
   // only when a checkpoint is overstepped, so it should not occupy registers.
   PDEQ_DI static void if_store(double* __restrict__ sm, int nthreads, int tid, const double (&m)[n][D],
@@ -180,42 +202,6 @@ struct ThreadLoop {
       }
     }
     t = sm[(IF_SLOTS - 1) * nthreads + tid];
-  }
-
-  // Accepted state in shared memory (SPEC >= 3), one column per thread (conflict-free).
-  PDEQ_DI static void st_store(double* __restrict__ sm, int nthreads, int tid, const double (&m)[n][D],
-                               const double (&L)[NB][n][n]) {
-    int s = 0;
-#pragma unroll
-    for (int i = 0; i < n; ++i) {
-#pragma unroll
-      for (int j = 0; j < D; ++j) sm[(s++) * nthreads + tid] = m[i][j];
-    }
-#pragma unroll
-    for (int k = 0; k < NB; ++k) {
-#pragma unroll
-      for (int i = 0; i < n; ++i) {
-#pragma unroll
-        for (int j = 0; j <= i; ++j) sm[(s++) * nthreads + tid] = L[k][i][j];
-      }
-    }
-  }
-  PDEQ_DI static void st_load(const double* __restrict__ sm, int nthreads, int tid, double (&m)[n][D],
-                              double (&L)[NB][n][n]) {
-    int s = 0;
-#pragma unroll
-    for (int i = 0; i < n; ++i) {
-#pragma unroll
-      for (int j = 0; j < D; ++j) m[i][j] = sm[(s++) * nthreads + tid];
-    }
-#pragma unroll
-    for (int k = 0; k < NB; ++k) {
-#pragma unroll
-      for (int i = 0; i < n; ++i) {
-#pragma unroll
-        for (int j = 0; j <= i; ++j) L[k][i][j] = sm[(s++) * nthreads + tid];
-      }
-    }
   }
 
   // Whitened RMS of the observation residual per block (IsotropicNormal.residual_whitened_rms_flat,
@@ -262,63 +248,217 @@ struct ThreadLoop {
     double t = 0.0, dt = 0.0, ctrl_lprev = 0.0, ndata = 0.0, t_next = 0.0;
     int nsteps = 0, nattempts = 0, ck = 0, status = 0;
     long b = -1;
-    bool need_load = true;
+
+    // ---- scheduling state ----
+    // Phase 1 (fresh instances left): a lane that finishes its instance pulls the next index from the global counter.
+    // Phase 2 (the counter ran past B for some lane of this warp): the FP64 pipe is what this kernel is bound by and a
+    // warp instruction costs the same with 1 or 32 active lanes, so warps must stay full. Every `pool_seg_len` loop
+    // iterations a warp that is no longer full parks its unfinished instances in a global pool (state written to a
+    // slot, slot id pushed on a ticket ring) and pops up to 32 parked instances back: warps re-form full or empty,
+    // empty warps poll until every instance is finished. Results do not depend on which lane runs an instance.
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = tid & 31;
+    unsigned long long* const ctl = a.work_counter;
+    const bool pooled = a.pool_slots != nullptr;
+    const long nslots = (long)a.pool_num_slots;
+    long slot = (long)blockIdx.x * blockDim.x + tid;  // parking slot; travels with the instance
+    bool have = false, drained = false;
+    int seg_left = 0;
 
     while (true) {
-      // ------------------------------------------------------------------ fetch the next instance
-      if (need_load) {
-        b = (long)atomicAdd(a.work_counter, 1ULL);
-        if (b >= B) break;
-        need_load = false;
-        const double* tc = a.prob.tcoeffs + b * (n * D);
+      __syncwarp();
+      if (!drained) {
+        // ---------------------------------------------------------------- fetch the next fresh instance
+        if (!have) {
+          b = (long)atomicAdd(ctl, 1ULL);
+          if (b < B) {
+            have = true;
+            const double* tc = a.prob.tcoeffs + b * (n * D);
 #pragma unroll
-        for (int i = 0; i < n; ++i) {
+            for (int i = 0; i < n; ++i) {
 #pragma unroll
-          for (int j = 0; j < D; ++j) m[i][j] = tc[i * D + j];
-        }
+              for (int j = 0; j < D; ++j) m[i][j] = tc[i * D + j];
+            }
 #pragma unroll
-        for (int k = 0; k < NB; ++k) {
+            for (int k = 0; k < NB; ++k) {
 #pragma unroll
-          for (int i = 0; i < n; ++i) {
+              for (int i = 0; i < n; ++i) {
 #pragma unroll
-            for (int j = 0; j <= i; ++j) L[k][i][j] = 0.0;
+                for (int j = 0; j <= i; ++j) L[k][i][j] = 0.0;
+              }
+            }
+            if (a.prob.init_std != nullptr) {
+              const double* sd = a.prob.init_std + b * a.prob.init_std_stride;
+#pragma unroll
+              for (int k = 0; k < NB; ++k) {
+#pragma unroll
+                for (int i = 0; i < n; ++i) L[k][i][i] = (FACT == PDEQ_FACT_BLOCKDIAG) ? sd[i * D + k] : sd[i];
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+              prior[k] = (!SP && a.prob.prior_scale != nullptr) ? a.prob.prior_scale[b * a.prob.prior_scale_stride + k] : 1.0;
+              sig[k] = 1.0;
+              run_scale[k] = 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < P; ++k)
+              params[k] = (VF::num_params > 0) ? a.prob.params[b * a.prob.params_stride + k] : 0.0;
+            t = a.grid[0];
+            dt = adaptive ? a.dt0[b * a.dt0_stride] : 0.0;
+            ctrl_lprev = 0.0;  // log2 of the PI controller's initial state 1.0 (controllers.py:42-44)
+            ndata = 0.0;
+            nsteps = 0;
+            nattempts = 0;
+            status = 0;
+            emit(a, b, 0, t, m, L, sig, 0);
+            ck = 1;
+            t_next = (T > 1) ? a.grid[1] : t;
+            if (needs_interp) if_store(smem_if, nthreads, tid, m, L, t);
           }
         }
-        if (a.prob.init_std != nullptr) {
-          const double* sd = a.prob.init_std + b * a.prob.init_std_stride;
+        drained = __any_sync(FULL, !have);
+        seg_left = 0;
+      }
+      if (drained) {
+        if (seg_left <= 0) {
+          const unsigned hm = __ballot_sync(FULL, have);
+          if (!pooled) {
+            if (hm == 0u) break;  // no compaction: the warp leaves when its last lane is done
+          } else if (hm != FULL) {
+            // ---- park this warp's unfinished instances ...
+            if (have) {
+              double* sl = a.pool_slots + slot;
+              int f = 0;
 #pragma unroll
-          for (int k = 0; k < NB; ++k) {
+              for (int i = 0; i < n; ++i) {
 #pragma unroll
-            for (int i = 0; i < n; ++i) L[k][i][i] = (FACT == PDEQ_FACT_BLOCKDIAG) ? sd[i * D + k] : sd[i];
+                for (int j = 0; j < D; ++j) __stcg(sl + (long)(f++) * nslots, m[i][j]);
+              }
+#pragma unroll
+              for (int k = 0; k < NB; ++k) {
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+#pragma unroll
+                  for (int j = 0; j <= i; ++j) __stcg(sl + (long)(f++) * nslots, L[k][i][j]);
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < NB; ++k) {
+                __stcg(sl + (long)(f++) * nslots, sig[k]);
+                __stcg(sl + (long)(f++) * nslots, run_scale[k]);
+              }
+              __stcg(sl + (long)(f++) * nslots, t);
+              __stcg(sl + (long)(f++) * nslots, dt);
+              __stcg(sl + (long)(f++) * nslots, ctrl_lprev);
+              __stcg(sl + (long)(f++) * nslots, ndata);
+              __stcg(sl + (long)(f++) * nslots, __longlong_as_double((long long)b));
+              __stcg(sl + (long)(f++) * nslots,
+                     __longlong_as_double(((long long)nsteps << 32) | (long long)(unsigned)nattempts));
+              __stcg(sl + (long)(f++) * nslots, __longlong_as_double(((long long)ck << 32) | (long long)(unsigned)status));
+              if (needs_interp) {
+                for (int e = 0; e < IF_SLOTS; ++e) __stcg(sl + (long)(f + e) * nslots, smem_if[e * nthreads + tid]);
+              }
+              __threadfence();
+            }
+            __syncwarp();
+            const int k_push = __popc(hm);
+            if (k_push > 0) {
+              unsigned long long base = 0;
+              if (lane == 0) base = atomicAdd(ctl + 2, (unsigned long long)k_push);
+              base = __shfl_sync(FULL, base, 0);
+              if (have) {
+                const unsigned r = __popc(hm & ((1u << lane) - 1u));
+                unsigned int* e = a.pool_ring + (unsigned)((base + r) & a.pool_ring_mask);
+                while (atomicCAS(e, 0u, (unsigned)slot + 1u) != 0u) {
+                }
+              }
+            }
+            have = false;
+            // ---- ... and pop up to 32 parked instances
+            int got = 0;
+            unsigned long long hbase = 0;
+            if (lane == 0) {
+              unsigned long long h = *(volatile unsigned long long*)(ctl + 1);
+              while (true) {
+                const unsigned long long tl = *(volatile unsigned long long*)(ctl + 2);
+                if (tl <= h) break;
+                const unsigned long long g = (tl - h) < 32ULL ? (tl - h) : 32ULL;
+                const unsigned long long old = atomicCAS(ctl + 1, h, h + g);
+                if (old == h) {
+                  got = (int)g;
+                  hbase = h;
+                  break;
+                }
+                h = old;
+              }
+            }
+            got = __shfl_sync(FULL, got, 0);
+            hbase = __shfl_sync(FULL, hbase, 0);
+            if (lane < got) {
+              unsigned int* e = a.pool_ring + (unsigned)((hbase + (unsigned)lane) & a.pool_ring_mask);
+              unsigned v;
+              while ((v = atomicExch(e, 0u)) == 0u) {
+              }
+              slot = (long)v - 1;
+              __threadfence();
+              const double* sl = a.pool_slots + slot;
+              int f = 0;
+#pragma unroll
+              for (int i = 0; i < n; ++i) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) m[i][j] = __ldcg(sl + (long)(f++) * nslots);
+              }
+#pragma unroll
+              for (int k = 0; k < NB; ++k) {
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+#pragma unroll
+                  for (int j = 0; j <= i; ++j) L[k][i][j] = __ldcg(sl + (long)(f++) * nslots);
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < NB; ++k) {
+                sig[k] = __ldcg(sl + (long)(f++) * nslots);
+                run_scale[k] = __ldcg(sl + (long)(f++) * nslots);
+              }
+              t = __ldcg(sl + (long)(f++) * nslots);
+              dt = __ldcg(sl + (long)(f++) * nslots);
+              ctrl_lprev = __ldcg(sl + (long)(f++) * nslots);
+              ndata = __ldcg(sl + (long)(f++) * nslots);
+              b = (long)__double_as_longlong(__ldcg(sl + (long)(f++) * nslots));
+              const long long w1 = __double_as_longlong(__ldcg(sl + (long)(f++) * nslots));
+              const long long w2 = __double_as_longlong(__ldcg(sl + (long)(f++) * nslots));
+              nsteps = (int)(w1 >> 32);
+              nattempts = (int)(unsigned)(w1 & 0xffffffffLL);
+              ck = (int)(w2 >> 32);
+              status = (int)(unsigned)(w2 & 0xffffffffLL);
+              if (needs_interp) {
+                for (int e = 0; e < IF_SLOTS; ++e) smem_if[e * nthreads + tid] = __ldcg(sl + (long)(f + e) * nslots);
+              }
+#pragma unroll
+              for (int k = 0; k < NB; ++k)
+                prior[k] = (!SP && a.prob.prior_scale != nullptr) ? a.prob.prior_scale[b * a.prob.prior_scale_stride + k] : 1.0;
+#pragma unroll
+              for (int k = 0; k < P; ++k)
+                params[k] = (VF::num_params > 0) ? a.prob.params[b * a.prob.params_stride + k] : 0.0;
+              t_next = (ck < T) ? a.grid[ck] : t;
+              have = true;
+            }
+            if (got == 0) {
+              unsigned long long fin = 0;
+              if (lane == 0) fin = *(volatile unsigned long long*)(ctl + 3);
+              fin = __shfl_sync(FULL, fin, 0);
+              if (fin >= (unsigned long long)B) break;  // every instance of the ensemble is finished
+              __nanosleep(400);
+              continue;  // poll again
+            }
           }
+          seg_left = a.pool_seg_len;
         }
-#pragma unroll
-        for (int k = 0; k < NB; ++k) {
-          prior[k] = (!SP && a.prob.prior_scale != nullptr) ? a.prob.prior_scale[b * a.prob.prior_scale_stride + k] : 1.0;
-          sig[k] = 1.0;
-          run_scale[k] = 0.0;
-        }
-#pragma unroll
-        for (int k = 0; k < P; ++k)
-          params[k] = (VF::num_params > 0) ? a.prob.params[b * a.prob.params_stride + k] : 0.0;
-        t = a.grid[0];
-        dt = adaptive ? a.dt0[b * a.dt0_stride] : 0.0;
-        ctrl_lprev = 0.0;  // log2 of the PI controller's initial state 1.0 (controllers.py:42-44)
-        ndata = 0.0;
-        nsteps = 0;
-        nattempts = 0;
-        status = 0;
-        emit(a, b, 0, t, m, L, sig, 0);
-        ck = 1;
-        t_next = (T > 1) ? a.grid[1] : t;
-        if (needs_interp) if_store(smem_if, nthreads, tid, m, L, t);
-        if (SMS) st_store(smem_if, nthreads, tid, m, L);
+        seg_left -= 1;
       }
-      if (SMS) st_load(smem_if, nthreads, tid, m, L);
-      if (PGL && VF::num_params > 0) {
-#pragma unroll
-        for (int k = 0; k < P; ++k) params[k] = a.prob.params[b * a.prob.params_stride + k];
-      }
+      if (!have) continue;
 
       // ------------------------------------------------------------------ checkpoint reached?
       // adaptive: RejectionLoop.loop's interpolation switch (solvers_via_adaptive_steps.py:241-247)
@@ -387,7 +527,8 @@ struct ThreadLoop {
           if (status == 0 && !finite) status = PDEQ_STATUS_NONFINITE;
           a.sol.status[b] = status;
           if (a.sol.num_attempts != nullptr) a.sol.num_attempts[b] = nattempts;
-          need_load = true;
+          have = false;
+          if (pooled) atomicAdd(ctl + 3, 1ULL);
         }
         continue;
       }
@@ -639,9 +780,11 @@ struct ThreadLoop {
           tr[3] = accept ? 1.0 : 0.0;
         }
         if (nattempts >= max_attempts) {
+          // give up on this instance: the checkpoints it never reached are NaN, not whatever the buffers held
           status = PDEQ_STATUS_MAX_ATTEMPTS;
           accept = true;
-          ck = T;  // give up on this instance
+          for (int c = ck; c < T; ++c) emit_nan(a, b, c, nsteps);
+          ck = T;
         }
       }
 
@@ -649,14 +792,10 @@ struct ThreadLoop {
       dt = dt_next;
       if (accept) {
         if (needs_interp) if_store(smem_if, nthreads, tid, m, L, t);  // interp_from <- step_from (:330-338)
-        if (SMS) {
-          st_store(smem_if, nthreads, tid, mn, Ln);
-        } else {
 #pragma unroll
-          for (int i = 0; i < n; ++i) {
+        for (int i = 0; i < n; ++i) {
 #pragma unroll
-            for (int j = 0; j < D; ++j) m[i][j] = mn[i][j];
-          }
+          for (int j = 0; j < D; ++j) m[i][j] = mn[i][j];
         }
 #pragma unroll
         for (int k = 0; k < NB; ++k) {
@@ -664,7 +803,7 @@ struct ThreadLoop {
           for (int i = 0; i < n; ++i) {
 #pragma unroll
             for (int j = 0; j <= i; ++j) {
-              if (!SMS) L[k][i][j] = Ln[k][i][j];
+              L[k][i][j] = Ln[k][i][j];
             }
           }
           if (cfg_solver == PDEQ_SOLVER_DYNAMIC) sig[k] = sig_new[k];

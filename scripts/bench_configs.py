@@ -139,13 +139,14 @@ CONFIGS = {
 if __name__ == "__main__":
     BUDGET = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     ONLY = sys.argv[2].split(",") if len(sys.argv) > 2 else None
+    SIZES = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else None  # override the size ladder
     torch.cuda.set_device(0)
     for name, (make, sizes) in CONFIGS.items():
         if ONLY and not any(name.startswith(o) for o in ONLY):
             continue
         t0 = time.time()
         try:
-            ladder(name, make, sizes)
+            ladder(name, make, SIZES or sizes)
         except Exception as exc:  # keep going: one config failing must not hide the others
             print(json.dumps(dict(config=name, error=repr(exc))), flush=True)
         print(f"# {name}: {time.time() - t0:.1f} s wall", flush=True)

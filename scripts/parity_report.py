@@ -1,0 +1,348 @@
+"""Parity of the CUDA step loop with the oracle on BASELINE configs 2 / 3 / 4a / 4b at their FULL horizons.
+
+For a sample of the seeded ensemble (default 256 instances per config) the kernel's attempt trace is compared with the
+oracle's over the whole solve and the report states, per config,
+
+  * the fraction of instances whose accept/reject sequence is identical attempt by attempt;
+  * for every divergent instance: the index of the first differing attempt and |error_power - 1| there, in both
+    traces (accept iff error_power >= 1, _ivpsolve/solvers_via_adaptive_steps.py:256-258) -- a
+    rounding-level tie-flip sits at the threshold, a defect does not;
+  * the maximum relative error of Taylor coefficient 0 at the terminal time among the sequence-identical instances,
+    and the CONTROL beside every number: the oracle against itself with dt0 moved by +-4 ulp (same statistics), which
+    is what bounds how closely any two implementations of the reference's arithmetic can agree;
+  * a lock-step check that removes the step-size feedback: `solve_fixed_grid` on the oracle's own accepted grid of
+    the full solve, kernel vs oracle at fixed-grid tolerance.
+
+The oracle (test infrastructure) is the checker here and runs on the host cores in a process pool.
+
+  python scripts/parity_report.py [--configs 2,3,4a,4b] [--instances 256] [--out gpurun_out/parity_r2.json]
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import pathlib
+import sys
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+for p in (str(ROOT), str(ROOT / "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+TOL_TERMINAL = 1e-8  # north_star: terminal values within 1e-8 (relative, coefficient 0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# configurations (BASELINE.json configs 2, 3, 4a, 4b)
+# ---------------------------------------------------------------------------------------------------
+def config_inputs(name: str, B: int):
+    """spec, vf name, ensemble inputs (host arrays) of the first B instances of the seeded ensemble."""
+    import pdeq_test_helpers as H
+    from probdiffeq_b200 import problems as pb
+
+    if name == "2":
+        params, u0 = pb.lotka_volterra_ensemble(B, seed=0)
+        return dict(spec=H.spec(), nu=4, params=params, inits=(u0,), save_at=np.asarray([0.0, 50.0]), atol=1e-8,
+                    rtol=1e-6, dt0="0.1", trace_capacity=1024)  # fmt: skip
+    if name == "3":
+        u0 = pb.pleiades_ensemble(B, seed=1)
+        s = H.spec(vf="pleiades", fact="blockdiag", strategy="fixedpoint", solver="solver_dynamic",
+                   error="residual_std", control="i", clip_dt=False)  # fmt: skip
+        return dict(spec=s, nu=5, params=None, inits=(u0,), save_at=np.linspace(0.0, 3.0, 33), atol=1e-9, rtol=1e-6,
+                    dt0="dt0", trace_capacity=6144)  # fmt: skip
+    if name == "4a":
+        rng = np.random.Generator(np.random.PCG64(2))
+        u0 = np.repeat(pb.HIRES_U0[None, :], B, axis=0)
+        sc = rng.uniform(0.9, 1.1, size=(B, 2))
+        u0[:, 0] *= sc[:, 0]
+        u0[:, 7] *= sc[:, 1]
+        s = H.spec(vf="hires", fact="dense", constraint="ts1", solver="solver_dynamic", error="residual_std",
+                   control="pi", clip_dt=True)  # fmt: skip
+        return dict(spec=s, nu=5, params=None, inits=(u0,), save_at=np.asarray([0.0, 321.8122]), atol=1e-11,
+                    rtol=1e-8, dt0="dt0", trace_capacity=4096)  # fmt: skip
+    if name == "4b":
+        rng = np.random.Generator(np.random.PCG64(2))
+        rng.uniform(0.9, 1.1, size=(16384, 2))  # continue the stream of config 4a
+        u0 = 2.0 * rng.uniform(0.9, 1.1, size=(B, 1))
+        s = H.spec(vf="vanderpol", fact="dense", constraint="ts1", solver="solver_dynamic", error="state_std",
+                   control="i", clip_dt=True)  # fmt: skip
+        return dict(spec=s, nu=3, params=np.full((B, 1), 1e3), inits=(u0, np.zeros((B, 1))),
+                    save_at=np.asarray([0.0, 6.3]), atol=1e-11, rtol=1e-8, dt0="0.1", trace_capacity=8192)  # fmt: skip
+    raise KeyError(name)
+
+
+def run_product(cfg):
+    """The CUDA path with the attempt trace on. Returns host arrays."""
+    import torch
+
+    import pdeq_test_helpers as H
+
+    s = cfg["spec"]
+    p_pdq, p_ivp, vf, ssm, solver, err, ctrl = H.product_build(s, cfg["params"])
+    tcoeffs, _ = p_pdq.jetexpand_ode_padded_scan(num=cfg["nu"])(vf, cfg["inits"], t=float(cfg["save_at"][0]))
+    prior = ssm.prior_wiener_integrated(tcoeffs)
+    B = tcoeffs.shape[0]
+    if cfg["dt0"] == "dt0":
+        dt0 = p_ivp.dt0(vf, cfg["inits"], t=float(cfg["save_at"][0]))
+        dt0_h = dt0.cpu().numpy()
+    else:
+        dt0, dt0_h = float(cfg["dt0"]), np.full((B,), float(cfg["dt0"]))
+    solve = p_ivp.solve_adaptive_save_at(solver=solver, error=err, control=ctrl, clip_dt=s["clip_dt"], warn=False)
+    sol = solve(prior, save_at=cfg["save_at"], atol=cfg["atol"], rtol=cfg["rtol"], dt0=dt0,
+                trace_capacity=cfg["trace_capacity"], want_posterior=False)  # fmt: skip
+    torch.cuda.synchronize()
+    return dict(
+        tcoeffs=tcoeffs.cpu().numpy(), dt0=dt0_h, trace=sol.trace.cpu().numpy(),
+        num_attempts=sol.num_attempts.cpu().numpy(), num_steps=sol.num_steps.cpu().numpy(),
+        status=sol.status.cpu().numpy(), mean=sol.u.mean_flat.cpu().numpy(), t=sol.t.cpu().numpy(),
+    )  # fmt: skip
+
+
+# ---------------------------------------------------------------------------------------------------
+# oracle workers
+# ---------------------------------------------------------------------------------------------------
+def _oracle_one(job):
+    import pdeq_test_helpers as H
+
+    s, tc, params, save_at, atol, rtol, dt0 = job
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    osol, trace = H.oracle_solve_save_at(s, tc, params, save_at, atol, rtol, dt0=dt0)
+    tr = np.asarray(trace, dtype=np.float64).reshape(-1, 4)
+    return dict(trace=tr, mean=np.asarray(osol.u_mean), num_steps=np.asarray(osol.num_steps))
+
+
+PERTURBATIONS = (1.0 + 8.9e-16, 1.0 - 8.9e-16)  # dt0 moved by +-4 ulp: the oracle's own conditioning control
+AMPLIFICATION_LEVELS = (1e-12, 1e-9, 1e-6, 1e-3)
+
+
+def run_oracle(cfg, tcoeffs, dt0, pool, factor=1.0, only=None):
+    idx = range(tcoeffs.shape[0]) if only is None else only
+    jobs = []
+    for b in idx:
+        params = None if cfg["params"] is None else cfg["params"][b]
+        jobs.append((cfg["spec"], tcoeffs[b], params, cfg["save_at"], cfg["atol"], cfg["rtol"], float(dt0[b]) * factor))
+    return pool.map(_oracle_one, jobs, chunksize=1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# comparison
+# ---------------------------------------------------------------------------------------------------
+def _rel0(got, ref):
+    """Relative error of Taylor coefficient 0 at the terminal time; got / ref are (T, n, d)."""
+    g, r = np.asarray(got)[-1, 0], np.asarray(ref)[-1, 0]
+    return float(np.max(np.abs(g - r)) / max(np.max(np.abs(r)), 1e-300))
+
+
+def pair_stats(tr_a, tr_b):
+    """Two attempt traces (rows t_from, dt, error_power, accepted) of the same instance: the first attempt whose
+    accept/reject decision differs (None = identical sequences), |error_power - 1| there in both, and how the
+    relative difference of the attempted step sizes grows along the common prefix (rounding amplification)."""
+    m = min(len(tr_a), len(tr_b))
+    acc_a, acc_b = tr_a[:m, 3] > 0.5, tr_b[:m, 3] > 0.5
+    diff = np.nonzero(acc_a != acc_b)[0]
+    if len(diff):
+        first = int(diff[0])
+    else:
+        first = None if len(tr_a) == len(tr_b) else m  # one trace is a prefix of the other
+    upto = m if first is None else min(first + 1, m)
+    rel_dt = np.abs(tr_a[:upto, 1] - tr_b[:upto, 1]) / np.abs(tr_b[:upto, 1])
+    amp = {}
+    for lvl in AMPLIFICATION_LEVELS:
+        hit = np.nonzero(rel_dt > lvl)[0]
+        amp["%g" % lvl] = int(hit[0]) if len(hit) else None
+    out = dict(first_differing_attempt=first, dt_rel_diff_first_exceeds=amp,
+               dt_rel_diff_max_on_common_prefix=float(rel_dt.max()) if upto else 0.0)
+    if first is not None:
+        j = min(first, m - 1)
+        out.update(error_power_a=float(tr_a[j, 2]), error_power_b=float(tr_b[j, 2]),
+                   dist_to_threshold=float(min(abs(tr_a[j, 2] - 1.0), abs(tr_b[j, 2] - 1.0))),
+                   dt_rel_diff_there=float(rel_dt[j]), t_from=float(tr_b[j, 0]))  # fmt: skip
+    return out
+
+
+def _median(xs):
+    xs = [x for x in xs if x is not None]
+    return float(np.median(xs)) if xs else None
+
+
+def compare(cfg, prod, ora, pool):
+    """Kernel vs oracle, next to the control: the oracle vs ITSELF with dt0 moved by +-4 ulp."""
+    B = prod["tcoeffs"].shape[0]
+    cap = prod["trace"].shape[1]
+    perturbed = [run_oracle(cfg, prod["tcoeffs"], prod["dt0"], pool, factor=f) for f in PERTURBATIONS]
+    rows = []
+    for b in range(B):
+        otr = ora[b]["trace"]
+        na = int(prod["num_attempts"][b])
+        gtr = prod["trace"][b, : min(na, cap)]
+        k = pair_stats(gtr, otr)
+        if k["first_differing_attempt"] is None and na != len(otr):  # trace capacity exhausted: not comparable
+            k["first_differing_attempt"] = min(na, cap)
+        selfs = [pair_stats(p[b]["trace"], otr) for p in perturbed]
+        self_first = [x["first_differing_attempt"] for x in selfs]
+        self_first_min = min((x for x in self_first if x is not None), default=None)
+        rows.append(dict(
+            instance=b, attempts_kernel=na, attempts_oracle=int(len(otr)),
+            kernel_vs_oracle=k,
+            oracle_vs_perturbed_oracle=dict(
+                first_differing_attempt=self_first_min,
+                dist_to_threshold=min((x["dist_to_threshold"] for x in selfs if "dist_to_threshold" in x), default=None),
+                dt_rel_diff_first_exceeds={lvl: min((x["dt_rel_diff_first_exceeds"][lvl] for x in selfs
+                                                     if x["dt_rel_diff_first_exceeds"][lvl] is not None), default=None)
+                                           for lvl in selfs[0]["dt_rel_diff_first_exceeds"]},
+                terminal_sensitivity=max(_rel0(p[b]["mean"], ora[b]["mean"]) for p in perturbed)),
+            rel_terminal_coeff0=_rel0(prod["mean"][b], ora[b]["mean"]),
+        ))  # fmt: skip
+    ident = [r for r in rows if r["kernel_vs_oracle"]["first_differing_attempt"] is None]
+    div = [r for r in rows if r["kernel_vs_oracle"]["first_differing_attempt"] is not None]
+    self_ident = [r for r in rows if r["oracle_vs_perturbed_oracle"]["first_differing_attempt"] is None]
+    vals = [r["rel_terminal_coeff0"] for r in ident]
+    above = [r for r in ident if r["rel_terminal_coeff0"] > TOL_TERMINAL]
+    amp_k = {lvl: _median([r["kernel_vs_oracle"]["dt_rel_diff_first_exceeds"][lvl] for r in rows])
+             for lvl in rows[0]["kernel_vs_oracle"]["dt_rel_diff_first_exceeds"]}
+    amp_o = {lvl: _median([r["oracle_vs_perturbed_oracle"]["dt_rel_diff_first_exceeds"][lvl] for r in rows])
+             for lvl in amp_k}
+    # divergences NOT explained by the oracle's own conditioning: the kernel parts from the oracle although the
+    # perturbed oracle keeps its sequence for that instance, or parts much earlier than the perturbed oracle does
+    unexplained = []
+    for r in div:
+        fk = r["kernel_vs_oracle"]["first_differing_attempt"]
+        fo = r["oracle_vs_perturbed_oracle"]["first_differing_attempt"]
+        if fo is None or fk < 0.5 * fo:
+            unexplained.append(dict(instance=r["instance"], kernel=fk, oracle_self=fo,
+                                    dist_to_threshold=r["kernel_vs_oracle"].get("dist_to_threshold")))
+    return dict(
+        instances=B,
+        failed_instances=int((prod["status"] != 0).sum()),
+        attempts_total_kernel=int(prod["num_attempts"].sum()),
+        attempts_total_oracle=int(sum(len(o["trace"]) for o in ora)),
+        kernel_vs_oracle=dict(
+            identical_sequence=len(ident), identical_fraction=len(ident) / B,
+            median_first_differing_attempt=_median([r["kernel_vs_oracle"]["first_differing_attempt"] for r in div]),
+            max_dist_to_threshold_at_divergence=max((r["kernel_vs_oracle"]["dist_to_threshold"] for r in div), default=None),
+            median_dist_to_threshold_at_divergence=_median([r["kernel_vs_oracle"]["dist_to_threshold"] for r in div]),
+            median_attempt_where_dt_rel_diff_first_exceeds=amp_k),
+        oracle_vs_perturbed_oracle=dict(
+            perturbation="dt0 * (1 +- 8.9e-16), the earlier of the two divergences",
+            identical_sequence=len(self_ident), identical_fraction=len(self_ident) / B,
+            median_first_differing_attempt=_median([r["oracle_vs_perturbed_oracle"]["first_differing_attempt"] for r in rows]),
+            median_dist_to_threshold_at_divergence=_median([r["oracle_vs_perturbed_oracle"]["dist_to_threshold"] for r in rows]),
+            median_attempt_where_dt_rel_diff_first_exceeds=amp_o,
+            max_terminal_sensitivity=max(r["oracle_vs_perturbed_oracle"]["terminal_sensitivity"] for r in rows)),
+        terminal_coeff0=dict(
+            max_rel_identical=max(vals) if vals else None,
+            median_rel_identical=float(np.median(vals)) if vals else None,
+            identical_within_tolerance=int(sum(v <= TOL_TERMINAL for v in vals)),
+            identical_above_tolerance=[dict(instance=r["instance"], rel=r["rel_terminal_coeff0"],
+                                            oracle_sensitivity=r["oracle_vs_perturbed_oracle"]["terminal_sensitivity"])
+                                       for r in above],
+            max_rel_divergent=max((r["rel_terminal_coeff0"] for r in div), default=None),
+            max_ratio_to_oracle_sensitivity_divergent=max(
+                (r["rel_terminal_coeff0"] / max(r["oracle_vs_perturbed_oracle"]["terminal_sensitivity"], 1e-16) for r in div),
+                default=None)),
+        divergences_not_explained_by_oracle_conditioning=unexplained,
+        per_instance=rows,
+    )  # fmt: skip
+
+
+# ---------------------------------------------------------------------------------------------------
+# lock-step check: the per-step arithmetic over the full horizon, without the step-size feedback
+# ---------------------------------------------------------------------------------------------------
+def _fixed_one(job):
+    import pdeq_test_helpers as H
+
+    s, tc, params, grid = job
+    osol = H.oracle_solve_fixed(s, tc, params, grid)
+    return dict(mean=np.asarray(osol.u_mean), chol=np.asarray(osol.u_chol))
+
+
+def lockstep(cfg, prod, ora, pool, instances=8):
+    """`solve_fixed_grid` (filter) on the grid of the ORACLE's accepted steps of the adaptive solve, kernel vs oracle:
+    every step of the full horizon is compared at fixed-grid tolerance (north_star: 1e-10 in means and Cholesky
+    covariances), which the chaotic step-size feedback of the adaptive loop cannot blur."""
+    import torch
+
+    import pdeq_test_helpers as H
+
+    s = dict(cfg["spec"], strategy="filter")
+    rows, jobs, grids = [], [], []
+    pick = list(range(min(instances, prod["tcoeffs"].shape[0])))
+    for b in pick:
+        tr = ora[b]["trace"]
+        acc = tr[tr[:, 3] > 0.5]
+        grid = np.concatenate([acc[:1, 0], acc[:, 0] + acc[:, 1]])
+        grids.append(grid)
+        jobs.append((s, prod["tcoeffs"][b], None if cfg["params"] is None else cfg["params"][b], grid))
+    ref = pool.map(_fixed_one, jobs, chunksize=1)
+    for b, grid, r in zip(pick, grids, ref):
+        params = None if cfg["params"] is None else cfg["params"][b : b + 1]
+        p_pdq, p_ivp, vf, ssm, solver, _err, _ctrl = H.product_build(s, params)
+        prior = ssm.prior_wiener_integrated(torch.as_tensor(prod["tcoeffs"][b : b + 1], device="cuda"))
+        sol = p_ivp.solve_fixed_grid(solver=solver)(prior, grid=grid)
+        torch.cuda.synchronize()
+        got_m = sol.u.mean_flat[0].cpu().numpy()
+        L = sol.u.cholesky_flat[0].cpu().numpy()
+        cov, cov_ref = L @ np.swapaxes(L, -1, -2), r["chol"] @ np.swapaxes(r["chol"], -1, -2)
+        ref_m = r["mean"].reshape(got_m.shape)
+        # relative to the largest entry of the same quantity at the same grid point
+        rel_m = np.max(np.abs(got_m - ref_m).reshape(len(grid), -1), axis=1) / np.max(np.abs(ref_m).reshape(len(grid), -1), axis=1)
+        den = np.maximum(np.max(np.abs(cov_ref).reshape(len(grid), -1), axis=1), 1e-300)
+        rel_c = np.max(np.abs(cov - cov_ref.reshape(cov.shape)).reshape(len(grid), -1), axis=1) / den
+        rows.append(dict(instance=b, grid_points=int(len(grid)), max_rel_mean=float(rel_m.max()),
+                         max_rel_cov=float(rel_c[1:].max()), rel_mean_terminal=float(rel_m[-1])))  # fmt: skip
+    return dict(what=lockstep.__doc__.split("\n\n")[0], instances=rows,
+                max_rel_mean=max(r["max_rel_mean"] for r in rows), max_rel_cov=max(r["max_rel_cov"] for r in rows))
+
+
+def report(names, B, workers=None, lockstep_instances=8, keep_rows=True):
+    out = {"what": __doc__.split("\n\n")[0], "tolerance_terminal": TOL_TERMINAL,
+           "oracle": "NumPy restatement of the reference (oracle/); parity with JAX itself is unpinned (no jax here)"}
+    workers = workers or len(os.sched_getaffinity(0))
+    with mp.get_context("spawn").Pool(workers) as pool:
+        for name in names:
+            t0 = time.time()
+            cfg = config_inputs(name, B)
+            prod = run_product(cfg)
+            t1 = time.time()
+            ora = run_oracle(cfg, prod["tcoeffs"], prod["dt0"], pool)
+            res = compare(cfg, prod, ora, pool)
+            if lockstep_instances:
+                res["lockstep_fixed_grid"] = lockstep(cfg, prod, ora, pool, lockstep_instances)
+            if not keep_rows:
+                res.pop("per_instance")
+            res["seconds"] = dict(kernel_and_setup=t1 - t0, oracle=time.time() - t1, host_workers=workers)
+            res["config"] = dict(spec=cfg["spec"], nu=cfg["nu"], save_at=[float(cfg["save_at"][0]), float(cfg["save_at"][-1]),
+                                 len(cfg["save_at"])], atol=cfg["atol"], rtol=cfg["rtol"])  # fmt: skip
+            out["config_" + name] = res
+            k, o = res["kernel_vs_oracle"], res["oracle_vs_perturbed_oracle"]
+            print(f"# config {name}: identical sequences kernel/oracle {k['identical_sequence']}/{B}, perturbed oracle/oracle "
+                  f"{o['identical_sequence']}/{B}; median first divergence {k['median_first_differing_attempt']} vs "
+                  f"{o['median_first_differing_attempt']}; max rel terminal (identical) {res['terminal_coeff0']['max_rel_identical']}; "
+                  f"unexplained {len(res['divergences_not_explained_by_oracle_conditioning'])}; "
+                  f"lockstep {res.get('lockstep_fixed_grid', {}).get('max_rel_mean')} / "
+                  f"{res.get('lockstep_fixed_grid', {}).get('max_rel_cov')}; {time.time() - t0:.0f} s", flush=True)  # fmt: skip
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="2,3,4a,4b")
+    ap.add_argument("--instances", type=int, default=256)
+    ap.add_argument("--workers", type=int, default=0)
+    ap.add_argument("--out", default="gpurun_out/parity_r2.json")
+    args = ap.parse_args()
+    res = report(args.configs.split(","), args.instances, args.workers or None)
+    path = pathlib.Path(args.out)
+    path.parent.mkdir(parents=True, exist_ok=True)
+    path.write_text(json.dumps(res, indent=1))
+    print(path)
+
+
+if __name__ == "__main__":
+    main()

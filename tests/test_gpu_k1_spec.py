@@ -1,4 +1,4 @@
-"""The compile-time specialised builds of the headline loop kernel (ThreadLoop SPEC = 1..5,
+"""The compile-time specialised builds of the headline loop kernel (ThreadLoop SPEC = 1..2,
 csrc/pdeq_loop_thread.cuh) against the general kernel (SPEC = 0), which the oracle parity tests pin.
 
 The specialisation removes run-time branches and moves the accepted state; it does not change a single floating-
@@ -57,7 +57,7 @@ def test_specialised_builds_are_bitwise_the_general_kernel(cuda, spec_env, contr
     ref = _solve(B, control)
     assert int(np.abs(ref[-1]).max()) == 0
     assert int(ref[4].min()) > 10
-    for spec in (1, 2, 3, 4, 5):
+    for spec in (1, 2):
         os.environ["PDEQ_K1_SPEC"] = str(spec)
         got = _solve(B, control)
         for a, b in zip(got, ref):
@@ -71,7 +71,7 @@ def test_specialised_builds_emit_the_same_attempt_trace(cuda, spec_env):
     ref = _solve(B, "pi", trace_capacity=256, t1=10.0)
     n_att = ref[5]
     assert int(n_att.max()) <= 256
-    for spec in (1, 2, 3, 4, 5):
+    for spec in (1, 2):
         os.environ["PDEQ_K1_SPEC"] = str(spec)
         got = _solve(B, "pi", trace_capacity=256, t1=10.0)
         for a, b in zip(got[:-1], ref[:-1]):

@@ -50,8 +50,8 @@ def test_k1_spec_choice_follows_the_environment(monkeypatch):
     lib = _lib.load()
     monkeypatch.delenv("PDEQ_K1_SPEC", raising=False)
     default = lib.pdeq_k1_spec_choice()
-    assert 1 <= default <= 5
-    for spec in range(0, 6):
+    assert 1 <= default <= 2
+    for spec in range(0, 3):
         monkeypatch.setenv("PDEQ_K1_SPEC", str(spec))
         assert lib.pdeq_k1_spec_choice() == spec
     for bad in ("-1", "99"):
