@@ -8,6 +8,7 @@ GPU box with the repository snapshot.  No GPU is needed to build.
 from __future__ import annotations
 
 import concurrent.futures
+import hashlib
 import os
 import pathlib
 import shutil
@@ -38,15 +39,21 @@ def sources() -> list[pathlib.Path]:
     return sorted(CSRC.glob("*.cu")) + sorted((CSRC / "inst").glob("*.cu"))
 
 
-def _headers_mtime() -> float:
-    hdrs = list(CSRC.glob("*.cuh")) + [ROOT.parent / "include" / "probdiffeq_b200.h"]
-    return max(h.stat().st_mtime for h in hdrs)
+def _headers_digest() -> bytes:
+    hdrs = sorted(CSRC.glob("*.cuh")) + [ROOT.parent / "include" / "probdiffeq_b200.h"]
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in hdrs:
+        h.update(f.name.encode() + f.read_bytes())
+    return h.digest()
 
 
-def _compile(src: pathlib.Path, force: bool, verbose: bool) -> pathlib.Path:
+def _compile(src: pathlib.Path, force: bool, verbose: bool, hdr_digest: bytes) -> pathlib.Path:
+    """An object is reused only if the CONTENT of its source, of every header and the flags are what it was built
+    from (a stamp beside the object records their hash) -- not because its mtime is newer."""
     obj = OBJ / (src.stem + ".o")
-    newest = max(src.stat().st_mtime, _headers_mtime())
-    if not force and obj.exists() and obj.stat().st_mtime >= newest:
+    stamp = OBJ / (src.stem + ".sha256")
+    want = hashlib.sha256(hdr_digest + src.read_bytes()).hexdigest()
+    if not force and obj.exists() and stamp.exists() and stamp.read_text() == want:
         return obj
     cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
     if verbose:
@@ -56,6 +63,7 @@ def _compile(src: pathlib.Path, force: bool, verbose: bool) -> pathlib.Path:
         raise RuntimeError(f"nvcc failed for {src.name}:\n{res.stdout}\n{res.stderr}")
     if verbose:
         sys.stderr.write(res.stderr)
+    stamp.write_text(want)
     return obj
 
 
@@ -64,13 +72,17 @@ def build(force: bool = False, verbose: bool = False, jobs: int | None = None) -
     LIB.parent.mkdir(exist_ok=True)
     srcs = sources()
     jobs = jobs or min(len(srcs), os.cpu_count() or 4)
+    digest = _headers_digest()
     with concurrent.futures.ThreadPoolExecutor(max_workers=jobs) as pool:
-        objs = list(pool.map(lambda s: _compile(s, force, verbose), srcs))
-    if force or not LIB.exists() or any(o.stat().st_mtime > LIB.stat().st_mtime for o in objs):
+        objs = list(pool.map(lambda s: _compile(s, force, verbose, digest), srcs))
+    link_stamp = OBJ / "link.sha256"
+    link_want = hashlib.sha256("".join((OBJ / (s.stem + ".sha256")).read_text() for s in srcs).encode()).hexdigest()
+    if force or not LIB.exists() or not link_stamp.exists() or link_stamp.read_text() != link_want:
         cmd = [_nvcc(), "-shared", "-o", str(LIB), *map(str, objs), "-ldl"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+        link_stamp.write_text(link_want)
     return LIB
 
 

@@ -248,6 +248,8 @@ static int run_loop(const pdeq_config* cfg, const pdeq_problem* pr, const pdeq_s
   a.pool_slots = nullptr;
   a.pool_num_slots = 0;
   a.pool_seg_len = 0;
+  a.pool_dissolve = 0;
+  a.pool_patience_ns = 0;
   cudaError_t e = cudaMemsetAsync(ws, 0, 256, s);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
   const LoopEntry* entry = select_loop(cfg);

@@ -53,6 +53,16 @@ inline int k1_pool_seg_len() {
   const int c = e == nullptr ? 32 : std::atoi(e);
   return (c >= 1 && c <= 4096) ? c : 32;
 }
+inline int k1_pool_dissolve() {
+  const char* e = std::getenv("PDEQ_K1_DISSOLVE");
+  const int c = e == nullptr ? 20 : std::atoi(e);
+  return (c >= 0 && c <= 32) ? c : 20;
+}
+inline int k1_pool_patience_ns() {
+  const char* e = std::getenv("PDEQ_K1_PATIENCE_NS");
+  const int c = e == nullptr ? 30000 : std::atoi(e);
+  return c >= 0 ? c : 30000;
+}
 constexpr int K1_MAX_CTAS_PER_SM = 6;
 inline size_t k1_pool_ring_entries(long lanes) {
   size_t cap = 1024;
@@ -94,6 +104,8 @@ cudaError_t k1_launch_impl(const LoopArgs& a_in, void* workspace, size_t workspa
   a.pool_ring_mask = 0;
   a.pool_num_slots = 0;
   a.pool_seg_len = k1_pool_seg_len();
+  a.pool_dissolve = k1_pool_dissolve();
+  a.pool_patience_ns = k1_pool_patience_ns();
   if (k1_pool_enabled() && workspace != nullptr && workspace_bytes >= 256 + k1_pool_bytes(lanes, park)) {
     const size_t ring = k1_pool_ring_entries(lanes);
     a.pool_ring = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + 256);

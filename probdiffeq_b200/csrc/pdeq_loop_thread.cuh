@@ -38,15 +38,18 @@ struct LoopArgs {
   unsigned long long* work_counter;  // zero-initialised by the host wrapper
   // Tail compaction of the thread-per-instance kernel (K1, see ThreadLoop::run): once the queue of fresh instances
   // is empty, warps that are no longer full park their unfinished instances in a pool and re-form as full warps.
-  // ctl = work_counter: [0] fresh-instance counter, [1] pool head, [2] pool tail, [3] finished instances (all zeroed
-  // by the host wrapper). ring: zero-initialised tickets (slot + 1). slots: [field][num_slots] parked states.
-  // slots == nullptr switches the compaction off.
+  // ctl = work_counter: [0] fresh-instance counter, [POOL_HEAD] / [POOL_TAIL] of the ticket ring, [POOL_DONE]
+  // finished instances -- 64 bytes apart, all zeroed by the host wrapper. ring: zero-initialised tickets (slot + 1).
+  // slots: [field][num_slots] parked states. slots == nullptr switches the compaction off.
   unsigned int* pool_ring;
   unsigned int pool_ring_mask;
   double* pool_slots;
   int64_t pool_num_slots;
-  int32_t pool_seg_len;
+  int32_t pool_seg_len;      // loop iterations between two visits of a warp to the pool
+  int32_t pool_dissolve;     // a warp with fewer unfinished instances than this parks them all
+  int32_t pool_patience_ns;  // an empty warp takes a batch of < 32 only after it has been on offer this long
 };
+constexpr int POOL_HEAD = 8, POOL_TAIL = 16, POOL_DONE = 24;  // indices into the 256-byte header (unsigned long long)
 
 constexpr int K1_THREADS = 128;
 // Resident CTAs per SM the register allocation is sized for. Measured on the headline kernel (2^20 Lotka-Volterra
@@ -252,17 +255,18 @@ struct ThreadLoop {
     // ---- scheduling state ----
     // Phase 1 (fresh instances left): a lane that finishes its instance pulls the next index from the global counter.
     // Phase 2 (the counter ran past B for some lane of this warp): the FP64 pipe is what this kernel is bound by and a
-    // warp instruction costs the same with 1 or 32 active lanes, so warps must stay full. Every `pool_seg_len` loop
-    // iterations a warp that is no longer full parks its unfinished instances in a global pool (state written to a
-    // slot, slot id pushed on a ticket ring) and pops up to 32 parked instances back: warps re-form full or empty,
-    // empty warps poll until every instance is finished. Results do not depend on which lane runs an instance.
+    // warp instruction costs the same with 1 or 32 active lanes, so warps should stay full. Every `pool_seg_len` loop
+    // iterations a warp that is no longer full (1) tops its idle lanes up with instances parked in a global pool,
+    // (2) if it is sparse (fewer than `pool_dissolve` instances) parks its own there -- state written to a slot, slot
+    // id pushed on a ticket ring -- and (3) when empty waits for a full batch of 32 (or for a leftover batch nobody
+    // topped up with) until every instance is finished. Results do not depend on which lane runs an instance.
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = tid & 31;
-    unsigned long long* const ctl = a.work_counter;
+#define ctl (a.work_counter)
     const bool pooled = a.pool_slots != nullptr;
-    const long nslots = (long)a.pool_num_slots;
-    long slot = (long)blockIdx.x * blockDim.x + tid;  // parking slot; travels with the instance
-    bool have = false, drained = false;
+    const int nslots = (int)a.pool_num_slots;
+    int slot = blockIdx.x * blockDim.x + tid;  // parking slot; travels with the instance
+    bool have = false, drained = false, settled = false;
     int seg_left = 0;
 
     while (true) {
@@ -322,137 +326,162 @@ struct ThreadLoop {
       }
       if (drained) {
         if (seg_left <= 0) {
-          const unsigned hm = __ballot_sync(FULL, have);
+          unsigned hm = __ballot_sync(FULL, have);
           if (!pooled) {
             if (hm == 0u) break;  // no compaction: the warp leaves when its last lane is done
           } else if (hm != FULL) {
-            // ---- park this warp's unfinished instances ...
-            if (have) {
-              double* sl = a.pool_slots + slot;
-              int f = 0;
-#pragma unroll
-              for (int i = 0; i < n; ++i) {
-#pragma unroll
-                for (int j = 0; j < D; ++j) __stcg(sl + (long)(f++) * nslots, m[i][j]);
+            // ---- 1. top up: idle lanes take parked instances, as many as there are
+            bool done_all = false;
+            int waited_ns = 0, backoff_ns = 500;
+            while (true) {
+              const int k_have = __popc(hm);
+              int got = 0;
+              unsigned long long hbase = 0;
+              if (lane == 0) {
+                unsigned long long h = *(volatile unsigned long long*)(ctl + POOL_HEAD);
+                while (true) {
+                  const unsigned long long tl = *(volatile unsigned long long*)(ctl + POOL_TAIL);
+                  if (tl <= h) break;
+                  const unsigned long long avail = tl - h;
+                  // an EMPTY warp waits for a full batch: taking whatever shows up would spread the remaining
+                  // instances thinly over all the idle warps. A partial batch is taken once it has sat in the pool
+                  // for `patience` (nobody topped up with it): the end of the run.
+                  if (k_have == 0 && avail < 32ULL && waited_ns < a.pool_patience_ns) {
+                    waited_ns += backoff_ns;
+                    break;
+                  }
+                  const unsigned long long want = (unsigned long long)(32 - k_have);
+                  const unsigned long long g = avail < want ? avail : want;
+                  const unsigned long long old = atomicCAS(ctl + POOL_HEAD, h, h + g);
+                  if (old == h) {
+                    got = (int)g;
+                    hbase = h;
+                    break;
+                  }
+                  h = old;
+                }
+                if (got == 0 && k_have == 0 && *(volatile unsigned long long*)(ctl + POOL_TAIL) <= *(volatile unsigned long long*)(ctl + POOL_HEAD))
+                  waited_ns = 0;  // the pool is empty: patience starts when something appears
               }
-#pragma unroll
-              for (int k = 0; k < NB; ++k) {
+              got = __shfl_sync(FULL, got, 0);
+              hbase = __shfl_sync(FULL, hbase, 0);
+              const unsigned idle_rank = __popc(~hm & ((1u << lane) - 1u));
+              if (!have && (int)idle_rank < got) {
+                unsigned int* e = a.pool_ring + (unsigned)((hbase + idle_rank) & a.pool_ring_mask);
+                unsigned v;
+                while ((v = atomicExch(e, 0u)) == 0u) {
+                }
+                slot = (int)v - 1;
+                __threadfence();
+                const double* sl = a.pool_slots + slot;
+                int f = 0;
 #pragma unroll
                 for (int i = 0; i < n; ++i) {
 #pragma unroll
-                  for (int j = 0; j <= i; ++j) __stcg(sl + (long)(f++) * nslots, L[k][i][j]);
+                  for (int j = 0; j < D; ++j) m[i][j] = __ldcg(sl + (long)(f++) * nslots);
                 }
-              }
 #pragma unroll
-              for (int k = 0; k < NB; ++k) {
-                __stcg(sl + (long)(f++) * nslots, sig[k]);
-                __stcg(sl + (long)(f++) * nslots, run_scale[k]);
-              }
-              __stcg(sl + (long)(f++) * nslots, t);
-              __stcg(sl + (long)(f++) * nslots, dt);
-              __stcg(sl + (long)(f++) * nslots, ctrl_lprev);
-              __stcg(sl + (long)(f++) * nslots, ndata);
-              __stcg(sl + (long)(f++) * nslots, __longlong_as_double((long long)b));
-              __stcg(sl + (long)(f++) * nslots,
-                     __longlong_as_double(((long long)nsteps << 32) | (long long)(unsigned)nattempts));
-              __stcg(sl + (long)(f++) * nslots, __longlong_as_double(((long long)ck << 32) | (long long)(unsigned)status));
-              if (needs_interp) {
-                for (int e = 0; e < IF_SLOTS; ++e) __stcg(sl + (long)(f + e) * nslots, smem_if[e * nthreads + tid]);
-              }
-              __threadfence();
-            }
-            __syncwarp();
-            const int k_push = __popc(hm);
-            if (k_push > 0) {
-              unsigned long long base = 0;
-              if (lane == 0) base = atomicAdd(ctl + 2, (unsigned long long)k_push);
-              base = __shfl_sync(FULL, base, 0);
-              if (have) {
-                const unsigned r = __popc(hm & ((1u << lane) - 1u));
-                unsigned int* e = a.pool_ring + (unsigned)((base + r) & a.pool_ring_mask);
-                while (atomicCAS(e, 0u, (unsigned)slot + 1u) != 0u) {
+                for (int k = 0; k < NB; ++k) {
+#pragma unroll
+                  for (int i = 0; i < n; ++i) {
+#pragma unroll
+                    for (int j = 0; j <= i; ++j) L[k][i][j] = __ldcg(sl + (long)(f++) * nslots);
+                  }
                 }
-              }
-            }
-            have = false;
-            // ---- ... and pop up to 32 parked instances
-            int got = 0;
-            unsigned long long hbase = 0;
-            if (lane == 0) {
-              unsigned long long h = *(volatile unsigned long long*)(ctl + 1);
-              while (true) {
-                const unsigned long long tl = *(volatile unsigned long long*)(ctl + 2);
-                if (tl <= h) break;
-                const unsigned long long g = (tl - h) < 32ULL ? (tl - h) : 32ULL;
-                const unsigned long long old = atomicCAS(ctl + 1, h, h + g);
-                if (old == h) {
-                  got = (int)g;
-                  hbase = h;
-                  break;
+#pragma unroll
+                for (int k = 0; k < NB; ++k) {
+                  sig[k] = __ldcg(sl + (long)(f++) * nslots);
+                  run_scale[k] = __ldcg(sl + (long)(f++) * nslots);
                 }
-                h = old;
-              }
-            }
-            got = __shfl_sync(FULL, got, 0);
-            hbase = __shfl_sync(FULL, hbase, 0);
-            if (lane < got) {
-              unsigned int* e = a.pool_ring + (unsigned)((hbase + (unsigned)lane) & a.pool_ring_mask);
-              unsigned v;
-              while ((v = atomicExch(e, 0u)) == 0u) {
-              }
-              slot = (long)v - 1;
-              __threadfence();
-              const double* sl = a.pool_slots + slot;
-              int f = 0;
-#pragma unroll
-              for (int i = 0; i < n; ++i) {
-#pragma unroll
-                for (int j = 0; j < D; ++j) m[i][j] = __ldcg(sl + (long)(f++) * nslots);
-              }
-#pragma unroll
-              for (int k = 0; k < NB; ++k) {
-#pragma unroll
-                for (int i = 0; i < n; ++i) {
-#pragma unroll
-                  for (int j = 0; j <= i; ++j) L[k][i][j] = __ldcg(sl + (long)(f++) * nslots);
+                t = __ldcg(sl + (long)(f++) * nslots);
+                dt = __ldcg(sl + (long)(f++) * nslots);
+                ctrl_lprev = __ldcg(sl + (long)(f++) * nslots);
+                ndata = __ldcg(sl + (long)(f++) * nslots);
+                b = (long)__double_as_longlong(__ldcg(sl + (long)(f++) * nslots));
+                const long long w1 = __double_as_longlong(__ldcg(sl + (long)(f++) * nslots));
+                const long long w2 = __double_as_longlong(__ldcg(sl + (long)(f++) * nslots));
+                nsteps = (int)(w1 >> 32);
+                nattempts = (int)(unsigned)(w1 & 0xffffffffLL);
+                ck = (int)(w2 >> 32);
+                status = (int)(unsigned)(w2 & 0xffffffffLL);
+                if (needs_interp) {
+                  for (int e2 = 0; e2 < IF_SLOTS; ++e2) smem_if[e2 * nthreads + tid] = __ldcg(sl + (long)(f + e2) * nslots);
                 }
-              }
 #pragma unroll
-              for (int k = 0; k < NB; ++k) {
-                sig[k] = __ldcg(sl + (long)(f++) * nslots);
-                run_scale[k] = __ldcg(sl + (long)(f++) * nslots);
-              }
-              t = __ldcg(sl + (long)(f++) * nslots);
-              dt = __ldcg(sl + (long)(f++) * nslots);
-              ctrl_lprev = __ldcg(sl + (long)(f++) * nslots);
-              ndata = __ldcg(sl + (long)(f++) * nslots);
-              b = (long)__double_as_longlong(__ldcg(sl + (long)(f++) * nslots));
-              const long long w1 = __double_as_longlong(__ldcg(sl + (long)(f++) * nslots));
-              const long long w2 = __double_as_longlong(__ldcg(sl + (long)(f++) * nslots));
-              nsteps = (int)(w1 >> 32);
-              nattempts = (int)(unsigned)(w1 & 0xffffffffLL);
-              ck = (int)(w2 >> 32);
-              status = (int)(unsigned)(w2 & 0xffffffffLL);
-              if (needs_interp) {
-                for (int e = 0; e < IF_SLOTS; ++e) smem_if[e * nthreads + tid] = __ldcg(sl + (long)(f + e) * nslots);
-              }
+                for (int k = 0; k < NB; ++k)
+                  prior[k] = (!SP && a.prob.prior_scale != nullptr) ? a.prob.prior_scale[b * a.prob.prior_scale_stride + k] : 1.0;
 #pragma unroll
-              for (int k = 0; k < NB; ++k)
-                prior[k] = (!SP && a.prob.prior_scale != nullptr) ? a.prob.prior_scale[b * a.prob.prior_scale_stride + k] : 1.0;
+                for (int k = 0; k < P; ++k)
+                  params[k] = (VF::num_params > 0) ? a.prob.params[b * a.prob.params_stride + k] : 0.0;
+                t_next = (ck < T) ? a.grid[ck] : t;
+                have = true;
+              }
+              hm = __ballot_sync(FULL, have);
+              const int k_now = __popc(hm);
+              if (k_have == 0 && k_now > 0 && k_now < 32) settled = true;  // took a leftover batch: keep it
+              // ---- 2. a sparse warp gives its instances away (they top up fuller warps) and goes idle
+              if (k_now > 0 && k_now < a.pool_dissolve && !settled) {
+                if (have) {
+                  double* sl = a.pool_slots + slot;
+                  int f = 0;
 #pragma unroll
-              for (int k = 0; k < P; ++k)
-                params[k] = (VF::num_params > 0) ? a.prob.params[b * a.prob.params_stride + k] : 0.0;
-              t_next = (ck < T) ? a.grid[ck] : t;
-              have = true;
-            }
-            if (got == 0) {
+                  for (int i = 0; i < n; ++i) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) __stcg(sl + (long)(f++) * nslots, m[i][j]);
+                  }
+#pragma unroll
+                  for (int k = 0; k < NB; ++k) {
+#pragma unroll
+                    for (int i = 0; i < n; ++i) {
+#pragma unroll
+                      for (int j = 0; j <= i; ++j) __stcg(sl + (long)(f++) * nslots, L[k][i][j]);
+                    }
+                  }
+#pragma unroll
+                  for (int k = 0; k < NB; ++k) {
+                    __stcg(sl + (long)(f++) * nslots, sig[k]);
+                    __stcg(sl + (long)(f++) * nslots, run_scale[k]);
+                  }
+                  __stcg(sl + (long)(f++) * nslots, t);
+                  __stcg(sl + (long)(f++) * nslots, dt);
+                  __stcg(sl + (long)(f++) * nslots, ctrl_lprev);
+                  __stcg(sl + (long)(f++) * nslots, ndata);
+                  __stcg(sl + (long)(f++) * nslots, __longlong_as_double((long long)b));
+                  __stcg(sl + (long)(f++) * nslots,
+                         __longlong_as_double(((long long)nsteps << 32) | (long long)(unsigned)nattempts));
+                  __stcg(sl + (long)(f++) * nslots, __longlong_as_double(((long long)ck << 32) | (long long)(unsigned)status));
+                  if (needs_interp) {
+                    for (int e2 = 0; e2 < IF_SLOTS; ++e2) __stcg(sl + (long)(f + e2) * nslots, smem_if[e2 * nthreads + tid]);
+                  }
+                  __threadfence();
+                }
+                __syncwarp();
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(ctl + POOL_TAIL, (unsigned long long)k_now);
+                base = __shfl_sync(FULL, base, 0);
+                if (have) {
+                  const unsigned r = __popc(hm & ((1u << lane) - 1u));
+                  unsigned int* e = a.pool_ring + (unsigned)((base + r) & a.pool_ring_mask);
+                  while (atomicCAS(e, 0u, (unsigned)slot + 1u) != 0u) {
+                  }
+                }
+                have = false;
+                hm = 0u;
+              }
+              if (hm != 0u) break;  // there is work: run a segment
+              // ---- 3. nothing to do: finished, or wait for parked instances
               unsigned long long fin = 0;
-              if (lane == 0) fin = *(volatile unsigned long long*)(ctl + 3);
+              if (lane == 0) fin = *(volatile unsigned long long*)(ctl + POOL_DONE);
               fin = __shfl_sync(FULL, fin, 0);
-              if (fin >= (unsigned long long)B) break;  // every instance of the ensemble is finished
-              __nanosleep(400);
-              continue;  // poll again
+              if (fin >= (unsigned long long)B) {
+                done_all = true;
+                break;
+              }
+              __nanosleep(backoff_ns);
+              backoff_ns = backoff_ns < 8000 ? 2 * backoff_ns : backoff_ns;
+              waited_ns = __shfl_sync(FULL, waited_ns, 0);
             }
+            if (done_all) break;  // every instance of the ensemble is finished
           }
           seg_left = a.pool_seg_len;
         }
@@ -528,7 +557,7 @@ struct ThreadLoop {
           a.sol.status[b] = status;
           if (a.sol.num_attempts != nullptr) a.sol.num_attempts[b] = nattempts;
           have = false;
-          if (pooled) atomicAdd(ctl + 3, 1ULL);
+          if (pooled) atomicAdd(ctl + POOL_DONE, 1ULL);
         }
         continue;
       }
@@ -820,6 +849,8 @@ struct ThreadLoop {
     }
   }
 };
+
+#undef ctl
 
 template <class VF, int NU, int FACT, int D, bool TS0, int SPEC = 0>
 __global__ void __launch_bounds__(K1_THREADS, SPEC != 0 ? PDEQ_K1_SPEC_MIN_BLOCKS(SPEC) : PDEQ_K1_MIN_BLOCKS(FACT)) k1_loop_kernel(const __grid_constant__ LoopArgs a) {

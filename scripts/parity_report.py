@@ -208,15 +208,21 @@ def compare(cfg, prod, ora, pool):
              for lvl in rows[0]["kernel_vs_oracle"]["dt_rel_diff_first_exceeds"]}
     amp_o = {lvl: _median([r["oracle_vs_perturbed_oracle"]["dt_rel_diff_first_exceeds"][lvl] for r in rows])
              for lvl in amp_k}
-    # divergences NOT explained by the oracle's own conditioning: the kernel parts from the oracle although the
-    # perturbed oracle keeps its sequence for that instance, or parts much earlier than the perturbed oracle does
-    unexplained = []
-    for r in div:
-        fk = r["kernel_vs_oracle"]["first_differing_attempt"]
-        fo = r["oracle_vs_perturbed_oracle"]["first_differing_attempt"]
-        if fo is None or fk < 0.5 * fo:
-            unexplained.append(dict(instance=r["instance"], kernel=fk, oracle_self=fo,
-                                    dist_to_threshold=r["kernel_vs_oracle"].get("dist_to_threshold")))
+    # Population-level control. Where the step-size feedback is chaotic (configs 3, 4a, 4b) WHICH instances keep their
+    # sequence is a lottery for any second implementation, so the kernel is held to the perturbed oracle's statistics:
+    # an instance counts as diverging EARLY if the kernel parts from the oracle before half the attempt index at which
+    # the 5 % most sensitive instances of the perturbed oracle part from it.
+    def _pos(r, key):
+        f = r[key]["first_differing_attempt"]
+        return float(r["attempts_oracle"]) if f is None else float(f)
+
+    self_pos = np.asarray([_pos(r, "oracle_vs_perturbed_oracle") for r in rows])
+    kern_pos = np.asarray([_pos(r, "kernel_vs_oracle") for r in rows])
+    early_bar = 0.5 * float(np.quantile(self_pos, 0.05))
+    unexplained = [dict(instance=r["instance"], kernel=r["kernel_vs_oracle"]["first_differing_attempt"],
+                        oracle_self=r["oracle_vs_perturbed_oracle"]["first_differing_attempt"],
+                        dist_to_threshold=r["kernel_vs_oracle"].get("dist_to_threshold"))
+                   for r in div if r["kernel_vs_oracle"]["first_differing_attempt"] < early_bar]
     return dict(
         instances=B,
         failed_instances=int((prod["status"] != 0).sum()),
@@ -246,6 +252,12 @@ def compare(cfg, prod, ora, pool):
             max_ratio_to_oracle_sensitivity_divergent=max(
                 (r["rel_terminal_coeff0"] / max(r["oracle_vs_perturbed_oracle"]["terminal_sensitivity"], 1e-16) for r in div),
                 default=None)),
+        sequence_kept_up_to=dict(
+            what="attempt index of the first differing accept/reject decision (instances that never differ count with "
+                 "their number of attempts): quantiles over the sample, kernel vs oracle beside perturbed oracle vs oracle",
+            kernel_vs_oracle={q: float(np.quantile(kern_pos, float(q))) for q in ("0.05", "0.25", "0.5")},
+            oracle_vs_perturbed_oracle={q: float(np.quantile(self_pos, float(q))) for q in ("0.05", "0.25", "0.5")},
+            early_bar=early_bar),
         divergences_not_explained_by_oracle_conditioning=unexplained,
         per_instance=rows,
     )  # fmt: skip
@@ -270,7 +282,10 @@ def lockstep(cfg, prod, ora, pool, instances=8):
 
     import pdeq_test_helpers as H
 
-    s = dict(cfg["spec"], strategy="filter")
+    # the plain `solver` (no calibration): with solver_dynamic the output scale of a step is a whitened residual that is
+    # pure cancellation noise wherever the extrapolation is nearly exact (first steps, equilibria), which would blur
+    # the comparison exactly like the step-size feedback does
+    s = dict(cfg["spec"], strategy="filter", solver="solver")
     rows, jobs, grids = [], [], []
     pick = list(range(min(instances, prod["tcoeffs"].shape[0])))
     for b in pick:
@@ -294,10 +309,15 @@ def lockstep(cfg, prod, ora, pool, instances=8):
         rel_m = np.max(np.abs(got_m - ref_m).reshape(len(grid), -1), axis=1) / np.max(np.abs(ref_m).reshape(len(grid), -1), axis=1)
         den = np.maximum(np.max(np.abs(cov_ref).reshape(len(grid), -1), axis=1), 1e-300)
         rel_c = np.max(np.abs(cov - cov_ref.reshape(cov.shape)).reshape(len(grid), -1), axis=1) / den
+        g0, r0 = got_m[:, 0].reshape(len(grid), -1), ref_m[:, 0].reshape(len(grid), -1)
+        rel_0 = np.max(np.abs(g0 - r0), axis=1) / np.max(np.abs(r0), axis=1)
         rows.append(dict(instance=b, grid_points=int(len(grid)), max_rel_mean=float(rel_m.max()),
-                         max_rel_cov=float(rel_c[1:].max()), rel_mean_terminal=float(rel_m[-1])))  # fmt: skip
-    return dict(what=lockstep.__doc__.split("\n\n")[0], instances=rows,
-                max_rel_mean=max(r["max_rel_mean"] for r in rows), max_rel_cov=max(r["max_rel_cov"] for r in rows))
+                         max_rel_mean_coeff0=float(rel_0.max()), max_rel_cov=float(rel_c[1:].max()),
+                         rel_mean_coeff0_terminal=float(rel_0[-1]), status=int(sol.status[0])))  # fmt: skip
+    return dict(what=" ".join(lockstep.__doc__.split()), solver="solver (uncalibrated), filter", instances=rows,
+                max_rel_mean=max(r["max_rel_mean"] for r in rows),
+                max_rel_mean_coeff0=max(r["max_rel_mean_coeff0"] for r in rows),
+                max_rel_cov=max(r["max_rel_cov"] for r in rows))
 
 
 def report(names, B, workers=None, lockstep_instances=8, keep_rows=True):
@@ -325,7 +345,7 @@ def report(names, B, workers=None, lockstep_instances=8, keep_rows=True):
                   f"{o['identical_sequence']}/{B}; median first divergence {k['median_first_differing_attempt']} vs "
                   f"{o['median_first_differing_attempt']}; max rel terminal (identical) {res['terminal_coeff0']['max_rel_identical']}; "
                   f"unexplained {len(res['divergences_not_explained_by_oracle_conditioning'])}; "
-                  f"lockstep {res.get('lockstep_fixed_grid', {}).get('max_rel_mean')} / "
+                  f"lockstep {res.get('lockstep_fixed_grid', {}).get('max_rel_mean_coeff0')} / "
                   f"{res.get('lockstep_fixed_grid', {}).get('max_rel_cov')}; {time.time() - t0:.0f} s", flush=True)  # fmt: skip
     return out
 

@@ -1,0 +1,67 @@
+"""BASELINE configs 2, 3, 4a, 4b at their FULL horizons (t1 = 50, 33 checkpoints to t = 3, t1 = 321.8122, t1 = 6.3): the
+kernel's attempt trace against the oracle's over the whole solve, with the first-divergence (tie-flip) diagnostic of
+SURVEY.md App. C.7 (scripts/parity_report.py; the committed full-sample run is profiles/parity_r2.json).
+
+What can be asserted depends on the conditioning of the reference algorithm itself, which the report measures beside
+every number by running the oracle against itself with dt0 moved by +-4 ulp:
+
+* config 2 is well conditioned: every instance must reproduce the oracle's accept/reject sequence attempt by attempt
+  and its terminal values to 1e-8 (north_star's tolerance);
+* configs 3, 4a, 4b have a chaotic step-size feedback (the perturbed oracle loses its OWN sequence for most instances):
+  there the kernel must keep the oracle's sequence as long as the perturbed oracle does (quantiles of the first
+  differing attempt), no instance may part early, sequence-identical instances must agree to 1e-8, and the others
+  must stay within the spread the perturbed oracle shows;
+* the lock-step check (fixed grid = the oracle's accepted grid of the full solve, uncalibrated filter) compares the
+  per-step arithmetic of the whole horizon without the step-size feedback.
+"""
+
+import sys
+
+import pytest
+
+sys.path.insert(0, "scripts")
+
+pytestmark = pytest.mark.gpu
+
+B = 48
+TOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def report(cuda):
+    import parity_report as pr
+
+    return pr.report(["2", "3", "4a", "4b"], B, lockstep_instances=3)
+
+
+def test_config2_identical_sequences_and_terminal_values(report):
+    res = report["config_2"]
+    assert res["failed_instances"] == 0
+    assert res["kernel_vs_oracle"]["identical_sequence"] == B, res["kernel_vs_oracle"]
+    assert res["attempts_total_kernel"] == res["attempts_total_oracle"]
+    assert res["terminal_coeff0"]["max_rel_identical"] <= TOL
+    assert res["lockstep_fixed_grid"]["max_rel_mean"] <= 1e-9
+    assert res["lockstep_fixed_grid"]["max_rel_cov"] <= 1e-10
+
+
+@pytest.mark.parametrize("name", ["3", "4a", "4b"])
+def test_chaotic_configs_track_the_oracle_as_long_as_the_oracle_tracks_itself(report, name):
+    res = report["config_" + name]
+    assert res["failed_instances"] == 0
+    k, o = res["sequence_kept_up_to"]["kernel_vs_oracle"], res["sequence_kept_up_to"]["oracle_vs_perturbed_oracle"]
+    # the kernel keeps the oracle's sequence (at least) 0.7 x as long as the oracle keeps its own under +-4 ulp
+    for q in ("0.05", "0.25", "0.5"):
+        assert k[q] >= 0.7 * o[q], (q, k, o)
+    assert res["divergences_not_explained_by_oracle_conditioning"] == []
+    t = res["terminal_coeff0"]
+    # sequence-identical instances: north_star's tolerance
+    if t["max_rel_identical"] is not None:
+        assert t["max_rel_identical"] <= TOL, t
+    # diverged instances: both are solutions of the same IVP at the requested tolerance, as far apart as the perturbed
+    # oracle is from the oracle
+    spread = res["oracle_vs_perturbed_oracle"]["max_terminal_sensitivity"]
+    if t["max_rel_divergent"] is not None:
+        assert t["max_rel_divergent"] <= max(TOL, 20.0 * spread), (t, spread)
+    # attempts in total: within the perturbed oracle's own variation
+    assert abs(res["attempts_total_kernel"] - res["attempts_total_oracle"]) <= 0.02 * res["attempts_total_oracle"]
+    assert res["lockstep_fixed_grid"]["max_rel_mean_coeff0"] <= 1e-6
