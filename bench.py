@@ -53,6 +53,7 @@ BASE_LV = np.asarray([0.5, 0.05, 0.5, 0.05])
 CPU_SAMPLE = 1 << 19  # cpu_baseline: ~10-30 s of host work
 REF_SAMPLE = 1 << 17  # --impl reference: instances per step
 PERM_SEED = 0
+PILOT = 4096  # instances of the pilot solve the scheduling cost model is fitted on (set-up)
 
 # Instruction mix of the headline kernel per attempted step, from the committed ncu capture named below
 # (profile-derived constants, NOT measured in this run): executed FP64 FLOPs = 2 DFMA + DMUL + DADD.
@@ -504,7 +505,27 @@ def run_ours(args) -> None:
         prior_d = ssm.prior_wiener_integrated(tcoeffs_d)
         solve_d = build_solver(vf_d)
 
+        # Scheduling hint (set-up, untimed): a quadratic model of the attempt count in (params, u0), fitted on a pilot
+        # solve of the shard's first PILOT instances. Inside every timed step the model is EVALUATED for the whole
+        # shard and the instances are sorted by it (longest first) -- that work is part of the step.
+        model = None
+        if not args.no_cost_hint:
+            M = min(PILOT, Bs)
+            vf_p = probdiffeq.ode("lotka_volterra", params=params_d[:M])
+            tc_p, _ = jetexpand(vf_p, (u0_d[:M],), t=T0)
+            pilot = build_solver(vf_p)(ssm.prior_wiener_integrated(tc_p), t0=T0, t1=T1, atol=ATOL, rtol=RTOL,
+                                       want_cholesky=False)
+            model = sharding.QuadraticCostModel.fit(
+                np.concatenate([params_np[:M], u0_np[:M]], axis=1), pilot.num_attempts.cpu().numpy().astype(np.float64))
+            del pilot
+
+        def hint_for(p, u):
+            return None if model is None else model.predict(torch.cat([p, u], dim=1))
+
         def step_resident():
+            return solve_d(prior_d, t0=T0, t1=T1, atol=ATOL, rtol=RTOL, cost_hint=hint_for(params_d, u0_d))
+
+        def step_plain():
             return solve_d(prior_d, t0=T0, t1=T1, atol=ATOL, rtol=RTOL)
 
         def step_e2e(slot: int = 0):
@@ -513,14 +534,15 @@ def run_ours(args) -> None:
             vf = probdiffeq.ode("lotka_volterra", params=p)
             tc, _ = jetexpand(vf, (u,), t=T0)
             prior = ssm.prior_wiener_integrated(tc)
-            sol = build_solver(vf)(prior, t0=T0, t1=T1, atol=ATOL, rtol=RTOL, want_cholesky=False)
+            sol = build_solver(vf)(prior, t0=T0, t1=T1, atol=ATOL, rtol=RTOL, want_cholesky=False,
+                                   cost_hint=hint_for(p, u))
             mean_hs[slot].copy_(sol.u.mean[0], non_blocking=True)
             steps_hs[slot].copy_(sol.num_steps, non_blocking=True)
             return sol
 
         h2d = int(params_h.numel() * 8 + u0_h.numel() * 8)
         d2h = int(mean_hs[0].numel() * 8 + steps_hs[0].numel() * 4)
-        return step_resident, step_e2e, steps_hs, h2d, d2h
+        return step_resident, step_e2e, steps_hs, h2d, d2h, step_plain
 
     params_all, u0_all = lv_ensemble(B_total, seed=0)
     if world > 1:
@@ -528,7 +550,7 @@ def run_ours(args) -> None:
     else:
         params_np, u0_np = params_all, u0_all
     B = params_np.shape[0]
-    step_resident, step_e2e, steps_hs, h2d_bytes, d2h_bytes = lv_arms(params_np, u0_np)
+    step_resident, step_e2e, steps_hs, h2d_bytes, d2h_bytes, step_plain = lv_arms(params_np, u0_np)
 
     # Untimed spin-up on top of the W warm-up steps: a fresh process finds the GPU at idle clocks, and W = 3 passes
     # can end before the clocks have ramped -- a whole run then reads ~30 % slow. Keep the device busy for at least
@@ -549,14 +571,19 @@ def run_ours(args) -> None:
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_res, sol = timed(step_resident, args.steps, args.warmup, "resident")
-    launches += args.steps * 1
+    k1_launches = 1  # one persistent loop kernel per solve (the cost model and the sort are torch kernels)
+    launches += args.steps * k1_launches
+    ms_plain = None
+    if not args.no_cost_hint:
+        ms_plain, _ = timed(step_plain, args.steps, args.warmup, "resident_no_hint")
+        launches += args.steps * k1_launches
     steps_pass = int(sol.num_steps.sum().item())
     attempts_pass = int(sol.num_attempts.sum().item())
     bad = int((sol.status != 0).sum().item())
     ms_e2e_serial, _ = timed(step_e2e, args.steps, max(args.warmup, 1), "e2e_serial")
     e2e_steps_pass = int(steps_hs[0].to(torch.int64).sum().item())
     ms_e2e = timed_pipelined(step_e2e, args.steps, max(args.warmup, 1))
-    launches += 2 * args.steps * (1 + NU)
+    launches += 2 * args.steps * (k1_launches + NU)
     clocks = sampler.stop()
     assert int(steps_hs[1].to(torch.int64).sum().item()) == e2e_steps_pass == int(steps_hs[0].to(torch.int64).sum().item())
     del sol
@@ -568,15 +595,17 @@ def run_ours(args) -> None:
 
     ms_rank = ms_res
     ms_res, ms_e2e, ms_e2e_serial = reduce_max(ms_res, ms_e2e, ms_e2e_serial)
+    if ms_plain is not None:
+        (ms_plain,) = reduce_max(ms_plain)
     steps_all, attempts_all, e2e_steps_all, bad = reduce_sum(steps_pass, attempts_pass, e2e_steps_pass, bad)
 
     # ---- the weak-scaling number of round 1 (N > 1 only): every rank its own 2^20-instance ensemble, seed = rank
     weak = None
     if world > 1 and not args.no_weak:
         wp, wu = lv_ensemble(B_total, seed=rank)
-        w_resident, _w_e2e, _sh, _a, _b = lv_arms(wp, wu)
+        w_resident, _w_e2e, _sh, _a, _b, _w_plain = lv_arms(wp, wu)
         ms_w, wsol = timed(w_resident, max(2, args.steps // 2), 2, "weak")
-        launches += max(2, args.steps // 2)
+        launches += max(2, args.steps // 2) * k1_launches
         (ms_w,) = reduce_max(ms_w)
         (w_steps,) = reduce_sum(int(wsol.num_steps.sum().item()))
         weak = {"value": w_steps / (ms_w * 1e-3), "unit": UNIT, "ms_per_step": ms_w,
@@ -701,8 +730,15 @@ def run_ours(args) -> None:
             "accepted_steps_per_pass": steps_all, "attempts_per_pass": attempts_all,
             "rejection_ratio": 1.0 - steps_all / max(attempts_all, 1), "failed_instances": bad,
             "attempts_per_s": attempts_all / kernel_s,
-            "tail_compaction": {"enabled": os.environ.get("PDEQ_K1_POOL", "1") != "0",
-                                "segment": int(os.environ.get("PDEQ_K1_SEG", "32"))},
+            "schedule": {
+                "cost_hint": not args.no_cost_hint,
+                "what": "every timed step evaluates a quadratic cost model of (params, u0) for its shard and serves the "
+                        "instances longest-predicted-first (solve(..., cost_hint=) -> pdeq_problem.order). The model was "
+                        "fitted in set-up (untimed) on a pilot solve of the shard's first %d instances" % PILOT,
+                "no_hint": None if ms_plain is None else {
+                    "value": steps_all / (ms_plain * 1e-3), "ms_per_step": ms_plain,
+                    "what": "the same solve in index order on the full grid (round 1's schedule)"},
+            },
             "e2e": {
                 "value": e2e_steps_all / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes * world if world > 1 else h2d_bytes,
@@ -716,8 +752,8 @@ def run_ours(args) -> None:
             },
             "gpu_launches": launches,
             "gpu_launches_note": "kernels of this library issued inside timed regions on rank 0: 1 loop kernel per "
-                                 "resident step; 1 loop + 4 Taylor-pass kernels per e2e step (two e2e arms); per "
-                                 "config pass: Taylor passes + dt0 + loop (+ lml)",
+                                 "resident step (both schedules); 1 loop + 4 Taylor-pass kernels per e2e step (two e2e "
+                                 "arms); per config pass: Taylor passes + dt0 + loop (+ lml)",
             "roofline": {
                 "bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
                 "frac": achieved_tflops / fp64_peak_tflops, "per": "GPU",
@@ -769,6 +805,7 @@ def main() -> None:
     ap.add_argument("--instances", type=int, default=B_DEFAULT, help="instances of the WHOLE ensemble (split over the GPUs)")
     ap.add_argument("--cpu-sample", type=int, default=None, help="instances in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cost-hint", action="store_true", help="index order on the full grid (no scheduling hint)")
     ap.add_argument("--no-weak", action="store_true", help="skip the extra weak-scaling pass for N > 1")
     ap.add_argument("--configs", default="3,4a,4b,5", help="other BASELINE configs to time ('' = none)")
     ap.add_argument("--config-steps", type=int, default=2, help="timed passes per other config")

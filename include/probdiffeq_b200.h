@@ -84,6 +84,12 @@ typedef struct pdeq_config {
   int32_t re_linearize_after_calibration;    /* solver_dynamic    solvers.py:496 */
   int32_t correct_asymptotic_underconfidence; /* solver_mle        solvers.py:332 */
   int32_t max_attempts;    /* guard the reference lacks; <=0 means 2^31-1 */
+  /* solver(..., constraint_init=constraint) (solvers.py:361-372, 526-537, 670-680): one Bayes update with the
+     constraint at t0 before the first step, its gain through a minimum-norm least-squares solve (a zero pivot of the
+     observed factor gives a zero gain component, which is what linalg.lstsq_svd returns for the diagonal / scalar
+     factors of the isotropic and block-diagonal models and for a dense factor whose zero pivots are decoupled). */
+  int32_t constraint_init;
+  int32_t reserved0;       /* keeps the doubles 8-byte aligned; must be 0 */
   double safety, factor_min, factor_max;            /* controllers.py:30-33 */
   double exponent_integral, exponent_proportional;  /* controllers.py:34-35 */
   /* IWP system matrices, computed by the host exactly like the reference does
@@ -112,6 +118,12 @@ typedef struct pdeq_problem {
   int64_t prior_scale_stride;
   const double* params;         /* [.][pdeq_vf_num_params(vf_id)] */
   int64_t params_stride;
+  /* Optional (NULL = index order): a permutation of 0..B-1 in which the persistent kernels hand instances to their
+     lanes / warps / CTAs. Listing expensive instances first (longest processing time first) shortens the end of a
+     solve that has only a few instances per lane, and lanes of a warp that run equally long instances finish (and
+     refill) together instead of one by one. Results do not depend on it. (The reference has no counterpart: under
+     jax.vmap every lane runs as long as the slowest instance, probdiffeq/backend/func.py:9-10.) */
+  const int32_t* order;
 } pdeq_problem;
 
 /* Outputs of the loop entry points (T checkpoints per instance). Optional pointers may be NULL. */

@@ -378,9 +378,21 @@ class ProbabilisticSolution:
 class _ProbabilisticSolver:
     """_probdiffeq/solvers.py:72-315."""
 
-    def __init__(self, *, strategy, constraint):
+    def __init__(self, *, strategy, constraint, constraint_init=None):
         self.strategy = strategy
         self.constraint = constraint
+        self.constraint_init = constraint_init
+
+    def _init_update(self, u_pred, prediction, *, t, damp):
+        """The optional Bayes update at t0 (solvers.py:361-372, 526-537, 670-680): linearise `constraint_init` at the
+        initial state and condition on a zero residual, the gain through the minimum-norm least-squares solve
+        (`linalg.lstsq_svd`) because the initial observation factor may be singular (exact Taylor coefficients)."""
+        if self.constraint_init is None:
+            return u_pred, prediction
+        fx_init, _ = self.constraint_init.linearize(u_pred, self.constraint_init.init_linearization(), damp=damp, t=t)
+        _, reverted = fx_init.revert(u_pred, solve=linalg.lstsq_triu)
+        updates = reverted.apply_flat(np.zeros_like(fx_init.noise.mean))
+        return self.strategy.apply_updates(prediction, updates=updates)
 
     @property
     def is_suitable_for_save_at(self):
@@ -462,10 +474,11 @@ class solver(_ProbabilisticSolver):
     def init(self, t, u, *, damp):
         prior = u
         u_pred, prediction = self.strategy.init_posterior(u=prior.init)
+        u0, posterior = self._init_update(u_pred, prediction, t=t, damp=damp)
         fx = self._zeros_like_fx(u_pred, t, damp)
         output_scale = np.ones_like(prior.alg.prototype_output_scale(u_pred))
         return ProbabilisticSolution(
-            t=t, u=u_pred, solution_full=prediction, num_steps=0, auxiliary=None,
+            t=t, u=u0, solution_full=posterior, num_steps=0, auxiliary=None,
             output_scale=output_scale, fun_evals=fx, prior=prior,
         )  # fmt: skip
 
@@ -496,18 +509,19 @@ class solver(_ProbabilisticSolver):
 class solver_mle(_ProbabilisticSolver):
     """Maximum-likelihood (running RMS) calibration. solvers.py:318-480."""
 
-    def __init__(self, *, strategy, constraint, correct_asymptotic_underconfidence=True):
-        super().__init__(strategy=strategy, constraint=constraint)
+    def __init__(self, *, strategy, constraint, constraint_init=None, correct_asymptotic_underconfidence=True):
+        super().__init__(strategy=strategy, constraint=constraint, constraint_init=constraint_init)
         self.correct_asymptotic_underconfidence = correct_asymptotic_underconfidence
 
     def init(self, t, u, *, damp):
         prior = u
         u_pred, prediction = self.strategy.init_posterior(u=prior.init)
+        u0, posterior = self._init_update(u_pred, prediction, t=t, damp=damp)
         output_scale_prior = np.ones_like(prior.alg.prototype_output_scale(u_pred))
         fx = self._zeros_like_fx(u_pred, t, damp)
         auxiliary = (None, np.zeros_like(output_scale_prior), 0.0)
         return ProbabilisticSolution(
-            t=t, u=u_pred, solution_full=prediction, auxiliary=auxiliary,
+            t=t, u=u0, solution_full=posterior, auxiliary=auxiliary,
             output_scale=output_scale_prior, num_steps=0, fun_evals=fx, prior=prior,
         )  # fmt: skip
 
@@ -545,17 +559,18 @@ class solver_mle(_ProbabilisticSolver):
 class solver_dynamic(_ProbabilisticSolver):
     """Per-step (dynamic) calibration. solvers.py:483-633."""
 
-    def __init__(self, *, strategy, constraint, re_linearize_after_calibration=False):
-        super().__init__(strategy=strategy, constraint=constraint)
+    def __init__(self, *, strategy, constraint, constraint_init=None, re_linearize_after_calibration=False):
+        super().__init__(strategy=strategy, constraint=constraint, constraint_init=constraint_init)
         self.re_linearize_after_calibration = re_linearize_after_calibration
 
     def init(self, t, u, *, damp):
         prior = u
         u_pred, prediction = self.strategy.init_posterior(u=prior.init)
+        u0, posterior = self._init_update(u_pred, prediction, t=t, damp=damp)
         output_scale = np.ones_like(prior.alg.prototype_output_scale(u_pred))
         fx = self._zeros_like_fx(u_pred, t, damp)
         return ProbabilisticSolution(
-            t=t, u=u_pred, solution_full=prediction, auxiliary=None,
+            t=t, u=u0, solution_full=posterior, auxiliary=None,
             output_scale=output_scale, num_steps=0, fun_evals=fx, prior=prior,
         )  # fmt: skip
 

@@ -38,6 +38,8 @@ class Config(C.Structure):
         ("re_linearize_after_calibration", C.c_int32),
         ("correct_asymptotic_underconfidence", C.c_int32),
         ("max_attempts", C.c_int32),
+        ("constraint_init", C.c_int32),
+        ("reserved0", C.c_int32),
         ("safety", C.c_double),
         ("factor_min", C.c_double),
         ("factor_max", C.c_double),
@@ -61,6 +63,7 @@ class Problem(C.Structure):
         ("prior_scale_stride", C.c_int64),
         ("params", C.c_void_p),
         ("params_stride", C.c_int64),
+        ("order", C.c_void_p),
     ]
 
 

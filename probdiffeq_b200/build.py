@@ -11,6 +11,7 @@ import concurrent.futures
 import hashlib
 import os
 import pathlib
+import re
 import shutil
 import subprocess
 import sys
@@ -39,20 +40,30 @@ def sources() -> list[pathlib.Path]:
     return sorted(CSRC.glob("*.cu")) + sorted((CSRC / "inst").glob("*.cu"))
 
 
-def _headers_digest() -> bytes:
-    hdrs = sorted(CSRC.glob("*.cuh")) + [ROOT.parent / "include" / "probdiffeq_b200.h"]
-    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
-    for f in hdrs:
-        h.update(f.name.encode() + f.read_bytes())
-    return h.digest()
+_INCLUDE = re.compile(r'^\s*#include\s+"([^"]+)"', re.M)
 
 
-def _compile(src: pathlib.Path, force: bool, verbose: bool, hdr_digest: bytes) -> pathlib.Path:
-    """An object is reused only if the CONTENT of its source, of every header and the flags are what it was built
-    from (a stamp beside the object records their hash) -- not because its mtime is newer."""
+def _includes(src: pathlib.Path, seen: dict[pathlib.Path, None] | None = None) -> list[pathlib.Path]:
+    """The project headers `src` includes, transitively (quoted includes only), in a stable order."""
+    seen = {} if seen is None else seen
+    for name in _INCLUDE.findall(src.read_text()):
+        hdr = (src.parent / name).resolve()
+        if hdr.exists() and hdr not in seen:
+            seen[hdr] = None
+            _includes(hdr, seen)
+    return sorted(seen)
+
+
+def _compile(src: pathlib.Path, force: bool, verbose: bool) -> pathlib.Path:
+    """An object is reused only if the CONTENT of its source, of every header it includes (transitively) and the flags
+    are what it was built from (a stamp beside the object records their hash) -- not because its mtime is newer. A
+    change to one kernel family's header therefore rebuilds that family's translation units only."""
     obj = OBJ / (src.stem + ".o")
     stamp = OBJ / (src.stem + ".sha256")
-    want = hashlib.sha256(hdr_digest + src.read_bytes()).hexdigest()
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in [src, *_includes(src)]:
+        h.update(f.name.encode() + f.read_bytes())
+    want = h.hexdigest()
     if not force and obj.exists() and stamp.exists() and stamp.read_text() == want:
         return obj
     cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
@@ -72,9 +83,8 @@ def build(force: bool = False, verbose: bool = False, jobs: int | None = None) -
     LIB.parent.mkdir(exist_ok=True)
     srcs = sources()
     jobs = jobs or min(len(srcs), os.cpu_count() or 4)
-    digest = _headers_digest()
     with concurrent.futures.ThreadPoolExecutor(max_workers=jobs) as pool:
-        objs = list(pool.map(lambda s: _compile(s, force, verbose, digest), srcs))
+        objs = list(pool.map(lambda s: _compile(s, force, verbose), srcs))
     link_stamp = OBJ / "link.sha256"
     link_want = hashlib.sha256("".join((OBJ / (s.stem + ".sha256")).read_text() for s in srcs).encode()).hexdigest()
     if force or not LIB.exists() or not link_stamp.exists() or link_stamp.read_text() != link_want:

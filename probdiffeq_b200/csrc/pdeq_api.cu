@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "pdeq_aux_kernels.cuh"
+#include "pdeq_limits.cuh"
 
 namespace pdeq {
 
@@ -243,13 +244,6 @@ static int run_loop(const pdeq_config* cfg, const pdeq_problem* pr, const pdeq_s
   a.dt0 = dt0;
   a.dt0_stride = dt0_stride;
   a.work_counter = (unsigned long long*)ws;
-  a.pool_ring = nullptr;
-  a.pool_ring_mask = 0;
-  a.pool_slots = nullptr;
-  a.pool_num_slots = 0;
-  a.pool_seg_len = 0;
-  a.pool_dissolve = 0;
-  a.pool_patience_ns = 0;
   cudaError_t e = cudaMemsetAsync(ws, 0, 256, s);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
   const LoopEntry* entry = select_loop(cfg);

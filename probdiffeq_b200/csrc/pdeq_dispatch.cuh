@@ -1,5 +1,8 @@
 // Kernel registry: explicit template instantiations live in their own translation units (so that nvcc
-// can build them in parallel) and register a launcher under a small key at load time.
+// can build them in parallel) and register a launcher under a small key at load time. This header holds the registry and
+// the launcher of the thread-per-instance kernels (K1); pdeq_dispatch_group.cuh and pdeq_dispatch_dense.cuh add K2 and
+// K3, so that a translation unit depends only on the kernel family it instantiates (probdiffeq_b200/build.py hashes
+// exactly the headers a unit includes).
 #pragma once
 #include <cstdlib>
 
@@ -9,8 +12,6 @@
 #include <cstdint>
 #include <cstdio>
 
-#include "pdeq_loop_dense.cuh"
-#include "pdeq_loop_group.cuh"
 #include "pdeq_loop_thread.cuh"
 
 namespace pdeq {
@@ -42,46 +43,16 @@ int device_sm_count();
 // ---------------------------------------------------------------------------------------------------
 // K1 launcher
 // ---------------------------------------------------------------------------------------------------
-// Tail compaction (ThreadLoop::run): PDEQ_K1_POOL=0 in the environment switches it off (A/B measurements),
-// PDEQ_K1_SEG sets how many loop iterations a warp runs between two visits to the pool.
-inline bool k1_pool_enabled() {
-  const char* e = std::getenv("PDEQ_K1_POOL");
-  return e == nullptr || std::atoi(e) != 0;
-}
-inline int k1_pool_seg_len() {
-  const char* e = std::getenv("PDEQ_K1_SEG");
-  const int c = e == nullptr ? 32 : std::atoi(e);
-  return (c >= 1 && c <= 4096) ? c : 32;
-}
-inline int k1_pool_dissolve() {
-  const char* e = std::getenv("PDEQ_K1_DISSOLVE");
-  const int c = e == nullptr ? 20 : std::atoi(e);
-  return (c >= 0 && c <= 32) ? c : 20;
-}
-inline int k1_pool_patience_ns() {
-  const char* e = std::getenv("PDEQ_K1_PATIENCE_NS");
-  const int c = e == nullptr ? 30000 : std::atoi(e);
-  return c >= 0 ? c : 30000;
-}
-constexpr int K1_MAX_CTAS_PER_SM = 6;
-inline size_t k1_pool_ring_entries(long lanes) {
-  size_t cap = 1024;
-  while ((long)cap < lanes) cap <<= 1;
-  return cap;
-}
-inline long k1_max_lanes(int64_t num_instances) {
-  const long want = (num_instances + K1_THREADS - 1) / K1_THREADS;
-  return std::max(1L, std::min(want, (long)K1_MAX_CTAS_PER_SM * device_sm_count())) * K1_THREADS;
-}
-inline size_t k1_pool_bytes(long lanes, int park_slots) {
-  return k1_pool_ring_entries(lanes) * sizeof(unsigned int) + (size_t)lanes * park_slots * sizeof(double);
-}
-
+// Grid of the thread-per-instance kernel: as many 128-thread CTAs as stay resident (or as the ensemble needs).
+// (Round 2 measured three ways of shortening the end of the run, where lanes go idle one by one: an in-kernel pool
+// of parked instances that re-forms full warps, a one-off repack between two launches, and a grid shaped so that
+// every lane serves the same number of instances. All three were slower than this plain queue -- a warp that runs
+// alone is only ~1.45x faster per attempt than one of twelve, so emptier SMs buy little, and the 128-register build
+// that offers the extra lanes costs 5 %. What does help is the ORDER of service, see pdeq_problem.order.)
 template <class VF, int NU, int FACT, int D, bool TS0, int SPEC>
-cudaError_t k1_launch_impl(const LoopArgs& a_in, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+cudaError_t k1_launch_impl(const LoopArgs& a, void*, size_t, cudaStream_t stream) {
   using TL = ThreadLoop<VF, NU, FACT, D, TS0, SPEC>;
   auto kern = k1_loop_kernel<VF, NU, FACT, D, TS0, SPEC>;
-  LoopArgs a = a_in;
   const bool needs_interp = a.fixed_grid == 0 && a.cfg.clip_dt == 0;
   const size_t smem = needs_interp ? size_t(TL::IF_SLOTS) * TL::THREADS * sizeof(double) : 0;
   cudaError_t err;
@@ -96,25 +67,6 @@ cudaError_t k1_launch_impl(const LoopArgs& a_in, void* workspace, size_t workspa
   const long want = (a.prob.num_instances + TL::THREADS - 1) / TL::THREADS;
   const long cap = (long)per_sm * device_sm_count();
   const int grid = (int)std::max(1L, std::min(want, cap));
-  // the pool of parked instances lives behind the 256-byte header of the workspace
-  const long lanes = (long)grid * TL::THREADS;
-  const int park = TL::PARK_BASE + (needs_interp ? TL::IF_SLOTS : 0);
-  a.pool_ring = nullptr;
-  a.pool_slots = nullptr;
-  a.pool_ring_mask = 0;
-  a.pool_num_slots = 0;
-  a.pool_seg_len = k1_pool_seg_len();
-  a.pool_dissolve = k1_pool_dissolve();
-  a.pool_patience_ns = k1_pool_patience_ns();
-  if (k1_pool_enabled() && workspace != nullptr && workspace_bytes >= 256 + k1_pool_bytes(lanes, park)) {
-    const size_t ring = k1_pool_ring_entries(lanes);
-    a.pool_ring = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + 256);
-    a.pool_ring_mask = (unsigned int)(ring - 1);
-    a.pool_slots = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256 + ring * sizeof(unsigned int));
-    a.pool_num_slots = lanes;
-    err = cudaMemsetAsync(a.pool_ring, 0, ring * sizeof(unsigned int), stream);
-    if (err != cudaSuccess) return err;
-  }
   kern<<<grid, TL::THREADS, smem, stream>>>(a);
   return cudaGetLastError();
 }
@@ -145,10 +97,7 @@ cudaError_t k1_launch(const LoopArgs& a, void* ws, size_t ws_bytes, cudaStream_t
 
 template <class VF, int NU, int FACT, int D, bool TS0, bool HAS_SPEC = false>
 struct K1Registrar {
-  static size_t ws(const pdeq_config&, int64_t num_instances, int32_t) {
-    using TL = ThreadLoop<VF, NU, FACT, D, TS0, 0>;
-    return 256 + k1_pool_bytes(k1_max_lanes(num_instances), TL::PARK_SLOTS_MAX);
-  }
+  static size_t ws(const pdeq_config&, int64_t, int32_t) { return 256; }
   explicit K1Registrar(int vf_id = VF::id) {
     register_loop({{vf_id, NU, FACT, D, TS0 ? 1 : 0, 0}, &k1_launch<VF, NU, FACT, D, TS0, HAS_SPEC>, &ws, "thread"});
   }
@@ -166,189 +115,5 @@ struct K1Registrar {
   static K1Registrar<VF, NU, PDEQ_FACT_ISOTROPIC, D, false> _k1_iso1_##VF##_##NU##_##D; \
   static K1Registrar<VF, NU, PDEQ_FACT_BLOCKDIAG, D, true> _k1_bd0_##VF##_##NU##_##D;  \
   static K1Registrar<VF, NU, PDEQ_FACT_BLOCKDIAG, D, false> _k1_bd1_##VF##_##NU##_##D;
-
-// ---------------------------------------------------------------------------------------------------
-// K2 launcher: warp per instance for d <= 32, CTA per instance otherwise.
-// ---------------------------------------------------------------------------------------------------
-struct K2Plan {
-  bool cta;
-  int mode;  // GroupLoop MODE
-  int threads, groups_per_cta, grid;
-  size_t smem_bytes, ring_bytes_per_group;
-};
-
-// PDEQ_K2_SPEC=0 in the environment forces the general kernel where a specialised build exists (GroupLoop SPEC);
-// 2 selects the smoother build that defers the backward conditional to accepted steps.
-inline int k2_spec_choice() {
-  const char* e = std::getenv("PDEQ_K2_SPEC");
-  const int c = e == nullptr ? 1 : std::atoi(e);
-  return (c >= 0 && c <= 2) ? c : 1;
-}
-
-template <class VF, int NU, int FACT, bool TS0, bool FP, int SPEC = 0>
-cudaError_t k2_plan(const pdeq_config& cfg, int64_t B, int32_t T, bool needs_interp, K2Plan* plan) {
-  using GL = GroupLoop<VF, NU, FACT, TS0, FP, 0>;
-  const int d = cfg.ode_dim;
-  const size_t per_group = GL::smem_doubles_per_group(d, needs_interp) * sizeof(double);
-  plan->cta = d > 32;
-  plan->mode = d <= 32 ? 0 : (d <= K2_CTA_THREADS ? 1 : 2);
-  if (plan->cta) {
-    using GC = GroupLoop<VF, NU, FACT, TS0, FP, 2>;
-    plan->threads = std::min(K2_CTA_THREADS, ((d + 31) / 32) * 32);
-    if ((d + plan->threads - 1) / plan->threads > GC::MAXR) return cudaErrorInvalidValue;
-    plan->groups_per_cta = 1;
-  } else {
-    plan->groups_per_cta = 4;
-    while (plan->groups_per_cta > 1 && per_group * plan->groups_per_cta > 96 * 1024) plan->groups_per_cta /= 2;
-    plan->threads = 32 * plan->groups_per_cta;
-  }
-  plan->smem_bytes = per_group * plan->groups_per_cta;
-  if (plan->smem_bytes > 227 * 1024) return cudaErrorInvalidValue;
-  // per resident group: the ring of per-checkpoint conditionals plus the interp_from slot (smoother only)
-  plan->ring_bytes_per_group = FP ? ((size_t)T * GL::NFC + GL::NF) * d * sizeof(double) : 0;
-  int per_sm = 0;
-  cudaError_t err;
-  if (plan->mode == 2) {
-    auto kern = k2_loop_kernel<VF, NU, FACT, TS0, FP, 2>;
-    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
-    if (err != cudaSuccess) return err;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, plan->threads, plan->smem_bytes);
-  } else if (plan->mode == 1) {
-    auto kern = k2_loop_kernel<VF, NU, FACT, TS0, FP, 1>;
-    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
-    if (err != cudaSuccess) return err;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, plan->threads, plan->smem_bytes);
-  } else {
-    auto kern = k2_loop_kernel<VF, NU, FACT, TS0, FP, 0, SPEC>;
-    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
-    if (err != cudaSuccess) return err;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, plan->threads, plan->smem_bytes);
-  }
-  if (err != cudaSuccess) return err;
-  if (per_sm < 1) per_sm = 1;
-  if (const char* cap = std::getenv("PDEQ_K2_CTAS_PER_SM")) {  // tuning knob: fewer resident CTAs per SM
-    const int c = std::atoi(cap);
-    if (c >= 1 && c < per_sm) per_sm = c;
-  }
-  const long want = (B + plan->groups_per_cta - 1) / plan->groups_per_cta;
-  plan->grid = (int)std::max(1L, std::min(want, (long)per_sm * device_sm_count()));
-  return cudaSuccess;
-}
-
-template <class VF, int NU, int FACT, bool TS0, bool FP>
-size_t k2_workspace(const pdeq_config& cfg, int64_t B, int32_t T) {
-  K2Plan plan;
-  if (k2_plan<VF, NU, FACT, TS0, FP>(cfg, B, T, /*needs_interp=*/true, &plan) != cudaSuccess) return 256;
-  K2Plan plan2;
-  size_t groups = (size_t)plan.grid * plan.groups_per_cta;
-  if (k2_plan<VF, NU, FACT, TS0, FP>(cfg, B, T, /*needs_interp=*/false, &plan2) == cudaSuccess)
-    groups = std::max(groups, (size_t)plan2.grid * plan2.groups_per_cta);
-  return 256 + groups * plan.ring_bytes_per_group;
-}
-
-template <class VF, int NU, int FACT, bool TS0, bool FP, bool HAS_SPEC = false>
-cudaError_t k2_launch(const LoopArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  const bool needs_interp = a.fixed_grid == 0 && a.cfg.clip_dt == 0;
-  K2Plan plan;
-  // the specialised build exists for the warp-per-instance mode only (d <= 32)
-  const int choice = k2_spec_choice();
-  const bool spec = HAS_SPEC && a.cfg.ode_dim <= 32 && k2_spec_matches(a) && choice != 0;
-  const bool defer = spec && FP && choice == 2 && a.fixed_grid == 0;
-  cudaError_t err = cudaSuccess;
-  if constexpr (HAS_SPEC) {
-    err = spec ? k2_plan<VF, NU, FACT, TS0, FP, 1>(a.cfg, a.prob.num_instances, a.T, needs_interp, &plan)
-               : k2_plan<VF, NU, FACT, TS0, FP, 0>(a.cfg, a.prob.num_instances, a.T, needs_interp, &plan);
-  } else {
-    err = k2_plan<VF, NU, FACT, TS0, FP>(a.cfg, a.prob.num_instances, a.T, needs_interp, &plan);
-  }
-  if (err != cudaSuccess) return err;
-  GroupLaunchInfo info;
-  info.groups_per_cta = plan.groups_per_cta;
-  info.cond_ring = reinterpret_cast<double*>(static_cast<char*>(workspace) + 256);
-  info.if_scratch = nullptr;
-  if (FP) {  // never launch more groups than the scratch has room for
-    using GL = GroupLoop<VF, NU, FACT, TS0, FP, 0>;
-    const size_t room = (workspace_bytes - 256) / plan.ring_bytes_per_group;
-    const int max_grid = (int)(room / plan.groups_per_cta);
-    if (max_grid < 1) return cudaErrorMemoryAllocation;
-    plan.grid = std::min(plan.grid, max_grid);
-    const size_t groups = (size_t)plan.grid * plan.groups_per_cta;
-    info.if_scratch = info.cond_ring + groups * (size_t)a.T * GL::NFC * a.cfg.ode_dim;
-  }
-  if (plan.mode == 2)
-    k2_loop_kernel<VF, NU, FACT, TS0, FP, 2><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);
-  else if (plan.mode == 1)
-    k2_loop_kernel<VF, NU, FACT, TS0, FP, 1><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);
-  else if (spec) {
-    if constexpr (HAS_SPEC) {
-      if (defer) {
-        if constexpr (FP) {
-          auto kern = k2_loop_kernel<VF, NU, FACT, TS0, FP, 0, 2>;
-          err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);
-          if (err != cudaSuccess) return err;
-          kern<<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);
-        }
-      } else {
-        k2_loop_kernel<VF, NU, FACT, TS0, FP, 0, 1><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);
-      }
-    }
-  } else
-    k2_loop_kernel<VF, NU, FACT, TS0, FP, 0><<<plan.grid, plan.threads, plan.smem_bytes, stream>>>(a, info);
-  return cudaGetLastError();
-}
-
-template <class VF, int NU, int FACT, bool TS0, bool FP, bool HAS_SPEC = false>
-struct K2Registrar {
-  explicit K2Registrar(int vf_id = VF::id) {
-    register_loop({{vf_id, NU, FACT, 0, TS0 ? 1 : 0, FP ? 1 : 0}, &k2_launch<VF, NU, FACT, TS0, FP, HAS_SPEC>,
-                   &k2_workspace<VF, NU, FACT, TS0, FP>, "group"});
-  }
-};
-
-// ---------------------------------------------------------------------------------------------------
-// K3 launcher: dense factorisation, CTA per instance.
-// ---------------------------------------------------------------------------------------------------
-template <class VF, int NU, bool TS0>
-cudaError_t k3_launch(const LoopArgs& a, void*, size_t, cudaStream_t stream) {
-  const bool needs_interp = a.fixed_grid == 0 && a.cfg.clip_dt == 0;
-  const DenseSmemLayout lay = DenseSmemLayout::make(NU + 1, a.cfg.ode_dim, VF::order, needs_interp);
-  const size_t smem = lay.total * sizeof(double);
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  auto kern = k3_loop_kernel<VF, NU, TS0>;
-  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (err != cudaSuccess) return err;
-  int per_sm = 0;
-  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K3_THREADS, smem);
-  if (err != cudaSuccess) return err;
-  if (per_sm < 1) per_sm = 1;
-  const long cap = (long)per_sm * device_sm_count();
-  const int grid = (int)std::max(1L, std::min((long)a.prob.num_instances, cap));
-  kern<<<grid, K3_THREADS, smem, stream>>>(a);
-  return cudaGetLastError();
-}
-
-template <class VF, int NU>
-struct K3Registrar {
-  static size_t ws(const pdeq_config&, int64_t, int32_t) { return 256; }
-  explicit K3Registrar(int vf_id = VF::id) {
-    register_loop({{vf_id, NU, PDEQ_FACT_DENSE, 0, 1, 0}, &k3_launch<VF, NU, true>, &ws, "dense"});
-    register_loop({{vf_id, NU, PDEQ_FACT_DENSE, 0, 0, 0}, &k3_launch<VF, NU, false>, &ws, "dense"});
-  }
-};
-#define PDEQ_INSTANTIATE_K3(VF, NU) static K3Registrar<VF, NU> _k3_##VF##_##NU;
-
-// as PDEQ_INSTANTIATE_K2, with the specialised warp-mode builds (GroupLoop SPEC = 1) behind the two ts0 entries
-#define PDEQ_INSTANTIATE_K2_WITH_SPEC(VF, NU, FACT, TAG)                      \
-  static K2Registrar<VF, NU, FACT, true, false, true> _k2_f0_##VF##_##NU##_##TAG;  \
-  static K2Registrar<VF, NU, FACT, false, false> _k2_f1_##VF##_##NU##_##TAG;       \
-  static K2Registrar<VF, NU, FACT, true, true, true> _k2_s0_##VF##_##NU##_##TAG;   \
-  static K2Registrar<VF, NU, FACT, false, true> _k2_s1_##VF##_##NU##_##TAG;
-
-// filter + fixed-point smoother, ts0 + ts1, for one factorisation
-#define PDEQ_INSTANTIATE_K2(VF, NU, FACT, TAG)                        \
-  static K2Registrar<VF, NU, FACT, true, false> _k2_f0_##VF##_##NU##_##TAG;  \
-  static K2Registrar<VF, NU, FACT, false, false> _k2_f1_##VF##_##NU##_##TAG; \
-  static K2Registrar<VF, NU, FACT, true, true> _k2_s0_##VF##_##NU##_##TAG;   \
-  static K2Registrar<VF, NU, FACT, false, true> _k2_s1_##VF##_##NU##_##TAG;
 
 }  // namespace pdeq

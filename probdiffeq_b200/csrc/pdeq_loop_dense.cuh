@@ -1,14 +1,23 @@
-// K3: the dense factorisation (probdiffeq/_probdiffeq/ssm_impl_dense.py), one IVP instance per CTA of 64 threads.
+// K3: the dense factorisation (probdiffeq/_probdiffeq/ssm_impl_dense.py), one IVP instance per CTA, COLUMNS IN REGISTERS.
 //
 // The state is a mean of length N = n d (coefficient-major, index k d + i) and a full N x N left square root.
 // Every step triangularises a 2N x N stack (extrapolation, DenseLatentCond.marginalise :24-33) and an
 // (N + d) x (N + d) stack (correction, DenseLatentCond.revert :51-77 with util/cholesky_util.py:27-82); for
-// HIRES (d = 8, nu = 5) these are 96 x 48 and 56 x 56.  Both live in ONE shared-memory work buffer W of
-// 2N x (N + d) doubles and are triangularised by a cooperative Householder: the 64 threads own the trailing
-// columns (row-major W => conflict-free, the reflector is a shared-memory broadcast), the column norm is a
-// two-warp reduction.  Reflectors follow LAPACK dlarfg (see pdeq_blockops.cuh).  Stack rows are ordered
-// [(H L)^T, L^T ; damp I, 0] -- a row permutation of the reference's block matrix that leaves R^T R, hence all
-// covariances and the gain, unchanged -- so that the extrapolated factor is reused in place.
+// HIRES (d = 8, nu = 5) these are 96 x 48 and 56 x 56, ~110 dependent Householder reflectors per attempt.
+//
+// Mapping. A column of the stack lives in the REGISTERS of TPC (2 or 4) adjacent lanes, rows dealt round-robin
+// (row r -> lane part r % TPC, register r / TPC); the CTA holds N "state" columns and d "observation" columns.
+// One reflector step: the lanes that own the pivot column reduce its norm with a shuffle, form the reflector
+// (LAPACK dlarfg convention, see pdeq_blockops.cuh) and publish it -- zero outside its row extent, v0 at the pivot
+// row, so that nobody needs a run-time register index -- in one of two shared-memory buffers; ONE block barrier;
+// every lane of a trailing column forms its part of v^T c from broadcast reads of that buffer and its own registers,
+// meets its partners with a shuffle and updates its registers. The trailing matrix is never read or written in shared
+// memory (round 1's kernel did both for every column and was bound by exactly that: ~2600 cycles per column with
+// four instances per SM), the reflector loop is ROLLED (a few hundred instructions, so the kernel lives in the
+// instruction cache), and the shared memory per instance drops from 55 KB to the packed accepted factor plus vectors.
+// Stack rows are ordered [(H L)^T, L^T ; damp I, 0] -- a row permutation of the reference's block matrix that leaves
+// R^T R, hence all covariances and the gain, unchanged -- so that the extrapolated factor is reused in place: the
+// registers that held column c of the extrapolation stack hold column d + c of the correction stack.
 //
 // Restates for the dense model: DenseWienerIntegrated.transition (:347-363), DenseOdeTs0.linearize (:243-259),
 // DenseResidual.linearize (:290-334, exact Jacobian, jacobians.py:93-98), DenseNormal.std (:144-150),
@@ -16,48 +25,27 @@
 // pdeq_loop_thread.cuh.  Filter strategy only.
 #pragma once
 
+#include "pdeq_limits.cuh"
 #include "pdeq_loop_thread.cuh"
 
 namespace pdeq {
-
-constexpr int K3_THREADS = 256;
-
-struct DenseSmemLayout {
-  int N, d, ld;  // ld = N + d
-  size_t off_W, off_Lfrom, off_Lif, off_vec, total;
-  __host__ __device__ static DenseSmemLayout make(int n, int d, int order, bool needs_interp) {
-    DenseSmemLayout s;
-    s.N = n * d;
-    s.d = d;
-    s.ld = s.N + d;
-    const size_t tri = (size_t)s.N * (s.N + 1) / 2;
-    size_t o = 0;
-    s.off_W = o;
-    o += (size_t)2 * s.N * s.ld;
-    s.off_Lfrom = o;
-    o += tri;
-    s.off_Lif = o;
-    o += needs_interp ? tri : 0;
-    s.off_vec = o;
-    // m_from, mp, m_new, m_if (4N) | Hs d x (order+1) d | mobs, wht, std, ref, lam (5d) | p, pinv (2 * 8) | red 8 | bc 8
-    // | rdiag N + d
-    o += (size_t)4 * s.N + (size_t)d * (order + 1) * d + 5 * d + 16 + 16 + s.ld;
-    s.total = o;
-    return s;
-  }
-};
 
 template <class VF, int NU, bool TS0>
 struct DenseLoop {
   static constexpr int n = NU + 1;
   static constexpr int q = VF::order;
   static constexpr int P = VF::num_params > 0 ? VF::num_params : 1;
-  static constexpr int G = K3_THREADS;
   // All extents are compile-time: the dense kernels exist for fixed-dimension vector fields only (the host checks
   // cfg.ode_dim == VF::fixed_dim), so every index split (e / N, e % d, ...) is a multiply-shift, not a division.
   static constexpr int D = VF::fixed_dim;
   static_assert(D > 0, "the dense kernels need a compile-time ODE dimension");
   static constexpr int N = n * D, LD = N + D, HW = (q + 1) * D, TRI_N = N * (N + 1) / 2;
+  static constexpr int TPC = DenseSmemLayout::tpc(N);               // lanes per column
+  static constexpr int RPT = DenseSmemLayout::rows_per_thread(N);   // registers per lane (rows of the 2N-row stack)
+  static constexpr int RPAD = DenseSmemLayout::rpad(N);
+  static constexpr int RB = TPC * RPAD + 2;                         // one reflector buffer: TPC row parts, tp
+  static constexpr int G = DenseSmemLayout::threads(N, D);
+  static_assert(TPC * RPT >= 2 * N, "rows do not fit");
 
   struct VecAcc {
     const double* u;  // coefficient-major mean
@@ -66,6 +54,13 @@ struct DenseLoop {
   };
 
   PDEQ_DI static int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // packed lower, j <= i
+
+  // sum over the TPC lanes that share a column
+  PDEQ_DI static double group_sum(double v, unsigned gmask) {
+#pragma unroll
+    for (int o = 1; o < TPC; o <<= 1) v += __shfl_xor_sync(gmask, v, o);
+    return v;
+  }
 
   PDEQ_DI static double block_sum(double v, double* red) {
 #pragma unroll
@@ -79,118 +74,123 @@ struct DenseLoop {
     return tot;
   }
 
-  // Sum of squares of W[j+1..h][j], by warp 0, into *dst; ends with a block barrier.
-  PDEQ_DI static void column_ss(const double* W, int j, int h, double* dst) {
-    if (threadIdx.x < 32) {
-      double part = 0.0;
-      for (int r = j + 1 + (int)threadIdx.x; r <= h; r += 32) part = fma(W[r * LD + j], W[r * LD + j], part);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      if (threadIdx.x == 0) *dst = part;
+  // Which rows a reflector touches. Pivot j (row j) reaches the rows r > j of the top block (r < SA) and, of the bottom
+  // block, row SA + k once k <= j (the bottom block of both stacks is upper triangular: row k enters with pivot k) --
+  // all of them for j >= CSPLIT (fill-in has made the trailing matrix dense by then).
+  PDEQ_DI static bool row_in(int r, int j, int csplit, int sa) {
+    return r > j && (r < sa || j >= csplit || r - sa <= j);
+  }
+  // The same for a BLOCK of pivots J0 <= j < J1, decided at compile time: 0 = no pivot of the block touches row r,
+  // 1 = every pivot does (and r is not a pivot row), 2 = it depends on j. A register holds TPC consecutive rows (which
+  // of them is this lane's is a run-time matter), so registers are classified by the union over their rows.
+  static constexpr int row_class(int r, int J0, int J1, int M, int CSPLIT, int SA) {
+    if (r >= M || r < J0) return 0;
+    if (r < J1) return 2;
+    if (r < SA || J0 >= CSPLIT) return 1;
+    const int k = r - SA;
+    if (k < J0) return 1;
+    if (J1 <= CSPLIT && k >= J1) return 0;
+    return 2;
+  }
+  static constexpr int reg_class(int i, int J0, int J1, int M, int CSPLIT, int SA) {
+    int c = row_class(i * TPC, J0, J1, M, CSPLIT, SA);
+    for (int hh = 1; hh < TPC; ++hh) {
+      const int c2 = row_class(i * TPC + hh, J0, J1, M, CSPLIT, SA);
+      if (c2 != c) c = 2;
     }
-    __syncthreads();
+    return c;
   }
 
-  // Cooperative in-place Householder triangularisation of the M x ncols matrix at W (leading dimension LD).
-  // hi(c) = min(hi_a + c, M - 1) for c < csplit, M - 1 otherwise: the last non-zero row of column c.
+  // Householder triangularisation of the M-row stack whose columns live in the lanes' registers.
+  // `mypos`: position of this lane's column in the elimination order (-1: no column); `first_lane(j)`: the first lane
+  // of the group that owns pivot j. After the call a column holds R above and on its diagonal and exact zeros below.
   //
-  // 256 threads = 64 column slots x 4 row groups. A warp holds 8 adjacent columns x 4 row groups (rows r, r+1 of
-  // LD = 56 doubles are 16 banks apart: each half-warp is conflict-free), so the four partial dot products of one
-  // column meet by two shuffles and there is ONE block barrier per column: the sum of squares of the next column
-  // is accumulated by the lanes that update it (always slot 0, i.e. warp 0), and the new diagonal goes to `rdiag`
-  // so that nobody races with the readers of alpha. Reflectors follow LAPACK dlarfg (H = I for a zero sub-column).
-  template <int M, int ncols, int csplit, int hi_a>
-  PDEQ_DI static void coop_qr(double* W, double* red, double* rdiag) {
-    constexpr int ld = LD;
-    const int tid = threadIdx.x;
-    const int cslot = (tid >> 5) * 8 + (tid & 7);
-    const int rg = (tid >> 3) & 3;
-    const bool warp0 = tid < 32;
-    auto hi = [](int c) { return (c < csplit) ? min(hi_a + c, M - 1) : M - 1; };
-    column_ss(W, 0, hi(0), red);
-    for (int j = 0; j < ncols; ++j) {
-      const int hj = hi(j);
-      const double alpha = W[j * ld + j];
-      const double ss = red[j & 1];
-      const bool last = j + 1 >= ncols;
-      if (hj <= j || ss == 0.0) {  // uniform: nothing to annihilate
-        if (tid == 0) rdiag[j] = alpha;
-        if (!last) column_ss(W, j + 1, hi(j + 1), red + ((j + 1) & 1));
-        continue;
-      }
-      const double tt = fma(alpha, alpha, ss);
-      const double y = fast_rsqrt(tt);
-      const double nrm = tt * y;
-      const double sgn_nrm = copysign(nrm, alpha);
-      const double v0 = alpha + sgn_nrm;
-      const double tp = y * fast_rcp(nrm + fabs(alpha));
-      if (tid == 0) rdiag[j] = -sgn_nrm;
-      const int h1 = last ? hj : hi(j + 1);
-      for (int c0 = j + 1; c0 < ncols; c0 += G / 4) {
-        const int c = c0 + cslot;
-        const bool active = c < ncols;
-        double w0 = 0.0, w1 = 0.0;
-        if (active) {
-          int r = j + 1 + rg;
-          for (; r + 4 <= hj; r += 8) {
-            w0 = fma(W[r * ld + j], W[r * ld + c], w0);
-            w1 = fma(W[(r + 4) * ld + j], W[(r + 4) * ld + c], w1);
-          }
-          if (r <= hj) w0 = fma(W[r * ld + j], W[r * ld + c], w0);
-          if (rg == 0) w1 = fma(v0, W[j * ld + c], w1);
-        }
-        double w = w0 + w1;
-        w += __shfl_xor_sync(0xffffffffu, w, 8);
-        w += __shfl_xor_sync(0xffffffffu, w, 16);
-        w *= tp;
-        const bool gather = warp0 && c0 == j + 1;  // warp-uniform: this warp owns column j + 1
-        double sq = 0.0, sq1 = 0.0;
-        if (active) {
-          if (rg == 0) W[j * ld + c] = fma(-w, v0, W[j * ld + c]);
-          if (gather) {
-            // ... and gathers that column's sum of squares below its diagonal for the next reflector
-            int r = j + 1 + rg;
-            for (; r + 4 <= hj; r += 8) {
-              const double x0 = fma(-w, W[r * ld + j], W[r * ld + c]);
-              const double x1 = fma(-w, W[(r + 4) * ld + j], W[(r + 4) * ld + c]);
-              W[r * ld + c] = x0;
-              W[(r + 4) * ld + c] = x1;
-              sq = (cslot == 0 && r > j + 1) ? fma(x0, x0, sq) : sq;
-              sq1 = (cslot == 0) ? fma(x1, x1, sq1) : sq1;
+  // One block barrier per reflector (the two reflector buffers alternate: whoever writes buffer (j & 1) again has
+  // passed barrier j + 1, which every reader of step j reaches only after its reads). The pivots are taken in blocks
+  // of eight, unrolled, so that inside a block the rows a reflector can touch are known at compile time (row_class):
+  // a step costs what its rows cost, not what the whole column costs, with run-time tests only for the eight rows
+  // around the pivots. Nothing in a step diverges inside a warp: every lane of the owning warp forms "its" reflector
+  // (the owner's is the one published), and a lane whose column is finished updates it with weight zero -- shuffles
+  // under a diverged mask go through a slow path that cost more than the arithmetic they saved.
+  template <int M, int NPOS, int CSPLIT, int SA, class FirstLane>
+  PDEQ_DI static void column_qr(double (&col)[RPT], int mypos, int h, FirstLane first_lane, double* rbuf) {
+    constexpr int RM = (M + TPC - 1) / TPC;  // registers in use for an M-row stack
+    constexpr int BS = 8;
+    const int warp = threadIdx.x >> 5;
+    static_for<0, (NPOS + BS - 1) / BS>([&](auto jb_) {
+      constexpr int J0 = decltype(jb_)::value * BS;
+      constexpr int J1 = imin(J0 + BS, NPOS);
+      for (int j = J0; j < J1; ++j) {
+        double* buf = rbuf + (j & 1) * RB;
+        if ((first_lane(j) >> 5) == warp) {  // warp-uniform: this warp holds the pivot column
+          double ss0 = 0.0, ss1 = 0.0, alpha = 0.0;
+          static_for<0, RM>([&](auto ic_) {
+            constexpr int i = decltype(ic_)::value;
+            constexpr int cls = reg_class(i, J0, J1, M, CSPLIT, SA);
+            if constexpr (cls == 1) {
+              if constexpr (i & 1) ss1 = fma(col[i], col[i], ss1);
+              else ss0 = fma(col[i], col[i], ss0);
+            } else if constexpr (cls == 2) {
+              const int r = i * TPC + h;
+              const double x = col[i];
+              ss0 = row_in(r, j, CSPLIT, SA) ? fma(x, x, ss0) : ss0;
+              alpha = (r == j) ? x : alpha;
             }
-            if (r <= hj) {
-              const double x0 = fma(-w, W[r * ld + j], W[r * ld + c]);
-              W[r * ld + c] = x0;
-              sq = (cslot == 0 && r > j + 1) ? fma(x0, x0, sq) : sq;
-            }
-            sq += sq1;
-          } else {
-#pragma unroll 2
-            for (int r = j + 1 + rg; r <= hj; r += 4) W[r * ld + c] = fma(-w, W[r * ld + j], W[r * ld + c]);
+          });
+          const double ss = group_sum(ss0 + ss1, 0xffffffffu);
+          alpha = group_sum(alpha, 0xffffffffu);
+          const bool live = ss != 0.0;  // dlarfg: xnorm == 0 -> tau = 0, H = I
+          const double tt = fma(alpha, alpha, ss);
+          const double y = fast_rsqrt(live ? tt : 1.0);
+          const double nrm = tt * y;
+          const double sgn_nrm = copysign(nrm, alpha);
+          const double v0 = alpha + sgn_nrm;
+          const double tp = live ? fast_rcp(fma(nrm, fabs(alpha), tt)) : 0.0;
+          const double beta = live ? -sgn_nrm : alpha;
+          if (mypos == j) {
+            static_for<0, RM>([&](auto ic_) {
+              constexpr int i = decltype(ic_)::value;
+              constexpr int cls = reg_class(i, J0, J1, M, CSPLIT, SA);
+              if constexpr (cls == 1) {
+                buf[h * RPAD + i] = col[i];
+                col[i] = 0.0;
+              } else if constexpr (cls == 2) {
+                const int r = i * TPC + h;
+                const bool below = row_in(r, j, CSPLIT, SA);
+                buf[h * RPAD + i] = (r == j) ? v0 : (below ? col[i] : 0.0);
+                col[i] = (r == j) ? beta : (below ? 0.0 : col[i]);
+              }
+            });
+            if (h == 0) buf[TPC * RPAD] = tp;
           }
         }
-        if (gather) {
-          if (tid == 0)  // rows of column j + 1 below this reflector's reach
-            for (int r = hj + 1; r <= h1; ++r) sq = fma(W[r * ld + c], W[r * ld + c], sq);
-          sq += __shfl_xor_sync(0xffffffffu, sq, 8);
-          sq += __shfl_xor_sync(0xffffffffu, sq, 16);
-          if (tid == 0) red[(j + 1) & 1] = sq;
+        __syncthreads();
+        if (__any_sync(0xffffffffu, mypos > j)) {  // warp-uniform: some column of this warp is still active
+          const double tp = (mypos > j) ? buf[TPC * RPAD] : 0.0;
+          const double* v = buf + h * RPAD;
+          double w0 = 0.0, w1 = 0.0;
+          static_for<0, RM>([&](auto ic_) {
+            constexpr int i = decltype(ic_)::value;
+            if constexpr (reg_class(i, J0, J1, M, CSPLIT, SA) != 0) {
+              if constexpr (i & 1) w1 = fma(v[i], col[i], w1);
+              else w0 = fma(v[i], col[i], w0);
+            }
+          });
+          const double w = group_sum(w0 + w1, 0xffffffffu) * tp;
+          static_for<0, RM>([&](auto ic_) {
+            constexpr int i = decltype(ic_)::value;
+            if constexpr (reg_class(i, J0, J1, M, CSPLIT, SA) != 0) col[i] = fma(-w, v[i], col[i]);
+          });
         }
       }
-      __syncthreads();
-    }
-    // the last column may have taken the barrier-free skip path: make its rdiag entry (and everyone's last read
-    // of the old diagonal) visible before the diagonal is restored
-    __syncthreads();
-    for (int j = tid; j < ncols; j += G) W[j * ld + j] = rdiag[j];
-    __syncthreads();
+    });
+    __syncthreads();  // the last buffer may be rewritten by whatever comes next
   }
 
   // Write one checkpoint (mean [n][d], chol [N][N]) from shared memory.
-  PDEQ_DI static void emit(const LoopArgs& a, long b, int ck, const DenseSmemLayout& lay, double t, const double* m,
-                           const double* Lpk, double chol_scale, double scale, int nsteps) {
+  PDEQ_DI static void emit(const LoopArgs& a, long b, int ck, double t, const double* m, const double* Lpk,
+                           double chol_scale, double scale, int nsteps) {
     const long bt = b * a.T + ck;
-    (void)lay;
     if (threadIdx.x == 0) {
       a.sol.t[bt] = t;
       a.sol.num_steps[bt] = nsteps;
@@ -206,54 +206,189 @@ struct DenseLoop {
     }
   }
 
-  // Fill W[0..2N) x [d..d+N) with the extrapolation stack [(A (pinv L))^T ; (s Q)^T], A = kron(a, I_d),
-  // Q = kron(q, diag(lam)); triangularise; scale the columns of R by |p| so that rows 0..N-1 hold L_pred^T.
-  PDEQ_DI static void extrapolate_chol(double* W, const DenseSmemLayout& lay, const double* Lpk, const double* p,
-                                       const double* pinv, const double* lam, double s,
-                                       const double (*A)[PDEQ_MAX_COEFFS], const double (*Qm)[PDEQ_MAX_COEFFS],
-                                       double* red) {
-    constexpr int d = D, ld = LD;
-    (void)lay;
-    for (int e = threadIdx.x; e < N * N; e += G) {
-      const int r = e / N, c = e % N;
-      const int ci = c / d, cj = c % d;
-      // (A L~)[c][r] = sum_k a[ci][k] pinv_k L[k d + cj][r]   (k >= ci, and k d + cj >= r)
-      double acc = 0.0;
-      for (int k = ci; k < n; ++k) {
-        const int row = k * d + cj;
-        if (row >= r) acc = fma(A[ci][k], pinv[k] * Lpk[tri(row, r)], acc);
-      }
-      W[r * ld + d + c] = acc;
-      const int ri = r / d, rj = r % d;
-      W[(N + r) * ld + d + c] = (cj == rj && ci >= ri) ? s * Qm[ci][ri] * lam[cj] : 0.0;
-    }
+  // Everything the per-step routines share: this lane's place in the column layout and the instance's shared memory.
+  // (Plain forced-inline functions taking the column registers by reference: a lambda that captures `col` and is not
+  // inlined takes its address and puts all of it in local memory -- measured: 4x slower than round 1's kernel.)
+  struct Ctx {
+    int tid, cp, h, ci, cj, oa, pos_pred, pos_obs, pos_rev;
+    bool is_state, is_obs;
+    unsigned gmask;
+    double inv_sqrt_d;
+    const double (*A)[PDEQ_MAX_COEFFS];
+    const double (*Qm)[PDEQ_MAX_COEFFS];
+    double *rbuf, *Hs, *Ush, *RY, *mobs, *wht, *stdv, *lam, *p, *pinv;
+  };
+
+  // Linearise the constraint at `mean` (DenseOdeTs0.linearize :243-259 / DenseResidual.linearize :290-334): the
+  // non-zero columns of H go to Hs, the observed mean H m + bias to mobs. Ends with a block barrier.
+  PDEQ_DI static void linearise_at(const Ctx& c, const double* mean, double tt, const double (&params)[P]) {
+    constexpr int d = D, hw = HW;
+    for (int e = c.tid; e < d * hw; e += G) c.Hs[e] = 0.0;
     __syncthreads();
-    coop_qr<2 * N, N, N, N>(W + d, red, red + 16);
-    for (int e = threadIdx.x; e < N * N; e += G) {
-      const int r = e / N, c = e % N;
-      if (r <= c) W[r * ld + d + c] *= fabs(p[c / d]);
-      else W[r * ld + d + c] = 0.0;  // drop the stored reflectors
+    VecAcc acc{mean, d};
+    for (int jd = c.tid; jd < d; jd += G) {
+      const double f = VF::template component<double>(jd, d, acc, params, tt);
+      c.Hs[jd * hw + q * d + jd] = 1.0;
+      if (TS0) {
+        c.mobs[jd] = mean[q * d + jd] + (-f);
+      } else {
+        const double rres = mean[q * d + jd] - f;
+        double hm = mean[q * d + jd];
+        for (int cc = 0; cc < q; ++cc) {
+          for (int l = 0; l < d; ++l) {
+            const double hv = -VF::jac(jd, cc, l, d, acc, params, tt);
+            c.Hs[jd * hw + cc * d + l] = hv;
+            hm = fma(hv, mean[cc * d + l], hm);
+          }
+        }
+        c.mobs[jd] = hm + (rres - hm);
+      }
     }
     __syncthreads();
   }
 
-  // With rows 0..N-1, cols d..d+N-1 of W holding an upper-triangular factor U = L^T, build and triangularise
-  // [(H L)^T | L^T ; damp I | 0]. Afterwards R_Y = W[0..d)[0..d), R12 = W[0..d)[d..), R_XY = W[d..d+N)[d..).
-  PDEQ_DI static void revert_stack(double* W, const DenseSmemLayout& lay, const double* Hs, double damp, double* red) {
-    constexpr int d = D, ld = LD, hw = HW;
-    (void)lay;
-    for (int e = threadIdx.x; e < N * d; e += G) {
-      const int r = e / d, a_ = e % d;
-      double acc = 0.0;  // (H L)[a][r] = sum_e' H[a][e'] L[e'][r], L[e'][r] = U[r][e'] (e' >= r)
-      for (int ee = r; ee < hw; ++ee) acc = fma(Hs[a_ * hw + ee], W[r * ld + d + ee], acc);
-      W[r * ld + a_] = acc;
+  // State columns <- the extrapolation stack [(A (pinv L))^T ; (s Q)^T] of the packed factor Lpk, A = kron(a, I_d),
+  // Q = kron(q, diag(lam)); triangularise; scale column c by |p| so that rows 0..c hold column c of L_pred^T.
+  PDEQ_DI static void extrapolate_chol(const Ctx& c, double (&col)[RPT], const double* Lpk, double s) {
+    constexpr int d = D;
+    if (c.is_state) {
+      const int ci = c.ci, cj = c.cj, h = c.h;
+      static_for<0, RPT>([&](auto ic_) {
+        constexpr int i = decltype(ic_)::value;
+        const int r = i * TPC + h;
+        double val = 0.0;
+        if (r < N) {
+          // (A L~)[c][r] = sum_k a[ci][k] pinv_k L[k d + cj][r]   (k >= ci, and k d + cj >= r)
+#pragma unroll
+          for (int k = 0; k < n; ++k) {
+            const int row = k * d + cj;
+            if (k >= ci && row >= r) val = fma(c.A[ci][k], c.pinv[k] * Lpk[tri(row, r)], val);
+          }
+        } else if (r < 2 * N) {
+          const int rr = r - N, ri = rr / d, rj = rr % d;
+          val = (cj == rj && ci >= ri) ? s * c.Qm[ci][ri] * c.lam[cj] : 0.0;
+        }
+        col[i] = val;
+      });
     }
-    for (int e = threadIdx.x; e < d * ld; e += G) {
-      const int r = e / ld, c = e % ld;
-      W[(N + r) * ld + c] = (c == r) ? damp : 0.0;
+    column_qr<2 * N, N, N, N>(col, c.pos_pred, c.h, [](int j) { return j * TPC; }, c.rbuf);
+    if (c.is_state) {
+      const double pc = fabs(c.p[c.ci]);
+      static_for<0, RPT>([&](auto ic_) { col[decltype(ic_)::value] *= pc; });
+    }
+  }
+
+  // With rows 0..N-1 of the state columns holding U = L^T (upper triangular), fill the observation columns with
+  // [(H L)^T ; damp I] and triangularise the (N + d)-row stack, observation columns first. Afterwards R_Y is in RY,
+  // R12 in rows 0..d-1 of the state columns, R_XY in their rows d..d+N-1.
+  PDEQ_DI static void revert_stack(const Ctx& c, double (&col)[RPT], double damp) {
+    constexpr int d = D, hw = HW;
+    const int h = c.h, cp = c.cp, oa = c.oa;
+    if (c.is_state && cp < hw) {  // publish rows 0..cp of the first hw columns of U
+      static_for<0, (hw + TPC - 1) / TPC>([&](auto ic_) {
+        constexpr int i = decltype(ic_)::value;
+        const int r = i * TPC + h;
+        if (r <= cp && r < hw) c.Ush[cp * hw + r] = col[i];
+      });
+    }
+    if (c.is_state) {  // rows N.. of the state columns belong to the damp block: zero
+      static_for<0, RPT>([&](auto ic_) {
+        constexpr int i = decltype(ic_)::value;
+        col[i] = (i * TPC + h >= N) ? 0.0 : col[i];
+      });
     }
     __syncthreads();
-    coop_qr<N + d, N + d, d, N>(W, red, red + 16);
+    if (c.is_obs) {
+      static_for<0, RPT>([&](auto ic_) {
+        constexpr int i = decltype(ic_)::value;
+        const int r = i * TPC + h;
+        double val = 0.0;
+        if (r < N) {
+          // (H L)[a][r] = sum_e H[a][e] L[e][r], L[e][r] = U[r][e] (e >= r); H touches the first hw coefficients
+          for (int e = r; e < hw; ++e) val = fma(c.Hs[oa * hw + e], c.Ush[e * hw + r], val);
+        } else if (r == N + oa) {
+          val = damp;
+        }
+        col[i] = val;
+      });
+    }
+    column_qr<N + d, N + d, d, N>(col, c.pos_rev, c.h, [](int j) { return (j < D ? N + j : j - D) * TPC; }, c.rbuf);
+    if (c.is_obs) {
+      static_for<0, (d + TPC - 1) / TPC>([&](auto ic_) {
+        constexpr int i = decltype(ic_)::value;
+        const int r = i * TPC + h;
+        if (r < d) c.RY[r * d + oa] = (r <= oa) ? col[i] : 0.0;
+      });
+    }
+    __syncthreads();
+  }
+
+  // gain^T = R_Y^-1 R12 column by column (every lane of a state column solves its own d x d system), then
+  // mean_out = mean_in - gain mobs. `lstsq`: a zero pivot gives a zero gain component (the minimum-norm solution of
+  // linalg.lstsq_svd when the zero pivots are decoupled) -- only the update at t0 can meet one.
+  PDEQ_DI static void apply_gain(const Ctx& c, const double (&col)[RPT], const double* mean_in, double* mean_out,
+                                 bool lstsq) {
+    constexpr int d = D;
+    if (c.is_state) {
+      double r12[d];
+      const int base = (c.tid & 31) & ~(TPC - 1);
+      static_for<0, (d + TPC - 1) / TPC>([&](auto ic_) {
+        constexpr int i = decltype(ic_)::value;
+        static_for<0, TPC>([&](auto pc_) {
+          constexpr int part = decltype(pc_)::value;
+          const double x = __shfl_sync(c.gmask, col[i], base + part);
+          if constexpr (i * TPC + part < d) r12[i * TPC + part] = x;
+        });
+      });
+      static_for<0, d>([&](auto ic_) {
+        constexpr int i = d - 1 - decltype(ic_)::value;
+        double acc = r12[i];
+        static_for<i + 1, d>([&](auto lc_) {
+          constexpr int l = decltype(lc_)::value;
+          acc = fma(-c.RY[i * d + l], r12[l], acc);
+        });
+        const double piv = c.RY[i * d + i];
+        r12[i] = (lstsq && piv == 0.0) ? 0.0 : acc * fast_rcp(piv);
+      });
+      double corr = 0.0;
+      static_for<0, d>([&](auto ac_) {
+        constexpr int a_ = decltype(ac_)::value;
+        corr = fma(r12[a_], c.mobs[a_], corr);
+      });
+      if (c.h == 0) mean_out[c.cp] = mean_in[c.cp] - corr;
+    }
+    __syncthreads();
+  }
+
+  // packed factor <- rows row0..row0+c of state column c (transposed): the accepted R_XY^T, or L_pred^T
+  PDEQ_DI static void store_factor(const Ctx& c, const double (&col)[RPT], double* Lpk, int row0) {
+    if (c.is_state) {
+      const int h = c.h, cp = c.cp;
+      static_for<0, RPT>([&](auto ic_) {
+        constexpr int i = decltype(ic_)::value;
+        const int jj = i * TPC + h - row0;
+        if (jj >= 0 && jj <= cp) Lpk[tri(cp, jj)] = col[i];
+      });
+    }
+  }
+
+  // whitened residual of an observation with upper-triangular factor RY (R^T is the left square root): solve
+  // R^T w = mobs, rms; optionally the row norms of R^T (the marginal standard deviations). One thread.
+  PDEQ_DI static double whiten(const Ctx& c, bool want_std) {
+    constexpr int d = D;
+    double ss = 0.0;
+    for (int i = 0; i < d; ++i) {
+      double acc = c.mobs[i];
+      for (int l = 0; l < i; ++l) acc = fma(-c.RY[l * d + i], c.wht[l], acc);
+      c.wht[i] = acc * fast_rcp(c.RY[i * d + i]);
+      ss = fma(c.wht[i], c.wht[i], ss);
+      if (want_std) {
+        double rn = 0.0;
+        for (int l = 0; l <= i; ++l) rn = fma(c.RY[l * d + i], c.RY[l * d + i], rn);
+        c.stdv[i] = safe_sqrt(rn);
+      }
+    }
+    return safe_sqrt(ss) * c.inv_sqrt_d;
   }
 
   PDEQ_DI static void run(const LoopArgs& a, double* __restrict__ smem) {
@@ -266,25 +401,36 @@ struct DenseLoop {
     const bool clip = cfg.clip_dt != 0;
     const bool needs_interp = adaptive && !clip;
     const int T = a.T;
-    constexpr int d = D;
+    constexpr int d = D, hw = HW;
     const long B = a.prob.num_instances;
     const int max_attempts = cfg.max_attempts > 0 ? cfg.max_attempts : 0x7fffffff;
     const double inv_sqrt_d = rsqrt((double)d);
     const double neg_inv_n = -1.0 / (double)n;
     const int tid = threadIdx.x;
     const DenseSmemLayout lay = DenseSmemLayout::make(n, d, q, needs_interp);
-    constexpr int ld = LD, hw = HW;
 
-    double* W = smem + lay.off_W;
+    // this lane's column: pairs 0..N-1 hold the state columns, pairs N..N+d-1 the observation columns
+    const int cp = tid / TPC, h = tid % TPC;
+    const bool is_state = cp < N, is_obs = cp >= N && cp < LD;
+    const int ci = is_state ? cp / d : 0, cj = is_state ? cp % d : 0;  // coefficient / dimension of a state column
+    const int oa = is_obs ? cp - N : 0;                                 // observation index of an observation column
+    const unsigned gmask = ((1u << TPC) - 1u) << ((tid & 31) & ~(TPC - 1));
+    const int pos_pred = is_state ? cp : -1;                    // extrapolation stack: state columns only
+    const int pos_obs = is_obs ? oa : -1;                       // observation-only stack
+    const int pos_rev = is_state ? d + cp : (is_obs ? oa : -1);  // correction stack: observation columns first
+
     double* Lfrom = smem + lay.off_Lfrom;
     double* Lif = smem + lay.off_Lif;
     double* v = smem + lay.off_vec;
-    double* m_from = v;
-    double* mp = v + N;
-    double* m_new = v + 2 * N;
-    double* m_if = v + 3 * N;
-    double* Hs = v + 4 * N;            // d x (q+1) d: the non-zero columns of the linearisation
-    double* mobs = Hs + d * hw;        // d
+    double* rbuf = v;                  // 2 x RB
+    double* m_from = rbuf + 2 * RB;
+    double* mp = m_from + N;
+    double* m_new = mp + N;
+    double* m_if = m_new + N;
+    double* Hs = m_if + N;             // d x (q+1) d: the non-zero columns of the linearisation
+    double* Ush = Hs + d * hw;         // hw x hw: rows 0..e of the first hw columns of the factor, for (H L)^T
+    double* RY = Ush + hw * hw;        // d x d: R_Y (correction) / R_obs (observation-only), row-major upper
+    double* mobs = RY + d * d;         // d
     double* wht = mobs + d;            // d: whitened residual
     double* stdv = wht + d;            // d: error estimate per dimension
     double* refv = stdv + d;           // d
@@ -292,23 +438,23 @@ struct DenseLoop {
     double* p = lam + d;               // 8
     double* pinv = p + 8;              // 8
     double* red = pinv + 8;            // 8
-    double* bc = red + 8;              // 8: broadcast slots; red + 16: N + d new diagonal entries (coop_qr)
+    double* bc = red + 8;              // 8: broadcast slots
 
-#ifdef PDEQ_K3_PROFILE
-    // phase cycle counters (development aid): totals per instance go to the first 8 trace slots
-    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, prof_last = clock64();
-#define PDEQ_K3_TICK(i) { const long long now_ = clock64(); prof_acc[i] += now_ - prof_last; prof_last = now_; }
-#define PDEQ_K3_DUMP if (tid == 0 && a.sol.trace != nullptr && a.sol.trace_capacity >= 2) { \
-      for (int i_ = 0; i_ < 8; ++i_) { a.sol.trace[b * a.sol.trace_capacity * 4 + i_] = (double)prof_acc[i_]; prof_acc[i_] = 0; } }
-#else
-#define PDEQ_K3_TICK(i)
-#define PDEQ_K3_DUMP
-#endif
+    double col[RPT];  // this lane's rows of its column
     double params[P];
     double t = 0.0, dt = 0.0, ctrl_lprev = 0.0, ndata = 0.0, t_next = 0.0, t_if = 0.0, sig = 1.0, run_scale = 0.0;
     int nsteps = 0, nattempts = 0, ck = 0, status = 0;
     long b = -1;
     bool need_load = true;
+
+    Ctx cx;
+    cx.tid = tid; cx.cp = cp; cx.h = h; cx.ci = ci; cx.cj = cj; cx.oa = oa;
+    cx.pos_pred = pos_pred; cx.pos_obs = pos_obs; cx.pos_rev = pos_rev;
+    cx.is_state = is_state; cx.is_obs = is_obs; cx.gmask = gmask; cx.inv_sqrt_d = inv_sqrt_d;
+    cx.A = A; cx.Qm = Qm; cx.rbuf = rbuf; cx.Hs = Hs; cx.Ush = Ush; cx.RY = RY; cx.mobs = mobs; cx.wht = wht;
+    cx.stdv = stdv; cx.lam = lam; cx.p = p; cx.pinv = pinv;
+
+    static_for<0, RPT>([&](auto ic_) { col[decltype(ic_)::value] = 0.0; });
 
     while (true) {
       if (need_load) {
@@ -317,6 +463,7 @@ struct DenseLoop {
         __syncthreads();
         b = reinterpret_cast<long*>(bc)[0];
         if (b >= B) break;
+        if (a.prob.order != nullptr) b = (long)a.prob.order[b];  // service order (pdeq_problem.order)
         need_load = false;
 #pragma unroll
         for (int k = 0; k < P; ++k)
@@ -340,7 +487,24 @@ struct DenseLoop {
         sig = 1.0;
         run_scale = 0.0;
         __syncthreads();
-        emit(a, b, 0, lay, t, m_from, Lfrom, 1.0, 1.0, 0);
+        if (cfg.constraint_init != 0) {
+          // solver.init with constraint_init (solvers.py:361-372, 526-537, 670-680): condition the initial state on a
+          // zero residual of the constraint linearised at it
+          if (is_state) {
+            static_for<0, RPT>([&](auto ic_) {
+              constexpr int i = decltype(ic_)::value;
+              const int r = i * TPC + h;  // U = L^T of the (diagonal) initial factor
+              col[i] = (r <= cp && r < N) ? Lfrom[tri(cp, r)] : 0.0;
+            });
+          }
+          linearise_at(cx, m_from, t, params);
+          revert_stack(cx, col, a.damp);
+          apply_gain(cx, col, m_from, m_new, true);
+          for (int e = tid; e < N; e += G) m_from[e] = m_new[e];
+          store_factor(cx, col, Lfrom, d);
+          __syncthreads();
+        }
+        emit(a, b, 0, t, m_from, Lfrom, 1.0, 1.0, 0);
         if (needs_interp) {
           for (int e = tid; e < N; e += G) m_if[e] = m_from[e];
           for (int e = tid; e < TRI_N; e += G) Lif[e] = Lfrom[e];
@@ -373,17 +537,15 @@ struct DenseLoop {
               for (int k = i; k < n; ++k) acc = fma(A[i][k], pinv[k] * m_if[k * d + jd], acc);
               mp[e] = p[i] * acc;
             }
-            extrapolate_chol(W, lay, Lif, p, pinv, lam, safe_sqrt(fabs(dti)) * sig, A, Qm, red);
-            for (int e = tid; e < N * N; e += G) {
-              const int jj = e / N, i = e % N;  // L[i][jj] = W[jj][d + i], lower triangle only
-              if (jj <= i) Lif[tri(i, jj)] = W[jj * ld + d + i];
-            }
+            extrapolate_chol(cx, col, Lif, safe_sqrt(fabs(dti)) * sig);
+            __syncthreads();
+            store_factor(cx, col, Lif, 0);
             for (int e = tid; e < N; e += G) m_if[e] = mp[e];
             __syncthreads();
-            emit(a, b, ck, lay, t_next, m_if, Lif, 1.0, sig, nsteps);
+            emit(a, b, ck, t_next, m_if, Lif, 1.0, sig, nsteps);
             t_if = t_next;
           } else {
-            emit(a, b, ck, lay, t, m_from, Lfrom, 1.0, sig, nsteps);
+            emit(a, b, ck, t, m_from, Lfrom, 1.0, sig, nsteps);
             if (needs_interp) {
               for (int e = tid; e < N; e += G) m_if[e] = m_from[e];
               for (int e = tid; e < TRI_N; e += G) Lif[e] = Lfrom[e];
@@ -411,7 +573,6 @@ struct DenseLoop {
           for (int e = tid; e < N; e += G) bad += isfinite(m_from[e]) ? 0.0 : 1.0;
           bad = block_sum(bad, red);
           if (status == 0 && bad > 0.0) status = PDEQ_STATUS_NONFINITE;
-          PDEQ_K3_DUMP
           if (tid == 0) {
             a.sol.status[b] = status;
             if (a.sol.num_attempts != nullptr) a.sol.num_attempts[b] = nattempts;
@@ -424,7 +585,6 @@ struct DenseLoop {
 
       // ------------------------------------------------------------------ one step attempt
       nattempts += 1;
-      PDEQ_K3_TICK(0)
       double dtc;
       if (adaptive) {
         dtc = clip ? fmin(dt, t_next - t) : dt;
@@ -452,132 +612,81 @@ struct DenseLoop {
       }
       __syncthreads();
 
-      // linearise at the extrapolated mean
-      for (int e = tid; e < d * hw; e += G) Hs[e] = 0.0;
-      __syncthreads();
-      {
-        VecAcc acc{mp, d};
-        for (int jd = tid; jd < d; jd += G) {
-          const double f = VF::template component<double>(jd, d, acc, params, t_new);
-          Hs[jd * hw + q * d + jd] = 1.0;
-          if (TS0) {
-            mobs[jd] = mp[q * d + jd] + (-f);
-          } else {
-            const double rres = mp[q * d + jd] - f;
-            double hm = mp[q * d + jd];
-            for (int c = 0; c < q; ++c) {
-              for (int l = 0; l < d; ++l) {
-                const double hv = -VF::jac(jd, c, l, d, acc, params, t_new);
-                Hs[jd * hw + c * d + l] = hv;
-                hm = fma(hv, mp[c * d + l], hm);
-              }
-            }
-            mobs[jd] = hm + (rres - hm);
-          }
-        }
-      }
-      __syncthreads();
+      linearise_at(cx, mp, t_new, params);
 
-      PDEQ_K3_TICK(1)
       // observation of the zero-error extrapolation: R_obs = qr_r([(H L_u)^T ; damp I]) (solver_dynamic, residual error)
       const bool need_obs = adaptive ? (cfg.solver == PDEQ_SOLVER_DYNAMIC || cfg.error == PDEQ_ERROR_RESIDUAL_STD)
                                      : (cfg.solver == PDEQ_SOLVER_DYNAMIC);
       double sig_new = 1.0, whitened_obs = 0.0;
       if (need_obs) {
-        // (H L_u)[a][k d + l] = sum_{i >= k} H[a][i d + l] |p_i| sq q[i][k] lam_l
-        for (int e = tid; e < N * d; e += G) {
-          const int r = e / d, a_ = e % d;
-          const int k = r / d, l = r % d;
-          double acc = 0.0;
-          for (int i = k; i <= q && i < n; ++i) acc = fma(Hs[a_ * hw + i * d + l], fabs(p[i]) * sq * Qm[i][k], acc);
-          W[r * ld + a_] = acc * lam[l];
+        if (is_obs) {
+          static_for<0, RPT>([&](auto ic_) {
+            constexpr int i = decltype(ic_)::value;
+            const int r = i * TPC + h;
+            double val = 0.0;
+            if (r < N) {
+              // (H L_u)[a][k d + l] = sum_{i >= k} H[a][i d + l] |p_i| sq q[i][k] lam_l
+              const int k = r / d, l = r % d;
+              for (int ii = k; ii <= q && ii < n; ++ii) val = fma(Hs[oa * hw + ii * d + l], fabs(p[ii]) * sq * Qm[ii][k], val);
+              val *= lam[l];
+            } else if (r == N + oa) {
+              val = a.damp;
+            }
+            col[i] = val;
+          });
         }
-        for (int e = tid; e < d * d; e += G) W[(N + e / d) * ld + (e % d)] = (e / d == e % d) ? a.damp : 0.0;
+        column_qr<N + d, d, d, N>(col, pos_obs, h, [](int j) { return (N + j) * TPC; }, rbuf);
+        if (is_obs) {
+          static_for<0, (d + TPC - 1) / TPC>([&](auto ic_) {
+            constexpr int i = decltype(ic_)::value;
+            const int r = i * TPC + h;
+            if (r < d) RY[r * d + oa] = (r <= oa) ? col[i] : 0.0;
+          });
+        }
         __syncthreads();
-        coop_qr<N + d, d, 0, 0>(W, red, red + 16);
-        if (tid == 0) {
-          // whitened residual: solve R_obs^T w = mobs (forward substitution), rms; and the row norms of R_obs^T
-          double ss = 0.0;
-          for (int i = 0; i < d; ++i) {
-            double acc = mobs[i];
-            for (int l = 0; l < i; ++l) acc = fma(-W[l * ld + i], wht[l], acc);
-            wht[i] = acc * fast_rcp(W[i * ld + i]);
-            ss = fma(wht[i], wht[i], ss);
-            double rn = 0.0;
-            for (int l = 0; l <= i; ++l) rn = fma(W[l * ld + i], W[l * ld + i], rn);
-            stdv[i] = safe_sqrt(rn);
-          }
-          bc[1] = safe_sqrt(ss) * inv_sqrt_d;
-        }
+        if (tid == 0) bc[1] = whiten(cx, true);
         __syncthreads();
         whitened_obs = bc[1];
         if (cfg.solver == PDEQ_SOLVER_DYNAMIC) sig_new = whitened_obs;
       }
 
       if (adaptive && cfg.error != PDEQ_ERROR_RESIDUAL_STD) {
-        // error_state_std (solvers.py:1070-1086): Bayes rule on the zero-error extrapolation. Done first because
-        // it needs the work buffer, which afterwards holds the proposal until the step is accepted or rejected.
+        // error_state_std (solvers.py:1070-1086): Bayes rule on the zero-error extrapolation. Done first because it
+        // needs the column registers, which afterwards hold the proposal until the step is accepted or rejected.
         const int idx = cfg.derivative_idx;
-        for (int e = tid; e < N * N; e += G) {
-          const int r = e / N, c = e % N;  // U = L_u^T: U[r][c] = L_u[c][r], block lower in (ci >= ri), same l
-          const int ci = c / d, cj = c % d, ri = r / d, rj = r % d;
-          W[r * ld + d + c] = (cj == rj && ci >= ri) ? fabs(p[ci]) * sq * Qm[ci][ri] * lam[cj] : 0.0;
+        if (is_state) {
+          static_for<0, RPT>([&](auto ic_) {
+            constexpr int i = decltype(ic_)::value;
+            const int r = i * TPC + h;  // U = L_u^T: U[r][c] = L_u[c][r], block lower in (ci >= ri), same dimension
+            const int ri = r / d, rj = r % d;
+            col[i] = (r < N && cj == rj && ci >= ri) ? fabs(p[ci]) * sq * Qm[ci][ri] * lam[cj] : 0.0;
+          });
         }
+        revert_stack(cx, col, a.damp);
+        if (tid == 0) bc[3] = whiten(cx, false);
         __syncthreads();
-        revert_stack(W, lay, Hs, a.damp, red);
-        if (tid == 0) {
-          double ss = 0.0;
-          for (int i = 0; i < d; ++i) {
-            double acc = mobs[i];
-            for (int l = 0; l < i; ++l) acc = fma(-W[l * ld + i], wht[l], acc);
-            wht[i] = acc * fast_rcp(W[i * ld + i]);
-            ss = fma(wht[i], wht[i], ss);
-          }
-          bc[3] = safe_sqrt(ss) * inv_sqrt_d;
-        }
-        __syncthreads();
-        for (int e = tid; e < d; e += G) {
-          const int col = idx * d + e;  // std of coefficient idx, dimension e: column norm of R_XY
+        if (is_state && ci == idx) {
+          // std of coefficient idx, dimension cj: norm of rows d..d+cp of this column (R_XY)
           double rn = 0.0;
-          for (int r = 0; r <= col; ++r) rn = fma(W[(d + r) * ld + d + col], W[(d + r) * ld + d + col], rn);
-          stdv[e] = bc[3] * safe_sqrt(rn);
+          static_for<0, RPT>([&](auto ic_) {
+            constexpr int i = decltype(ic_)::value;
+            const int r = i * TPC + h;
+            rn = (r >= d && r <= d + cp) ? fma(col[i], col[i], rn) : rn;
+          });
+          rn = group_sum(rn, gmask);
+          if (h == 0) stdv[cj] = bc[3] * safe_sqrt(rn);
         }
         __syncthreads();
       }
 
-      // extrapolate the factor, correct
-      PDEQ_K3_TICK(2)
-      extrapolate_chol(W, lay, Lfrom, p, pinv, lam, sq * sig_new, A, Qm, red);
-      PDEQ_K3_TICK(3)
-      revert_stack(W, lay, Hs, a.damp, red);
-      PDEQ_K3_TICK(4)
-      // gain^T = R_Y^-1 R12 (d x N), in place over R12; one column per thread
-      for (int c = tid; c < N; c += G) {
-        for (int i = d - 1; i >= 0; --i) {
-          double acc = W[i * ld + d + c];
-          for (int l = i + 1; l < d; ++l) acc = fma(-W[i * ld + l], W[l * ld + d + c], acc);
-          W[i * ld + d + c] = acc * fast_rcp(W[i * ld + i]);
-        }
-      }
-      __syncthreads();
-      for (int e = tid; e < N; e += G) {
-        double acc = mp[e];
-        for (int a_ = 0; a_ < d; ++a_) acc = fma(-W[a_ * ld + d + e], mobs[a_], acc);
-        m_new[e] = acc;
-      }
-      // the proposal's factor stays in W (rows / columns d .. d+N) until the step is accepted
+      // extrapolate the factor, correct; the proposal's factor stays in the column registers until the step is
+      // accepted or rejected
+      extrapolate_chol(cx, col, Lfrom, sq * sig_new);
+      revert_stack(cx, col, a.damp);
+      apply_gain(cx, col, mp, m_new, false);
       double run_new = run_scale;
       if (cfg.solver == PDEQ_SOLVER_MLE) {
-        if (tid == 0) {
-          double ss = 0.0;
-          for (int i = 0; i < d; ++i) {
-            double acc = mobs[i];
-            for (int l = 0; l < i; ++l) acc = fma(-W[l * ld + i], wht[l], acc);
-            wht[i] = acc * fast_rcp(W[i * ld + i]);
-            ss = fma(wht[i], wht[i], ss);
-          }
-          bc[2] = safe_sqrt(ss) * inv_sqrt_d;
-        }
+        if (tid == 0) bc[2] = whiten(cx, false);
         __syncthreads();
         const double w1 = sqrt(ndata / (ndata + 1.0)), w2 = sqrt(1.0 / (ndata + 1.0));
         const double x1 = w1 * run_scale, x2 = w2 * bc[2];
@@ -585,7 +694,6 @@ struct DenseLoop {
       }
       __syncthreads();
 
-      PDEQ_K3_TICK(5)
       // ------------------------------------------------------------------ error estimate + control
       bool accept = true;
       double dt_next = dt;
@@ -599,8 +707,7 @@ struct DenseLoop {
           }
           kpow = q;
         } else {
-          // error_state_std (solvers.py:1070-1086): Bayes rule on the zero-error extrapolation
-          idx = cfg.derivative_idx;  // stdv was computed ahead of the extrapolation (W is the proposal's home)
+          idx = cfg.derivative_idx;  // stdv was computed ahead of the extrapolation
           for (int e = tid; e < d; e += G) refv[e] = fmax(fabs(m_from[idx * d + e]), fabs(m_new[idx * d + e]));
           kpow = idx;
         }
@@ -657,7 +764,6 @@ struct DenseLoop {
       }
 
       // ------------------------------------------------------------------ commit
-      PDEQ_K3_TICK(6)
       dt = dt_next;
       if (accept) {
         if (needs_interp) {
@@ -667,10 +773,7 @@ struct DenseLoop {
         }
         __syncthreads();
         for (int e = tid; e < N; e += G) m_from[e] = m_new[e];
-        for (int e = tid; e < N * N; e += G) {
-          const int jj = e / N, i = e % N;
-          if (jj <= i) Lfrom[tri(i, jj)] = W[(d + jj) * ld + d + i];
-        }
+        store_factor(cx, col, Lfrom, d);
         if (cfg.solver == PDEQ_SOLVER_DYNAMIC) sig = sig_new;
         run_scale = run_new;
         ndata += 1.0;
@@ -678,7 +781,7 @@ struct DenseLoop {
         nsteps += 1;
         __syncthreads();
         if (!adaptive) {
-          emit(a, b, ck, lay, t, m_from, Lfrom, 1.0, sig, nsteps);
+          emit(a, b, ck, t, m_from, Lfrom, 1.0, sig, nsteps);
           ck += 1;
         }
       }
@@ -687,7 +790,8 @@ struct DenseLoop {
 };
 
 template <class VF, int NU, bool TS0>
-__global__ void __launch_bounds__(K3_THREADS, 4) k3_loop_kernel(const __grid_constant__ LoopArgs a) {
+__global__ void __launch_bounds__(DenseSmemLayout::threads((NU + 1) * VF::fixed_dim, VF::fixed_dim), 3)
+    k3_loop_kernel(const __grid_constant__ LoopArgs a) {
   extern __shared__ double smem_k3[];
   DenseLoop<VF, NU, TS0>::run(a, smem_k3);
 }

@@ -20,6 +20,7 @@
 // a proposal lives in registers (one dimension per lane) or thread-local scratch (several).
 #pragma once
 
+#include "pdeq_limits.cuh"
 #include "pdeq_loop_thread.cuh"
 
 namespace pdeq {
@@ -27,8 +28,6 @@ namespace pdeq {
 #ifndef PDEQ_K2_WARP_FILTER_BLOCKS
 #define PDEQ_K2_WARP_FILTER_BLOCKS 3  // resident 128-thread CTAs per SM of the warp-mode filter kernels (<= 168 registers)
 #endif
-constexpr int K2_MAX_DPL = 4;       // dimensions per lane in CTA mode
-constexpr int K2_CTA_THREADS = 256;  // upper bound of a CTA-mode block
 
 // MODE 0: a warp per instance (d <= 32). MODE 1: a CTA per instance, one dimension per lane (d <= 256).
 // MODE 2: a CTA per instance, up to K2_MAX_DPL dimensions per lane (d <= 1024); its proposal arrays cost ~160
@@ -356,6 +355,7 @@ struct GroupLoop {
         if (g.lane == 0) nb = (long)atomicAdd(a.work_counter, 1ULL);
         b = g.bcast_long(nb);
         if (b >= B) break;
+        if (a.prob.order != nullptr) b = (long)a.prob.order[b];  // service order (pdeq_problem.order)
         need_load = false;
 #pragma unroll
         for (int k = 0; k < P; ++k)
@@ -379,18 +379,70 @@ struct GroupLoop {
           double prior = 1.0;
           if (a.prob.prior_scale != nullptr)
             prior = a.prob.prior_scale[b * a.prob.prior_scale_stride + (ISO ? 0 : j)];
-          emit(a, b, 0, d, j, t, m, L, 1.0, 0);
           st_store(st_from, d, j, m, L);
           st_from[F_SIG * d + j] = 1.0;
           st_from[F_RUN * d + j] = 0.0;
           st_from[F_PRIOR * d + j] = prior;
-          if (needs_interp) st_store(st_if, d, j, m, L);
           if (FP) {
             BlockCond<n> c;
             cond_identity<n>(c);
             cond_store(st_from + F_G * d, d, j, c);
             if (needs_interp) cond_store(st_if + F_G * d, d, j, c);
           }
+        }
+        if (cfg.constraint_init != 0) {
+          // solver.init with constraint_init (solvers.py:361-372, 526-537, 670-680): condition the initial state on a
+          // zero residual of the constraint linearised at it; a zero observed factor gives a zero gain (lstsq_svd)
+          g.sync();
+          for (int r = 0; r < nrounds; ++r) {
+            const int j = g.lane + r * g.size;
+            if (j >= d) continue;
+#pragma unroll
+            for (int c = 0; c < q; ++c) exch[c * d + j] = st_from[(F_M + c) * d + j];
+          }
+          g.sync();
+          for (int r = 0; r < MAXR; ++r) {
+            if (r >= nrounds) break;
+            const int j = g.lane + r * g.size;
+            const bool active = j < d;
+            if (!active && !ISO) continue;
+            const int jj = active ? j : 0;
+            double m[n], L[n][n], h[q + 1], mobs;
+            st_load(st_from, d, jj, m, L);
+            ExchAcc acc{exch, d};
+            const double f = VF::template component<double>(jj, d, acc, params, t);
+            if (TS0) {
+#pragma unroll
+              for (int c = 0; c <= q; ++c) h[c] = (c == q) ? 1.0 : 0.0;
+              mobs = m[q] + (-f);
+            } else {
+#pragma unroll
+              for (int c = 0; c < q; ++c) {
+                const double jd = -VF::jac(jj, c, jj, d, acc, params, t);
+                h[c] = ISO ? g.sum(active ? jd : 0.0) / (double)d : jd;
+              }
+              h[q] = 1.0;
+              const double rres = m[q] - f;
+              double hm = 0.0;
+#pragma unroll
+              for (int c = 0; c <= q; ++c) hm = fma(h[c], m[c], hm);
+              mobs = hm + (rres - hm);
+            }
+            double ry0, gain0[n], Ln0[n][n];
+            revert_obs<n, q, TS0>(L, h, a.damp, ry0, gain0, Ln0);
+#pragma unroll
+            for (int i = 0; i < n; ++i) m[i] = (ry0 == 0.0) ? m[i] : fma(-gain0[i], mobs, m[i]);
+            if (active) st_store(st_from, d, j, m, Ln0);
+          }
+          g.sync();
+        }
+        for (int r = 0; r < nrounds; ++r) {
+          const int j = g.lane + r * g.size;
+          if (j >= d) continue;
+          double m[n], L[n][n];
+          st_load(st_from, d, j, m, L);
+          emit(a, b, 0, d, j, t, m, L, 1.0, 0);
+          if (needs_interp) st_store(st_if, d, j, m, L);
         }
         dt = adaptive ? a.dt0[b * a.dt0_stride] : 0.0;
         ctrl_lprev = 0.0;

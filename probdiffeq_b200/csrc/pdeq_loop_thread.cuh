@@ -36,20 +36,7 @@ struct LoopArgs {
   const double* dt0;
   int64_t dt0_stride;
   unsigned long long* work_counter;  // zero-initialised by the host wrapper
-  // Tail compaction of the thread-per-instance kernel (K1, see ThreadLoop::run): once the queue of fresh instances
-  // is empty, warps that are no longer full park their unfinished instances in a pool and re-form as full warps.
-  // ctl = work_counter: [0] fresh-instance counter, [POOL_HEAD] / [POOL_TAIL] of the ticket ring, [POOL_DONE]
-  // finished instances -- 64 bytes apart, all zeroed by the host wrapper. ring: zero-initialised tickets (slot + 1).
-  // slots: [field][num_slots] parked states. slots == nullptr switches the compaction off.
-  unsigned int* pool_ring;
-  unsigned int pool_ring_mask;
-  double* pool_slots;
-  int64_t pool_num_slots;
-  int32_t pool_seg_len;      // loop iterations between two visits of a warp to the pool
-  int32_t pool_dissolve;     // a warp with fewer unfinished instances than this parks them all
-  int32_t pool_patience_ns;  // an empty warp takes a batch of < 32 only after it has been on offer this long
 };
-constexpr int POOL_HEAD = 8, POOL_TAIL = 16, POOL_DONE = 24;  // indices into the 256-byte header (unsigned long long)
 
 constexpr int K1_THREADS = 128;
 // Resident CTAs per SM the register allocation is sized for. Measured on the headline kernel (2^20 Lotka-Volterra
@@ -104,9 +91,6 @@ struct ThreadLoop {
   static constexpr int P = VF::num_params > 0 ? VF::num_params : 1;
   static constexpr int IF_SLOTS = n * D + NB * n * n + 1;  // interp_from: mean, chol, t
   static constexpr int NLOW = NB * (n * (n + 1)) / 2;
-  // a parked instance (tail compaction): mean, packed factor, calibration state, 4 scalars, 3 packed integers
-  static constexpr int PARK_BASE = n * D + NLOW + 2 * NB + 7;
-  static constexpr int PARK_SLOTS_MAX = PARK_BASE + IF_SLOTS;
   static_assert(q < n, "need more Taylor coefficients than the ODE order");
 
   PDEQ_DI static constexpr int blk(int j) { return FACT == PDEQ_FACT_BLOCKDIAG ? j : 0; }
@@ -225,6 +209,53 @@ struct ThreadLoop {
     }
   }
 
+  // Linearise the constraint at a mean (ts0: ssm_impl_isotropic.py:304-317 / ssm_impl_blockdiag.py:129-144;
+  // ts1: ssm_impl_isotropic.py:326-355 / ssm_impl_blockdiag.py:153-183): observation rows h (coefficients 0..q of each
+  // block) and the observed mean mobs = h m + bias.
+  PDEQ_DI static void linearise(const double (&mp)[n][D], const double (&params)[P], double t_new, double (&h)[NB][q + 1],
+                                double (&mobs)[D]) {
+    RegAcc acc{mp};
+    double f[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) f[j] = VF::template component<double>(j, D, acc, params, t_new);
+    if (TS0) {
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+#pragma unroll
+        for (int c = 0; c <= q; ++c) h[k][c] = (c == q) ? 1.0 : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < D; ++j) mobs[j] = mp[q][j] + (-f[j]);
+    } else {
+      if (FACT == PDEQ_FACT_BLOCKDIAG) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+#pragma unroll
+          for (int c = 0; c < q; ++c) h[blk(j)][c] = -VF::jac(j, c, j, D, acc, params, t_new);
+          h[blk(j)][q] = 1.0;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < q; ++c) {
+          double tr = 0.0;
+#pragma unroll
+          for (int j = 0; j < D; ++j) tr += -VF::jac(j, c, j, D, acc, params, t_new);
+          h[0][c] = tr / (double)D;
+        }
+        h[0][q] = 1.0;  // trace(I_d) / d
+      }
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        const double r = mp[q][j] - f[j];
+        double hm = 0.0;
+#pragma unroll
+        for (int c = 0; c <= q; ++c) hm = fma(h[blk(j)][c], mp[c][j], hm);
+        const double bias = r - hm;
+        mobs[j] = hm + bias;
+      }
+    }
+  }
+
   PDEQ_DI static void run(const LoopArgs& a, double* __restrict__ smem_if) {
     const pdeq_config& cfg = a.cfg;
     const double(*__restrict__ A)[PDEQ_MAX_COEFFS] = cfg.sys_a;
@@ -252,242 +283,86 @@ struct ThreadLoop {
     int nsteps = 0, nattempts = 0, ck = 0, status = 0;
     long b = -1;
 
-    // ---- scheduling state ----
-    // Phase 1 (fresh instances left): a lane that finishes its instance pulls the next index from the global counter.
-    // Phase 2 (the counter ran past B for some lane of this warp): the FP64 pipe is what this kernel is bound by and a
-    // warp instruction costs the same with 1 or 32 active lanes, so warps should stay full. Every `pool_seg_len` loop
-    // iterations a warp that is no longer full (1) tops its idle lanes up with instances parked in a global pool,
-    // (2) if it is sparse (fewer than `pool_dissolve` instances) parks its own there -- state written to a slot, slot
-    // id pushed on a ticket ring -- and (3) when empty waits for a full batch of 32 (or for a leftover batch nobody
-    // topped up with) until every instance is finished. Results do not depend on which lane runs an instance.
-    constexpr unsigned FULL = 0xffffffffu;
-    const int lane = tid & 31;
-#define ctl (a.work_counter)
-    const bool pooled = a.pool_slots != nullptr;
-    const int nslots = (int)a.pool_num_slots;
-    int slot = blockIdx.x * blockDim.x + tid;  // parking slot; travels with the instance
-    bool have = false, drained = false, settled = false;
-    int seg_left = 0;
-
+    bool need_load = true;
+    // A lane that finishes its instance pulls the next ticket from the global counter, so all 32 lanes of a warp keep
+    // executing the same attempt body on different instances; a lane leaves when the tickets run out. The lanes of a
+    // warp finish at different times, and the ~450 instructions of a switch-over (last checkpoint, status, ticket,
+    // inputs, first checkpoint) are issued for the whole warp each time: 32 times per instance length, ~5 % of the
+    // run (measured: with the instances served in exact order of their attempt counts the lanes of a warp switch
+    // together and a 2^20-instance pass takes 16.4 instead of 17.1 ms). Hiding the memory latency of the switch-over
+    // (ticket drawn ahead, inputs staged with cp.async) changed nothing: it is the instruction issue that costs.
     while (true) {
-      __syncwarp();
-      if (!drained) {
-        // ---------------------------------------------------------------- fetch the next fresh instance
-        if (!have) {
-          b = (long)atomicAdd(ctl, 1ULL);
-          if (b < B) {
-            have = true;
-            const double* tc = a.prob.tcoeffs + b * (n * D);
+      // ------------------------------------------------------------------ fetch the next instance
+      if (need_load) {
+        b = (long)atomicAdd(a.work_counter, 1ULL);
+        if (b >= B) break;
+        if (a.prob.order != nullptr) b = (long)a.prob.order[b];  // service order (pdeq_problem.order)
+        need_load = false;
+        const double* tc = a.prob.tcoeffs + b * (n * D);
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+#pragma unroll
+          for (int j = 0; j < D; ++j) m[i][j] = tc[i * D + j];
+        }
+#pragma unroll
+        for (int k = 0; k < P; ++k)
+          params[k] = (VF::num_params > 0) ? a.prob.params[b * a.prob.params_stride + k] : 0.0;
+        dt = adaptive ? a.dt0[b * a.dt0_stride] : 0.0;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int j = 0; j <= i; ++j) L[k][i][j] = 0.0;
+          }
+        }
+        if (a.prob.init_std != nullptr) {
+          const double* sd = a.prob.init_std + b * a.prob.init_std_stride;
+#pragma unroll
+          for (int k = 0; k < NB; ++k) {
+#pragma unroll
+            for (int i = 0; i < n; ++i) L[k][i][i] = (FACT == PDEQ_FACT_BLOCKDIAG) ? sd[i * D + k] : sd[i];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          prior[k] = (!SP && a.prob.prior_scale != nullptr) ? a.prob.prior_scale[b * a.prob.prior_scale_stride + k] : 1.0;
+          sig[k] = 1.0;
+          run_scale[k] = 0.0;
+        }
+        t = a.grid[0];
+        ctrl_lprev = 0.0;  // log2 of the PI controller's initial state 1.0 (controllers.py:42-44)
+        ndata = 0.0;
+        nsteps = 0;
+        nattempts = 0;
+        status = 0;
+        if (!SP && cfg.constraint_init != 0) {
+          // solver.init with constraint_init (solvers.py:361-372, 526-537, 670-680): condition the initial state on a
+          // zero residual of the constraint linearised at it; a zero observed factor gives a zero gain (lstsq_svd)
+          double h0[NB][q + 1], mobs0[D], gain0[NB][n];
+          linearise(m, params, t, h0, mobs0);
+#pragma unroll
+          for (int k = 0; k < NB; ++k) {
+            double ry0, Ln0[n][n];
+            revert_obs<n, q, TS0>(L[k], h0[k], damp, ry0, gain0[k], Ln0);
 #pragma unroll
             for (int i = 0; i < n; ++i) {
+              gain0[k][i] = (ry0 == 0.0) ? 0.0 : gain0[k][i];
 #pragma unroll
-              for (int j = 0; j < D; ++j) m[i][j] = tc[i * D + j];
+              for (int j = 0; j <= i; ++j) L[k][i][j] = Ln0[i][j];
             }
+          }
 #pragma unroll
-            for (int k = 0; k < NB; ++k) {
+          for (int j = 0; j < D; ++j) {
 #pragma unroll
-              for (int i = 0; i < n; ++i) {
-#pragma unroll
-                for (int j = 0; j <= i; ++j) L[k][i][j] = 0.0;
-              }
-            }
-            if (a.prob.init_std != nullptr) {
-              const double* sd = a.prob.init_std + b * a.prob.init_std_stride;
-#pragma unroll
-              for (int k = 0; k < NB; ++k) {
-#pragma unroll
-                for (int i = 0; i < n; ++i) L[k][i][i] = (FACT == PDEQ_FACT_BLOCKDIAG) ? sd[i * D + k] : sd[i];
-              }
-            }
-#pragma unroll
-            for (int k = 0; k < NB; ++k) {
-              prior[k] = (!SP && a.prob.prior_scale != nullptr) ? a.prob.prior_scale[b * a.prob.prior_scale_stride + k] : 1.0;
-              sig[k] = 1.0;
-              run_scale[k] = 0.0;
-            }
-#pragma unroll
-            for (int k = 0; k < P; ++k)
-              params[k] = (VF::num_params > 0) ? a.prob.params[b * a.prob.params_stride + k] : 0.0;
-            t = a.grid[0];
-            dt = adaptive ? a.dt0[b * a.dt0_stride] : 0.0;
-            ctrl_lprev = 0.0;  // log2 of the PI controller's initial state 1.0 (controllers.py:42-44)
-            ndata = 0.0;
-            nsteps = 0;
-            nattempts = 0;
-            status = 0;
-            emit(a, b, 0, t, m, L, sig, 0);
-            ck = 1;
-            t_next = (T > 1) ? a.grid[1] : t;
-            if (needs_interp) if_store(smem_if, nthreads, tid, m, L, t);
+            for (int i = 0; i < n; ++i) m[i][j] = fma(-gain0[blk(j)][i], mobs0[j], m[i][j]);
           }
         }
-        drained = __any_sync(FULL, !have);
-        seg_left = 0;
+        emit(a, b, 0, t, m, L, sig, 0);
+        ck = 1;
+        t_next = (T > 1) ? a.grid[1] : t;
+        if (needs_interp) if_store(smem_if, nthreads, tid, m, L, t);
       }
-      if (drained) {
-        if (seg_left <= 0) {
-          unsigned hm = __ballot_sync(FULL, have);
-          if (!pooled) {
-            if (hm == 0u) break;  // no compaction: the warp leaves when its last lane is done
-          } else if (hm != FULL) {
-            // ---- 1. top up: idle lanes take parked instances, as many as there are
-            bool done_all = false;
-            int waited_ns = 0, backoff_ns = 500;
-            while (true) {
-              const int k_have = __popc(hm);
-              int got = 0;
-              unsigned long long hbase = 0;
-              if (lane == 0) {
-                unsigned long long h = *(volatile unsigned long long*)(ctl + POOL_HEAD);
-                while (true) {
-                  const unsigned long long tl = *(volatile unsigned long long*)(ctl + POOL_TAIL);
-                  if (tl <= h) break;
-                  const unsigned long long avail = tl - h;
-                  // an EMPTY warp waits for a full batch: taking whatever shows up would spread the remaining
-                  // instances thinly over all the idle warps. A partial batch is taken once it has sat in the pool
-                  // for `patience` (nobody topped up with it): the end of the run.
-                  if (k_have == 0 && avail < 32ULL && waited_ns < a.pool_patience_ns) {
-                    waited_ns += backoff_ns;
-                    break;
-                  }
-                  const unsigned long long want = (unsigned long long)(32 - k_have);
-                  const unsigned long long g = avail < want ? avail : want;
-                  const unsigned long long old = atomicCAS(ctl + POOL_HEAD, h, h + g);
-                  if (old == h) {
-                    got = (int)g;
-                    hbase = h;
-                    break;
-                  }
-                  h = old;
-                }
-                if (got == 0 && k_have == 0 && *(volatile unsigned long long*)(ctl + POOL_TAIL) <= *(volatile unsigned long long*)(ctl + POOL_HEAD))
-                  waited_ns = 0;  // the pool is empty: patience starts when something appears
-              }
-              got = __shfl_sync(FULL, got, 0);
-              hbase = __shfl_sync(FULL, hbase, 0);
-              const unsigned idle_rank = __popc(~hm & ((1u << lane) - 1u));
-              if (!have && (int)idle_rank < got) {
-                unsigned int* e = a.pool_ring + (unsigned)((hbase + idle_rank) & a.pool_ring_mask);
-                unsigned v;
-                while ((v = atomicExch(e, 0u)) == 0u) {
-                }
-                slot = (int)v - 1;
-                __threadfence();
-                const double* sl = a.pool_slots + slot;
-                int f = 0;
-#pragma unroll
-                for (int i = 0; i < n; ++i) {
-#pragma unroll
-                  for (int j = 0; j < D; ++j) m[i][j] = __ldcg(sl + (long)(f++) * nslots);
-                }
-#pragma unroll
-                for (int k = 0; k < NB; ++k) {
-#pragma unroll
-                  for (int i = 0; i < n; ++i) {
-#pragma unroll
-                    for (int j = 0; j <= i; ++j) L[k][i][j] = __ldcg(sl + (long)(f++) * nslots);
-                  }
-                }
-#pragma unroll
-                for (int k = 0; k < NB; ++k) {
-                  sig[k] = __ldcg(sl + (long)(f++) * nslots);
-                  run_scale[k] = __ldcg(sl + (long)(f++) * nslots);
-                }
-                t = __ldcg(sl + (long)(f++) * nslots);
-                dt = __ldcg(sl + (long)(f++) * nslots);
-                ctrl_lprev = __ldcg(sl + (long)(f++) * nslots);
-                ndata = __ldcg(sl + (long)(f++) * nslots);
-                b = (long)__double_as_longlong(__ldcg(sl + (long)(f++) * nslots));
-                const long long w1 = __double_as_longlong(__ldcg(sl + (long)(f++) * nslots));
-                const long long w2 = __double_as_longlong(__ldcg(sl + (long)(f++) * nslots));
-                nsteps = (int)(w1 >> 32);
-                nattempts = (int)(unsigned)(w1 & 0xffffffffLL);
-                ck = (int)(w2 >> 32);
-                status = (int)(unsigned)(w2 & 0xffffffffLL);
-                if (needs_interp) {
-                  for (int e2 = 0; e2 < IF_SLOTS; ++e2) smem_if[e2 * nthreads + tid] = __ldcg(sl + (long)(f + e2) * nslots);
-                }
-#pragma unroll
-                for (int k = 0; k < NB; ++k)
-                  prior[k] = (!SP && a.prob.prior_scale != nullptr) ? a.prob.prior_scale[b * a.prob.prior_scale_stride + k] : 1.0;
-#pragma unroll
-                for (int k = 0; k < P; ++k)
-                  params[k] = (VF::num_params > 0) ? a.prob.params[b * a.prob.params_stride + k] : 0.0;
-                t_next = (ck < T) ? a.grid[ck] : t;
-                have = true;
-              }
-              hm = __ballot_sync(FULL, have);
-              const int k_now = __popc(hm);
-              if (k_have == 0 && k_now > 0 && k_now < 32) settled = true;  // took a leftover batch: keep it
-              // ---- 2. a sparse warp gives its instances away (they top up fuller warps) and goes idle
-              if (k_now > 0 && k_now < a.pool_dissolve && !settled) {
-                if (have) {
-                  double* sl = a.pool_slots + slot;
-                  int f = 0;
-#pragma unroll
-                  for (int i = 0; i < n; ++i) {
-#pragma unroll
-                    for (int j = 0; j < D; ++j) __stcg(sl + (long)(f++) * nslots, m[i][j]);
-                  }
-#pragma unroll
-                  for (int k = 0; k < NB; ++k) {
-#pragma unroll
-                    for (int i = 0; i < n; ++i) {
-#pragma unroll
-                      for (int j = 0; j <= i; ++j) __stcg(sl + (long)(f++) * nslots, L[k][i][j]);
-                    }
-                  }
-#pragma unroll
-                  for (int k = 0; k < NB; ++k) {
-                    __stcg(sl + (long)(f++) * nslots, sig[k]);
-                    __stcg(sl + (long)(f++) * nslots, run_scale[k]);
-                  }
-                  __stcg(sl + (long)(f++) * nslots, t);
-                  __stcg(sl + (long)(f++) * nslots, dt);
-                  __stcg(sl + (long)(f++) * nslots, ctrl_lprev);
-                  __stcg(sl + (long)(f++) * nslots, ndata);
-                  __stcg(sl + (long)(f++) * nslots, __longlong_as_double((long long)b));
-                  __stcg(sl + (long)(f++) * nslots,
-                         __longlong_as_double(((long long)nsteps << 32) | (long long)(unsigned)nattempts));
-                  __stcg(sl + (long)(f++) * nslots, __longlong_as_double(((long long)ck << 32) | (long long)(unsigned)status));
-                  if (needs_interp) {
-                    for (int e2 = 0; e2 < IF_SLOTS; ++e2) __stcg(sl + (long)(f + e2) * nslots, smem_if[e2 * nthreads + tid]);
-                  }
-                  __threadfence();
-                }
-                __syncwarp();
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(ctl + POOL_TAIL, (unsigned long long)k_now);
-                base = __shfl_sync(FULL, base, 0);
-                if (have) {
-                  const unsigned r = __popc(hm & ((1u << lane) - 1u));
-                  unsigned int* e = a.pool_ring + (unsigned)((base + r) & a.pool_ring_mask);
-                  while (atomicCAS(e, 0u, (unsigned)slot + 1u) != 0u) {
-                  }
-                }
-                have = false;
-                hm = 0u;
-              }
-              if (hm != 0u) break;  // there is work: run a segment
-              // ---- 3. nothing to do: finished, or wait for parked instances
-              unsigned long long fin = 0;
-              if (lane == 0) fin = *(volatile unsigned long long*)(ctl + POOL_DONE);
-              fin = __shfl_sync(FULL, fin, 0);
-              if (fin >= (unsigned long long)B) {
-                done_all = true;
-                break;
-              }
-              __nanosleep(backoff_ns);
-              backoff_ns = backoff_ns < 8000 ? 2 * backoff_ns : backoff_ns;
-              waited_ns = __shfl_sync(FULL, waited_ns, 0);
-            }
-            if (done_all) break;  // every instance of the ensemble is finished
-          }
-          seg_left = a.pool_seg_len;
-        }
-        seg_left -= 1;
-      }
-      if (!have) continue;
 
       // ------------------------------------------------------------------ checkpoint reached?
       // adaptive: RejectionLoop.loop's interpolation switch (solvers_via_adaptive_steps.py:241-247)
@@ -556,8 +431,7 @@ struct ThreadLoop {
           if (status == 0 && !finite) status = PDEQ_STATUS_NONFINITE;
           a.sol.status[b] = status;
           if (a.sol.num_attempts != nullptr) a.sol.num_attempts[b] = nattempts;
-          have = false;
-          if (pooled) atomicAdd(ctl + POOL_DONE, 1ULL);
+          need_load = true;
         }
         continue;
       }
@@ -586,52 +460,10 @@ struct ThreadLoop {
         for (int i = 0; i < n; ++i) mp[i][j] = out[i];
       }
 
-      // linearise at the extrapolated mean (ts0: ssm_impl_isotropic.py:304-317 / ssm_impl_blockdiag.py:129-144;
-      // ts1: ssm_impl_isotropic.py:326-355 / ssm_impl_blockdiag.py:153-183)
+      // linearise at the extrapolated mean
       const double t_new = t + dtc;
       double h[NB][q + 1], mobs[D];
-      {
-        RegAcc acc{mp};
-        double f[D];
-#pragma unroll
-        for (int j = 0; j < D; ++j) f[j] = VF::template component<double>(j, D, acc, params, t_new);
-        if (TS0) {
-#pragma unroll
-          for (int k = 0; k < NB; ++k) {
-#pragma unroll
-            for (int c = 0; c <= q; ++c) h[k][c] = (c == q) ? 1.0 : 0.0;
-          }
-#pragma unroll
-          for (int j = 0; j < D; ++j) mobs[j] = mp[q][j] + (-f[j]);
-        } else {
-          if (FACT == PDEQ_FACT_BLOCKDIAG) {
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-#pragma unroll
-              for (int c = 0; c < q; ++c) h[blk(j)][c] = -VF::jac(j, c, j, D, acc, params, t_new);
-              h[blk(j)][q] = 1.0;
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < q; ++c) {
-              double tr = 0.0;
-#pragma unroll
-              for (int j = 0; j < D; ++j) tr += -VF::jac(j, c, j, D, acc, params, t_new);
-              h[0][c] = tr / (double)D;
-            }
-            h[0][q] = 1.0;  // trace(I_d) / d
-          }
-#pragma unroll
-          for (int j = 0; j < D; ++j) {
-            const double r = mp[q][j] - f[j];
-            double hm = 0.0;
-#pragma unroll
-            for (int c = 0; c <= q; ++c) hm = fma(h[blk(j)][c], mp[c][j], hm);
-            const double bias = r - hm;
-            mobs[j] = hm + bias;
-          }
-        }
-      }
+      linearise(mp, params, t_new, h, mobs);
 
       // Cholesky factor of the zero-error extrapolation (process noise only), shared by solver_dynamic and
       // the error estimators
@@ -850,8 +682,6 @@ struct ThreadLoop {
   }
 };
 
-#undef ctl
-
 template <class VF, int NU, int FACT, int D, bool TS0, int SPEC = 0>
 __global__ void __launch_bounds__(K1_THREADS, SPEC != 0 ? PDEQ_K1_SPEC_MIN_BLOCKS(SPEC) : PDEQ_K1_MIN_BLOCKS(FACT)) k1_loop_kernel(const __grid_constant__ LoopArgs a) {
   extern __shared__ double smem_if[];
@@ -864,7 +694,7 @@ inline bool k1_spec_matches(const LoopArgs& a, bool ts0) {
   return ts0 && a.fixed_grid == 0 && c.clip_dt != 0 && c.solver == PDEQ_SOLVER_PLAIN &&
          c.error == PDEQ_ERROR_STATE_STD && c.derivative_idx == 0 && c.error_per_unit_step == 0 &&
          c.error_norm == PDEQ_NORM_SCALE_THEN_RMS && a.damp == 0.0 && c.err_const[0] != 0.0 &&
-         a.prob.prior_scale == nullptr;
+         a.prob.prior_scale == nullptr && c.constraint_init == 0;
 }
 
 }  // namespace pdeq

@@ -102,7 +102,22 @@ def _lower(prior, solver, error, control, clip_dt, max_attempts=0) -> _lib.Confi
     return cfg
 
 
-def _problem(prior, vf):
+def _service_order(cost_hint, B, device):
+    """`cost_hint` (B,): any positive proxy of how expensive each instance is (a previous solve's `num_attempts`, a
+    model of the parameters, ...). The persistent kernels then serve the instances longest-first, which evens out the
+    end of a solve with few instances per lane (pdeq_problem.order). Results do not depend on it."""
+    hint = torch.as_tensor(cost_hint, device=device).reshape(-1)
+    if hint.shape[0] != B:
+        raise ValueError("cost_hint must have one entry per ensemble member.")
+    # Measured on the thread-per-instance kernel (scripts/sweep_k1_order.py): with 2.3 instances per lane the order
+    # is worth 7 %, with 18 per lane the sort costs more than it gains -- many rounds even out by themselves.
+    lanes = torch.cuda.get_device_properties(device).multi_processor_count * 384
+    if B > COST_HINT_MAX_ROUNDS * lanes:
+        return None
+    return torch.argsort(hint, descending=True).to(torch.int32)
+
+
+def _problem(prior, vf, cost_hint=None):
     B = prior.tcoeffs.shape[0]
     params, pstride = vf.params_on_device(B)
     pr = _lib.Problem()
@@ -116,9 +131,12 @@ def _problem(prior, vf):
     )
     pr.params = _pdq._ptr(params)
     pr.params_stride = pstride
-    return pr, (params,)
+    order = None if cost_hint is None or B == 0 else _service_order(cost_hint, B, prior.tcoeffs.device)
+    pr.order = _pdq._ptr(order)
+    return pr, (params, order)
 
 
+COST_HINT_MAX_ROUNDS = 8  # instances per resident lane above which `cost_hint` is ignored
 POSTERIOR_AUTO_BYTES = 2 << 30  # smoothers return their backward conditionals by default up to this size
 
 
@@ -213,7 +231,7 @@ def _workspace(cfg, B, T, device):
 
 
 def _run_adaptive(prior, solver, error, control, clip_dt, save_at, atol, rtol, dt0, eps, damp, *, terminal,
-                  want_chol=True, max_attempts=0, trace_capacity=0, want_posterior=None):  # fmt: skip
+                  want_chol=True, max_attempts=0, trace_capacity=0, want_posterior=None, cost_hint=None):  # fmt: skip
     if control is None:
         control = control_integral()  # solvers_via_adaptive_steps.py:87-90
     cfg = _lower(prior, solver, error, control, clip_dt, max_attempts)
@@ -225,7 +243,7 @@ def _run_adaptive(prior, solver, error, control, clip_dt, save_at, atol, rtol, d
     dt0_t = _pdq._as_device_f64(dt0).reshape(-1)
     if dt0_t.shape[0] not in (1, B):
         raise ValueError("dt0 must be a scalar or have one entry per ensemble member.")
-    pr, keep = _problem(prior, solver.constraint.ode)
+    pr, keep = _problem(prior, solver.constraint.ode, cost_hint)
     so, bufs = _alloc_solution(prior, T, want_chol, trace_capacity,
                                _want_posterior(want_posterior, solver, prior, T, want_chol) and not terminal)
     if B > 0:  # an empty ensemble returns empty arrays (there is nothing to launch)
@@ -244,11 +262,12 @@ def solve_adaptive_terminal_values(solver, error, control=None, clip_dt: bool = 
                                    max_attempts: int = DEFAULT_MAX_ATTEMPTS):
     """reference: _ivpsolve/solvers_via_adaptive_steps.py:16-43."""
 
-    def solve(u, /, *, t0, t1, atol, rtol, dt0=0.1, eps=1e-8, damp=0.0, want_cholesky=True, trace_capacity=0):
+    def solve(u, /, *, t0, t1, atol, rtol, dt0=0.1, eps=1e-8, damp=0.0, want_cholesky=True, trace_capacity=0,
+              cost_hint=None):
         save_at = np.asarray([t0, t1], dtype=np.float64)
         return _run_adaptive(u, solver, error, control, clip_dt, save_at, atol, rtol, dt0, eps, damp,
                              terminal=True, want_chol=want_cholesky, max_attempts=max_attempts,
-                             trace_capacity=trace_capacity)  # fmt: skip
+                             trace_capacity=trace_capacity, cost_hint=cost_hint)  # fmt: skip
 
     return solve
 
@@ -263,10 +282,10 @@ def solve_adaptive_save_at(*, solver, error, control=None, clip_dt: bool = False
         warnings.warn(msg, stacklevel=1)
 
     def solve(u, save_at, atol, rtol, dt0=0.1, eps=1e-8, damp=0.0, want_cholesky=True, trace_capacity=0,
-              want_posterior=None):
+              want_posterior=None, cost_hint=None):
         return _run_adaptive(u, solver, error, control, clip_dt, save_at, atol, rtol, dt0, eps, damp,
                              terminal=False, want_chol=want_cholesky, max_attempts=max_attempts,
-                             trace_capacity=trace_capacity, want_posterior=want_posterior)  # fmt: skip
+                             trace_capacity=trace_capacity, want_posterior=want_posterior, cost_hint=cost_hint)  # fmt: skip
 
     return solve
 

@@ -392,12 +392,20 @@ class _Solver:
     kind = ""
 
     def __init__(self, *, strategy, constraint, constraint_init=None, **options):
-        if constraint_init is not None:
-            raise NotImplementedError("constraint_init is outside the accelerated path.")
         if not isinstance(constraint, _Constraint):
             raise TypeError(constraint)
+        if constraint_init is not None:
+            # reference: solvers.py:361-372, 526-537, 670-680 -- one Bayes update with `constraint_init` at t0. The
+            # kernels run it with the step constraint's own linearisation, so the two must describe the same thing.
+            if not isinstance(constraint_init, _Constraint):
+                raise TypeError(constraint_init)
+            c0, c1 = constraint_init, constraint
+            if c0 is not c1 and not (c0.ode is c1.ode and (c0.kind, c0.factorisation) == (c1.kind, c1.factorisation)):
+                raise NotImplementedError("constraint_init must be the solver's own constraint on the accelerated path.")
+            options = dict(options, constraint_init=1)
         self.strategy = strategy
         self.constraint = constraint
+        self.constraint_init = constraint_init
         self.options = options
 
     @property

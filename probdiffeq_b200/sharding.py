@@ -56,6 +56,51 @@ def unshard(per_rank_values, per_rank_indices):
     return out
 
 
+class QuadraticCostModel:
+    """A cheap predictor of how expensive each ensemble member is, for `solve(..., cost_hint=...)`.
+
+    The number of step attempts of an adaptive solve varies smoothly with the parameters and initial values of the
+    ensemble member. `fit` regresses the attempt counts of a small pilot solve on a quadratic polynomial of the
+    (standardised, by default log-transformed) inputs on the host; `predict` evaluates it for a whole ensemble on the
+    device (a handful of small torch kernels). Only the ORDER of the predictions is used (longest first), so the
+    model needs to rank well, not to be calibrated.
+    """
+
+    def __init__(self, mu, sd, w0, w1, W2, log):
+        self.mu, self.sd, self.w0, self.w1, self.W2, self.log = mu, sd, float(w0), w1, W2, bool(log)
+        self._dev = {}
+
+    @classmethod
+    def fit(cls, inputs: np.ndarray, cost: np.ndarray, log: bool = True) -> "QuadraticCostModel":
+        x = np.asarray(inputs, dtype=np.float64)
+        log = bool(log and np.all(x > 0))
+        z = np.log(x) if log else x
+        mu, sd = z.mean(axis=0), z.std(axis=0)
+        sd = np.where(sd > 0, sd, 1.0)
+        z = (z - mu) / sd
+        F = z.shape[1]
+        iu = np.triu_indices(F)
+        feats = np.concatenate([np.ones((len(z), 1)), z, z[:, iu[0]] * z[:, iu[1]]], axis=1)
+        w, *_ = np.linalg.lstsq(feats, np.asarray(cost, dtype=np.float64), rcond=None)
+        W2 = np.zeros((F, F))
+        W2[iu] = w[1 + F :]
+        W2 = 0.5 * (W2 + W2.T)  # z^T W2 z reproduces the upper-triangular products
+        return cls(mu, sd, w[0], w[1 : 1 + F], W2, log)
+
+    def _on(self, device):
+        key = str(device)
+        if key not in self._dev:
+            f64 = dict(dtype=torch.float64, device=device)
+            self._dev[key] = (torch.as_tensor(self.mu, **f64), torch.as_tensor(1.0 / self.sd, **f64),
+                              torch.as_tensor(self.w1, **f64), torch.as_tensor(self.W2, **f64))  # fmt: skip
+        return self._dev[key]
+
+    def predict(self, inputs: torch.Tensor) -> torch.Tensor:
+        mu, isd, w1, W2 = self._on(inputs.device)
+        z = ((torch.log(inputs) if self.log else inputs) - mu) * isd
+        return torch.addmv(torch.sum((z @ W2) * z, dim=1), z, w1) + self.w0
+
+
 def allreduce_sum(x: torch.Tensor) -> torch.Tensor:
     """Sum over ranks through `torch.distributed` (NCCL on GPUs, gloo on CPU); identity when not distributed."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:

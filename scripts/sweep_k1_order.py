@@ -1,19 +1,21 @@
-"""A/B of the tail compaction of the thread-per-instance kernel (csrc/pdeq_loop_thread.cuh, ThreadLoop::run) on one GPU.
+"""A/B of longest-first service in the thread-per-instance kernel (pdeq_problem.order, `solve(..., cost_hint=)`).
 
 For each ensemble size (2^20 = the whole BASELINE config-2 ensemble on one GPU, 2^17 = its per-GPU share on 8 GPUs, ...)
-the headline solve is timed with the compaction off (PDEQ_K1_POOL=0: a warp runs until its last lane is done) and on
-with several segment lengths (PDEQ_K1_SEG), and every output is compared byte for byte with the run without it: where
-an instance runs must not change a single bit. `strong_eff_vs_2^20` is the throughput relative to the 2^20-instance
-run of the same setting -- the strong-scaling efficiency a GPU of an N-GPU split of the 2^20 ensemble would see.
+the headline solve is timed
+  plain    index order, full grid (what round 1 measured);
+  hint     `cost_hint` from a quadratic cost model fitted on a 4096-instance pilot solve (sharding.QuadraticCostModel):
+           longest-first service; the model evaluation and the sort are inside the timed region;
+  oracle   the same with the TRUE attempt counts of a previous solve as the hint (what a perfect predictor would give);
+and every output is compared byte for byte with the plain run: where and when an instance runs must not change a bit.
+`strong_eff_vs_2^20` = throughput relative to the 2^20-instance run of the same setting.
 
-usage: python scripts/sweep_k1_pool.py [--sizes 1048576,131072] [--segs 16,32,64] [--steps K]
+usage: python scripts/sweep_k1_order.py [--sizes 1048576,131072] [--steps K] [--modes plain,hint,oracle]
 """
 
 from __future__ import annotations
 
 import argparse
 import json
-import os
 import pathlib
 import sys
 
@@ -26,9 +28,9 @@ import numpy as np  # noqa: E402
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--sizes", default="1048576,524288,262144,131072")
-    ap.add_argument("--segs", default="16,32,64")
     ap.add_argument("--steps", type=int, default=6)
-    ap.add_argument("--spec", default=None)
+    ap.add_argument("--modes", default="plain,hint,oracle")
+    ap.add_argument("--pilot", type=int, default=4096)
     args = ap.parse_args()
 
     import torch
@@ -36,8 +38,6 @@ def main() -> None:
     from probdiffeq_b200 import ivpsolve, probdiffeq, problems, sharding
 
     dev = torch.device("cuda", 0)
-    if args.spec is not None:
-        os.environ["PDEQ_K1_SPEC"] = args.spec
     full = 1 << 20
     params_np, u0_np = problems.lotka_volterra_ensemble(full, seed=0)
     perm = sharding.permutation(full, seed=0)
@@ -48,6 +48,7 @@ def main() -> None:
         idx = perm[:B]  # the first rank's shard of the permuted ensemble when 2^20 / B GPUs split it
         params = torch.from_numpy(params_np[idx]).to(dev)
         u0 = torch.from_numpy(u0_np[idx]).to(dev)
+        inputs = torch.cat([params, u0], dim=1)
         vf = probdiffeq.ode("lotka_volterra", params=params)
         tcoeffs, _ = probdiffeq.jetexpand_ode_padded_scan(num=4)(vf, (u0,), t=0.0)
         prior = ssm.prior_wiener_integrated(tcoeffs)
@@ -55,16 +56,26 @@ def main() -> None:
         solver = probdiffeq.solver(strategy=probdiffeq.strategy_filter(), constraint=ts0)
         error = probdiffeq.error_state_std(constraint=ts0)
         solve = ivpsolve.solve_adaptive_terminal_values(solver=solver, error=error,
-                                                        control=ivpsolve.control_proportional_integral())
+                                                        control=ivpsolve.control_proportional_integral())  # fmt: skip
+        kw = dict(t0=0.0, t1=50.0, atol=1e-8, rtol=1e-6)
+        first = solve(prior, **kw)
+        true_cost = first.num_attempts.to(torch.float64)
+        M = min(args.pilot, B)
+        model = sharding.QuadraticCostModel.fit(inputs[:M].cpu().numpy(), true_cost[:M].cpu().numpy())
+        rank_err = float((model.predict(inputs) - true_cost).std().item())
+
+        def run(mode):
+            if mode == "plain":
+                return solve(prior, **kw)
+            if mode == "hint":
+                return solve(prior, cost_hint=model.predict(inputs), **kw)
+            return solve(prior, cost_hint=true_cost, **kw)
+
         ref = None
-        settings = [("off", None)] + [("on", int(s)) for s in args.segs.split(",")]
-        for pool, seg in settings:
-            os.environ["PDEQ_K1_POOL"] = "0" if pool == "off" else "1"
-            if seg is not None:
-                os.environ["PDEQ_K1_SEG"] = str(seg)
+        for mode in args.modes.split(","):
             held = None
             for _ in range(3):
-                cur = solve(prior, t0=0.0, t1=50.0, atol=1e-8, rtol=1e-6)
+                cur = run(mode)
                 flush.fill_(1)
                 held = cur
             del held, cur
@@ -74,7 +85,7 @@ def main() -> None:
                 flush.fill_(0)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                sol = solve(prior, t0=0.0, t1=50.0, atol=1e-8, rtol=1e-6)
+                sol = run(mode)
                 e1.record()
                 evs.append((e0, e1))
             torch.cuda.synchronize()
@@ -84,17 +95,17 @@ def main() -> None:
                 ref = outs
             same = all(torch.equal(a.contiguous().view(torch.uint8), b.contiguous().view(torch.uint8)) for a, b in zip(outs, ref))
             steps = int(sol.num_steps.sum().item())
-            key = (pool, seg)
             rate = steps / (ms * 1e-3)
             if B == full:
-                base[key] = rate
-            line = dict(instances=B, pool=pool, seg=seg, ms=round(ms, 4), accepted_steps=steps, steps_per_s=rate,
-                        failed=int((sol.status != 0).sum().item()), bitwise_equal_to_pool_off=bool(same))
-            if key in base:
-                line["strong_eff_vs_2^20"] = rate / base[key]
+                base[mode] = rate
+            line = dict(instances=B, mode=mode, ms=round(ms, 4), accepted_steps=steps, steps_per_s=rate,
+                        failed=int((sol.status != 0).sum().item()), bitwise_equal_to_first_mode=bool(same),
+                        cost_model_residual_std_attempts=round(rank_err, 2))  # fmt: skip
+            if mode in base:
+                line["strong_eff_vs_2^20"] = rate / base[mode]
+            if "plain" in base:
+                line["eff_vs_plain_2^20"] = rate / base["plain"]
             print(json.dumps(line), flush=True)
-    os.environ.pop("PDEQ_K1_POOL", None)
-    os.environ.pop("PDEQ_K1_SEG", None)
 
 
 if __name__ == "__main__":

@@ -36,7 +36,8 @@ def _build(mod_pdq, mod_ivp, s, vf):
     else:
         strat = {"filter": mod_pdq.strategy_filter, "fixedpoint": mod_pdq.strategy_smoother_fixedpoint,
                  "fixedinterval": mod_pdq.strategy_smoother_fixedinterval}[s["strategy"]]()
-    solver = getattr(mod_pdq, s["solver"])(strategy=strat, constraint=cons)
+    extra = {"constraint_init": cons} if s.get("constraint_init") else {}
+    solver = getattr(mod_pdq, s["solver"])(strategy=strat, constraint=cons, **extra)
     norm = getattr(mod_pdq, "error_norm_" + s["error_norm"])()
     if s["error"] == "state_std":
         err = mod_pdq.error_state_std(constraint=cons, error_norm=norm, derivative_idx=s["derivative_idx"],
@@ -66,10 +67,13 @@ def oracle_solve_save_at(s, tcoeffs, params, save_at, atol, rtol, dt0=0.1, init_
     return solve(prior, save_at=save_at, atol=atol, rtol=rtol, dt0=dt0), trace
 
 
-def oracle_solve_fixed(s, tcoeffs, params, grid, output_scale=None):
+def oracle_solve_fixed(s, tcoeffs, params, grid, output_scale=None, init_std=None):
     vf = oracle_vf(s, params)
     ssm, solver, _err, _ctrl = _build(o_pdq, o_ivp, s, vf)
-    prior = ssm.prior_wiener_integrated(tcoeffs, output_scale=output_scale)
+    if init_std is None:
+        prior = ssm.prior_wiener_integrated(tcoeffs, output_scale=output_scale)
+    else:
+        prior = ssm.prior_wiener_integrated_diffuse(tcoeffs, init_std, output_scale=output_scale)
     import warnings
 
     with warnings.catch_warnings():

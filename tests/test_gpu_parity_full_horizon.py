@@ -64,4 +64,7 @@ def test_chaotic_configs_track_the_oracle_as_long_as_the_oracle_tracks_itself(re
         assert t["max_rel_divergent"] <= max(TOL, 20.0 * spread), (t, spread)
     # attempts in total: within the perturbed oracle's own variation
     assert abs(res["attempts_total_kernel"] - res["attempts_total_oracle"]) <= 0.02 * res["attempts_total_oracle"]
-    assert res["lockstep_fixed_grid"]["max_rel_mean_coeff0"] <= 1e-6
+    # lock-step over the oracle's accepted grid; a scalar solution that crosses zero (Van der Pol) has no pointwise
+    # relative error, so 4b is held to the error against the size of the trajectory
+    key = "max_err_coeff0_over_trajectory_scale" if name == "4b" else "max_rel_mean_coeff0"
+    assert res["lockstep_fixed_grid"][key] <= 1e-6, res["lockstep_fixed_grid"]

@@ -27,9 +27,9 @@ def test_library_exports_every_symbol_the_header_declares():
 
 
 def test_struct_layouts_match_the_header():
-    # sizes computed from the C declarations: 16 int32 + 5 double + 2*64 double + 3*9 double
-    assert C.sizeof(_lib.Config) == 16 * 4 + 5 * 8 + 2 * 64 * 8 + 3 * 9 * 8
-    assert C.sizeof(_lib.Problem) == 8 * 8
+    # sizes computed from the C declarations: 18 int32 + 5 double + 2*64 double + 3*9 double
+    assert C.sizeof(_lib.Config) == 18 * 4 + 5 * 8 + 2 * 64 * 8 + 3 * 9 * 8
+    assert C.sizeof(_lib.Problem) == 9 * 8
     assert C.sizeof(_lib.Solution) == 14 * 8  # 13 pointers + trace_capacity
 
 

@@ -461,3 +461,76 @@ def test_re_linearize_flags_change_nothing_for_prior_taylor_points(fact, constra
     else:
         for a, b in zip(base, with_solver_flag):
             assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------
+# constraint_init: the Bayes update at t0 (solvers.py:361-372, 526-537, 670-680)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["isotropic", "blockdiag", "dense"])
+@pytest.mark.parametrize("solver_name", ["solver", "solver_mle", "solver_dynamic"])
+def test_constraint_init_pins_the_first_derivative_of_a_diffuse_prior(kind, solver_name):
+    """What tests/test_probdiffeq/test_solver_uses_constraint_init.py checks for jet-lifted residuals, for the ODE
+    constraint itself: with an exact u0 and diffuse derivatives, conditioning on u' - f(u0) = 0 at t0 makes the mean
+    of coefficient 1 equal f(u0) and removes its uncertainty; the other diffuse coefficients stay diffuse."""
+    params = np.asarray([0.5, 0.05, 0.5, 0.05])
+    u0 = np.asarray([20.0, 19.0])
+    vf = pdq.ode("lotka_volterra", params)
+    model = getattr(pdq, "state_space_model_" + kind)()
+    ts0 = model.constraint_ode_ts0(vf)
+    n, d, big = 4, 2, 1e3
+    tcoeffs = np.zeros((n, d))
+    tcoeffs[0] = u0
+    std = np.full((n,) if kind == "isotropic" else (n, d), big)
+    std[0] = 0.0
+    prior = model.prior_wiener_integrated_diffuse(tcoeffs, std)
+    slv = getattr(pdq, solver_name)(strategy=pdq.strategy_filter(), constraint=ts0, constraint_init=ts0)
+    state = slv.init(0.0, prior, damp=0.0)
+    f0 = np.asarray([0.5 * u0[0] - 0.05 * u0[0] * u0[1], -0.5 * u0[1] + 0.05 * u0[0] * u0[1]])
+    mean = state.u.tcoeffs
+    sd = np.asarray(state.u.std).reshape(n, -1)
+    np.testing.assert_allclose(mean[0], u0, rtol=0, atol=0)
+    np.testing.assert_allclose(mean[1], f0, rtol=1e-13)
+    assert np.all(sd[0] == 0.0) and np.all(sd[1] <= 1e-9 * big)
+    np.testing.assert_allclose(sd[2:], big, rtol=1e-12)
+    # without constraint_init nothing happens at t0
+    plain = getattr(pdq, solver_name)(strategy=pdq.strategy_filter(), constraint=ts0).init(0.0, prior, damp=0.0)
+    np.testing.assert_array_equal(plain.u.tcoeffs, tcoeffs)
+
+
+def test_constraint_init_is_gaussian_conditioning_dense_ts1():
+    """Dense model, ts1, inexact u0: the update equals m - S H^T (H S H^T + damp^2 I)^-1 r in covariance form."""
+    params = np.asarray([0.5, 0.05, 0.5, 0.05])
+    vf = pdq.ode("lotka_volterra", params)
+    model = pdq.state_space_model_dense()
+    ts1 = model.constraint_ode_ts1(vf)
+    n, d = 3, 2
+    rng = np.random.default_rng(3)
+    tcoeffs = rng.normal(size=(n, d)) + np.asarray([[20.0, 19.0], [0.0, 0.0], [0.0, 0.0]])
+    std = rng.uniform(0.1, 2.0, size=(n, d))
+    prior = model.prior_wiener_integrated_diffuse(tcoeffs, std)
+    damp = 0.3
+    state = pdq.solver(strategy=pdq.strategy_filter(), constraint=ts1, constraint_init=ts1).init(0.0, prior, damp=damp)
+    fx, _ = ts1.linearize(prior.init, None, damp=damp, t=0.0)
+    H, bias = fx.A, np.asarray(fx.noise.mean).reshape(-1)
+    m0 = prior.init.mean.reshape(-1)
+    S0 = prior.init.cov_dense()[1]
+    r = H @ m0 + bias
+    K = S0 @ H.T @ np.linalg.inv(H @ S0 @ H.T + damp**2 * np.eye(d))
+    np.testing.assert_allclose(state.u.mean.reshape(-1), m0 - K @ r, rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(state.u.cov_dense()[1], S0 - K @ (H @ S0 @ H.T + damp**2 * np.eye(d)) @ K.T, rtol=1e-9, atol=1e-11)
+
+
+def test_constraint_init_solve_is_accurate(truth):
+    """A diffuse-derivative start with constraint_init still solves the IVP (adaptive, save_at)."""
+    model = pdq.state_space_model_isotropic()
+    ts0 = model.constraint_ode_ts0(LV)
+    n = 4
+    tcoeffs = np.zeros((n, 2))
+    tcoeffs[0] = U0
+    std = np.asarray([0.0, 1.0, 1.0, 1.0])
+    prior = model.prior_wiener_integrated_diffuse(tcoeffs, std)
+    slv = pdq.solver_dynamic(strategy=pdq.strategy_filter(), constraint=ts0, constraint_init=ts0)
+    err = pdq.error_residual_std(constraint=ts0)
+    solve = ivpsolve.solve_adaptive_save_at(solver=slv, error=err, warn=False)
+    sol = solve(prior, save_at=np.linspace(0.0, 2.0, 5), atol=1e-8, rtol=1e-6, dt0=1e-3)
+    np.testing.assert_allclose(np.asarray(sol.u_mean)[:, 0], truth, rtol=2e-3)
