@@ -797,6 +797,12 @@ def run_ours(args) -> None:
 
 
 def main() -> None:
+    # The driver reads ONE JSON line from stdout. Libraries write there too (NCCL prints its version banner on the first
+    # communicator): file descriptor 1 is pointed at stderr for the whole run and `print` keeps the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -20,6 +20,7 @@
 // a proposal lives in registers (one dimension per lane) or thread-local scratch (several).
 #pragma once
 
+#include "pdeq_blockops_smoother.cuh"
 #include "pdeq_limits.cuh"
 #include "pdeq_loop_thread.cuh"
 
@@ -41,13 +42,6 @@ namespace pdeq {
 template <class VF, int NU, int FACT, bool TS0, bool FP, int MODE, int SPEC = 0>
 struct GroupLoop {
   static constexpr bool SPD = SPEC >= 1;
-  // SPEC = 2 (smoother only): the backward conditional of a step -- the gain rows and backward noise of the reverted
-  // transition and their merge into the carried conditional -- is computed when the step is ACCEPTED instead of with
-  // every attempt (acceptance is uniform across the lanes of an instance). An attempt then costs what a filter
-  // attempt costs; an accepted step pays one extra prediction triangularisation. Same operations on the same
-  // values for every accepted step, hence bitwise the same results. (dt > 0, where the filter's and the smoother's
-  // prediction stacks coincide: |p^-1| = p^-1.)
-  static constexpr bool DEFER = FP && SPEC == 2;
   static constexpr bool CTA = MODE != 0;
   static constexpr int n = NU + 1;
   static constexpr int q = VF::order;
@@ -233,36 +227,6 @@ struct GroupLoop {
     return fabs(w);
   }
 
-  // The per-lane part of one extrapolation with the transition (dt, scale s): predicted factor, and for the
-  // smoother the merged backward conditional.
-  // A stored conditional -- NFC rows [field][dim] in the order of cond_store -- read in place, written in place,
-  // or copied row by row. With these the carried and the merged conditional never occupy registers (they were
-  // 2 x 90 doubles per lane at nu = 5 and the reason for a 4.7 KB stack frame whose spill traffic reached DRAM).
-  struct CondFields {
-    const double* base;
-    int d, j;
-    PDEQ_DI double G(int i, int k) const { return base[(i * n + k) * d + j]; }
-    PDEQ_DI double xi(int i) const { return base[(n * n + i) * d + j]; }
-    PDEQ_DI double Xi(int i, int k) const { return base[(n * n + n + i * (i + 1) / 2 + k) * d + j]; }
-    PDEQ_DI double tl(int i) const { return base[(n * n + n + TRI + i) * d + j]; }
-    PDEQ_DI double to(int i) const { return base[(n * n + n + TRI + n + i) * d + j]; }
-  };
-  struct CondIdentity {  // *Normal.identity_conditional (ssm_impl_blockdiag.py:353-359)
-    PDEQ_DI double G(int i, int k) const { return i == k ? 1.0 : 0.0; }
-    PDEQ_DI double xi(int) const { return 0.0; }
-    PDEQ_DI double Xi(int, int) const { return 0.0; }
-    PDEQ_DI double tl(int) const { return 1.0; }
-    PDEQ_DI double to(int) const { return 1.0; }
-  };
-  struct CondSink {
-    double* base;
-    int d, j;
-    PDEQ_DI void set_G(int i, int k, double v) { base[(i * n + k) * d + j] = v; }
-    PDEQ_DI void set_xi(int i, double v) { base[(n * n + i) * d + j] = v; }
-    PDEQ_DI void set_Xi(int i, int k, double v) { base[(n * n + n + i * (i + 1) / 2 + k) * d + j] = v; }
-    PDEQ_DI void set_tl(int i, double v) { base[(n * n + n + TRI + i) * d + j] = v; }
-    PDEQ_DI void set_to(int i, double v) { base[(n * n + n + TRI + n + i) * d + j] = v; }
-  };
   PDEQ_DI static void cond_copy(double* dst, const double* src, int d, int j) {
 #pragma unroll
     for (int e = 0; e < NFC; ++e) dst[e * d + j] = src[e * d + j];
@@ -278,29 +242,25 @@ struct GroupLoop {
                                   const double (*Q)[PDEQ_MAX_COEFFS], double (&Lp)[n][n]) {
     predict_chol<n>(L, p, pinv, s, A, Q, Lp);
   }
-  // Smoother: the transition is reverted, and the new backward conditional is composed with the one found at
-  // `carried` into `merged` (strategy_smoother_fixedpoint.predict, estimators_and_losses.py:526-532).
-  template <class Outer>
-  PDEQ_DI static void extrapolate_smoother(const double (&L)[n][n], const double (&m)[n], const double (&p)[n],
-                                           const double (&pinv)[n], double s, const double (*A)[PDEQ_MAX_COEFFS],
-                                           const double (*Q)[PDEQ_MAX_COEFFS], const Outer& carried,
-                                           double (&Lp)[n][n], double* merged, int d, int j) {
-    BlockCond<n> bw;
-    revert_transition<n>(L, m, p, pinv, s, A, Q, Lp, bw);
-    CondSink sink{merged, d, j};
-    merge_cond_streamed<n>(carried, bw, sink);
-  }
+  // Smoother (strategy_smoother_fixedpoint.predict, estimators_and_losses.py:526-532): the transition is reverted and
+  // the new backward conditional composed with the carried one. Both halves live in pdeq_blockops_smoother.cuh:
+  // revert_push (with every attempt; parks the new conditional in the lane's working column) and remainder_merge (for
+  // accepted steps; overwrites the carried conditional in place).
+  static constexpr int NFW = FP ? SmootherScratch<n>::NFW : 0;  // fields of a working column
 
   // For the smoother the interp_from copy of the state (written on every accepted step, read only when a checkpoint
   // is overstepped) lives in an L2-resident global scratch slot instead of shared memory: it halves the shared
   // memory per instance and doubles the number of resident warps (4 -> 8 per SM for Pleiades).
   static constexpr bool IF_GLOBAL = FP;
-  PDEQ_HDI static constexpr size_t smem_doubles_per_group(int d, bool needs_interp) {
-    return (size_t)((needs_interp && !IF_GLOBAL) ? 2 : 1) * NF * d + (size_t)q * d + 32;
+  // wk_smem: the smoother's working columns live in shared memory (always in warp mode; in CTA mode only when they
+  // fit, otherwise in an L2-resident global slot per resident group).
+  PDEQ_HDI static constexpr size_t smem_doubles_per_group(int d, bool needs_interp, bool wk_smem = true) {
+    return (size_t)((needs_interp && !IF_GLOBAL) ? 2 : 1) * NF * d + (size_t)q * d + 32 +
+           (wk_smem ? (size_t)NFW * d : 0);
   }
 
   PDEQ_DI static void run(const LoopArgs& a, double* __restrict__ smem, double* __restrict__ cond_ring,
-                          double* __restrict__ if_scratch, int groups_per_cta) {
+                          double* __restrict__ if_scratch, double* __restrict__ wk_scratch, int groups_per_cta) {
     const pdeq_config& cfg = a.cfg;
     const double(*__restrict__ A)[PDEQ_MAX_COEFFS] = cfg.sys_a;
     const double(*__restrict__ Q)[PDEQ_MAX_COEFFS] = cfg.sys_q;
@@ -313,7 +273,8 @@ struct GroupLoop {
     const int cfg_error = SPD ? (int)PDEQ_ERROR_RESIDUAL_STD : cfg.error;
     const bool per_unit_step = SPD ? false : cfg.error_per_unit_step != 0;
     const int T = a.T;
-    const int d = cfg.ode_dim;
+    // a vector field of fixed dimension (validated by the host) makes every [field][dim] offset a compile-time constant
+    const int d = VF::fixed_dim > 0 ? VF::fixed_dim : cfg.ode_dim;
     const long B = a.prob.num_instances;
     const int max_attempts = cfg.max_attempts > 0 ? cfg.max_attempts : 0x7fffffff;
     const double inv_sqrt_d = rsqrt((double)d);
@@ -326,13 +287,16 @@ struct GroupLoop {
     const int nrounds = (d + g.size - 1) / g.size;  // <= MAXR, enforced by the launcher
 
     // shared memory of this group: [state_from | interp_from | exchange u | reduction scratch]
-    const size_t per_group = smem_doubles_per_group(d, needs_interp);
+    const size_t per_group = smem_doubles_per_group(d, needs_interp, wk_scratch == nullptr);
     const size_t group_slot = (size_t)blockIdx.x * groups_per_cta + gidx;
     double* base = smem + (size_t)gidx * per_group;
     double* st_from = base;
     double* st_if = IF_GLOBAL ? if_scratch + group_slot * (size_t)NF * d : base + NF * d;
     double* exch = base + ((needs_interp && !IF_GLOBAL) ? 2 : 1) * NF * d;
     g.red = exch + q * d;
+    // (warp mode: always shared memory -- said so at compile time, so that the accesses are LDS / STS, not generic)
+    double* wk = !FP ? nullptr
+                     : ((CTA && wk_scratch != nullptr) ? wk_scratch + group_slot * (size_t)NFW * d : g.red + 32);
     // global scratch ring for the per-checkpoint conditionals of the instance this group is working on
     double* ring = FP ? cond_ring + group_slot * (size_t)T * NFC * d : nullptr;
 
@@ -344,9 +308,6 @@ struct GroupLoop {
 
     // thread-local proposal scratch (registers when a lane serves one dimension)
     double pm[MAXR][n], pL[MAXR][n][n], psig[MAXR], prun[MAXR];
-    // smoother: slot 0 of the ring (conditionals are stored from checkpoint 1 on) holds the merged conditional of
-    // the current attempt until the step is accepted
-    double* pending = ring;
 
     while (true) {
       // ------------------------------------------------------------------ fetch the next instance
@@ -472,10 +433,11 @@ struct GroupLoop {
               const double dt0_ = t_next - t_if;
               preconditioner<n>(dt0_, ifact, fact, p, pinv);
               predict_mean<n>(mi, p, pinv, A, mo);
-              if (FP) {  // the conditional checkpoint ck -> ck - 1 goes straight to its ring slot
-                const CondFields c_if{st_if + F_G * d, d, j};
-                extrapolate_smoother(Li, mi, p, pinv, safe_sqrt(fabs(dt0_)) * prior * sig, A, Q, c_if, Lo,
-                                     ring + (size_t)ck * NFC * d, d, j);
+              if (FP) {  // the conditional checkpoint ck -> ck - 1: merged in place in its ring slot
+                double* slot = ring + (size_t)ck * NFC * d;
+                revert_push<n>(st_if + j, d, p, pinv, safe_sqrt(fabs(dt0_)) * prior * sig, A, Q, wk + j, Lo);
+                cond_copy(slot, st_if + F_G * d, d, j);
+                remainder_merge<n>(slot + j, d, p, pinv, wk + j);
               } else {
                 extrapolate(Li, mi, p, pinv, safe_sqrt(fabs(dt0_)) * prior * sig, A, Q, Lo);
               }
@@ -486,11 +448,14 @@ struct GroupLoop {
                 double p1[n], pinv1[n], Ltmp[n][n];
                 const double dt1_ = t - t_next;
                 preconditioner<n>(dt1_, ifact, fact, p1, pinv1);
-                extrapolate_smoother(Lo, mo, p1, pinv1, safe_sqrt(fabs(dt1_)) * prior * sig, A, Q, CondIdentity{}, Ltmp,
-                                     st_from + F_G * d, d, j);
+                st_store(st_if, d, j, mo, Lo);
+                revert_push<n>(st_if + j, d, p1, pinv1, safe_sqrt(fabs(dt1_)) * prior * sig, A, Q, wk + j, Ltmp);
+                cond_store_identity(st_from + F_G * d, d, j);
+                remainder_merge<n>(st_from + F_G * d + j, d, p1, pinv1, wk + j);
                 cond_store_identity(st_if + F_G * d, d, j);
+              } else {
+                st_store(st_if, d, j, mo, Lo);
               }
-              st_store(st_if, d, j, mo, Lo);
             } else {
               // interp_at_t1 (solvers_via_adaptive_steps.py:362-375 -> solvers.py:271-315)
               double m[n], L[n][n];
@@ -663,9 +628,8 @@ struct GroupLoop {
         if (cfg_solver == PDEQ_SOLVER_DYNAMIC) sig_new = whitened(g, mobs * fast_rcp(robs), active, inv_sqrt_d);
 
         double Lp[n][n], Ln[n][n], gain[n], ry, mn[n];
-        if (FP && !DEFER) {
-          const CondFields carried{st_from + F_G * d, d, jj};
-          extrapolate_smoother(L, m, p, pinv, sq * prior * sig_new, A, Q, carried, Lp, pending, d, jj);
+        if (FP) {
+          revert_push<n>(st_from + jj, d, p, pinv, sq * prior * sig_new, A, Q, wk + jj, Lp);
         } else {
           extrapolate(L, m, p, pinv, sq * prior * sig_new, A, Q, Lp);
         }
@@ -785,39 +749,38 @@ struct GroupLoop {
       if (accept) {
         // every lane has finished reading the accepted state (isotropic: idle lanes read lane 0's copy)
         g.sync();
+        // interp_from (solvers_via_adaptive_steps.py:268-273: the state the accepted step started from) is read only by
+        // the checkpoint branch that follows a step which reaches or oversteps t_next -- known here. Every other accepted
+        // step's copy would be overwritten unread by the next one, so it is not made (config 3: 32 copies of the
+        // 102-field state and conditional per instance instead of ~1500).
+        const bool reaches = needs_interp && !(t_new + a.eps < t_next);
         for (int r = 0; r < MAXR; ++r) {
           if (r >= nrounds) break;
           const int j = g.lane + r * g.size;
           if (j >= d) continue;
-          if (needs_interp) {  // interp_from <- step_from
+          if (reaches) {  // interp_from <- step_from
             double m[n], L[n][n];
             st_load(st_from, d, j, m, L);
             st_store(st_if, d, j, m, L);
             if (FP) cond_copy(st_if + F_G * d, st_from + F_G * d, d, j);
           }
-          if (DEFER) {  // the accepted step's backward conditional, from the state it started from
-            double m0[n], L0[n][n], Lp_again[n][n];
-            st_load(st_from, d, j, m0, L0);
-            const CondFields carried{st_from + F_G * d, d, j};
-            extrapolate_smoother(L0, m0, p, pinv, sq * st_from[F_PRIOR * d + j] * psig[r], A, Q, carried, Lp_again,
-                                 pending, d, j);
-          }
           st_store(st_from, d, j, pm[r], pL[r]);
           if (FP) {
+            // the step's backward conditional (parked in the working column by this attempt's revert_push) is composed
+            // with the carried one, in place
+            remainder_merge<n>(st_from + F_G * d + j, d, p, pinv, wk + j);
             if (!adaptive) {
               // fixed grid: every grid point is a checkpoint. Store the backward conditional of this step and
               // restart from the identity -- the fixed-interval smoother (estimators_and_losses.py:612-620).
-              cond_copy(ring + (size_t)ck * NFC * d, pending, d, j);
+              cond_copy(ring + (size_t)ck * NFC * d, st_from + F_G * d, d, j);
               cond_store_identity(st_from + F_G * d, d, j);
-            } else {
-              cond_copy(st_from + F_G * d, pending, d, j);
             }
           }
           if (cfg_solver == PDEQ_SOLVER_DYNAMIC) st_from[F_SIG * d + j] = psig[r];
           st_from[F_RUN * d + j] = prun[r];
           if (!adaptive) emit(a, b, ck, d, j, t_new, pm[r], pL[r], st_from[F_SIG * d + j], nsteps + 1);
         }
-        if (needs_interp) t_if = t;
+        if (reaches) t_if = t;
         ndata += 1.0;
         t = t_new;
         nsteps += 1;
@@ -830,6 +793,7 @@ struct GroupLoop {
 struct GroupLaunchInfo {
   double* cond_ring;
   double* if_scratch;
+  double* wk_scratch;  // smoother working columns when they do not fit in shared memory (CTA mode), else nullptr
   int groups_per_cta;
 };
 
@@ -837,7 +801,8 @@ template <class VF, int NU, int FACT, bool TS0, bool FP, int MODE, int SPEC = 0>
 __global__ void __launch_bounds__(MODE != 0 ? K2_CTA_THREADS : 128, MODE == 1 ? 2 : ((MODE == 0 && !FP) ? PDEQ_K2_WARP_FILTER_BLOCKS : 1))
     k2_loop_kernel(const __grid_constant__ LoopArgs a, const __grid_constant__ GroupLaunchInfo info) {
   extern __shared__ double smem_k2[];
-  GroupLoop<VF, NU, FACT, TS0, FP, MODE, SPEC>::run(a, smem_k2, info.cond_ring, info.if_scratch, info.groups_per_cta);
+  GroupLoop<VF, NU, FACT, TS0, FP, MODE, SPEC>::run(a, smem_k2, info.cond_ring, info.if_scratch, info.wk_scratch,
+                                                    info.groups_per_cta);
 }
 
 // Host-side test for GroupLoop SPEC = 1.
