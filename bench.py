@@ -509,7 +509,7 @@ def run_ours(args) -> None:
         # solve of the shard's first PILOT instances. Inside every timed step the model is EVALUATED for the whole
         # shard and the instances are sorted by it (longest first) -- that work is part of the step.
         model = None
-        if not args.no_cost_hint:
+        if not args.no_cost_hint and ivpsolve.cost_hint_is_used(Bs, dev):  # large shards: the hint would be ignored
             M = min(PILOT, Bs)
             vf_p = probdiffeq.ode("lotka_volterra", params=params_d[:M])
             tc_p, _ = jetexpand(vf_p, (u0_d[:M],), t=T0)
@@ -542,7 +542,7 @@ def run_ours(args) -> None:
 
         h2d = int(params_h.numel() * 8 + u0_h.numel() * 8)
         d2h = int(mean_hs[0].numel() * 8 + steps_hs[0].numel() * 4)
-        return step_resident, step_e2e, steps_hs, h2d, d2h, step_plain
+        return step_resident, step_e2e, steps_hs, h2d, d2h, step_plain, model is not None
 
     params_all, u0_all = lv_ensemble(B_total, seed=0)
     if world > 1:
@@ -550,11 +550,16 @@ def run_ours(args) -> None:
     else:
         params_np, u0_np = params_all, u0_all
     B = params_np.shape[0]
-    step_resident, step_e2e, steps_hs, h2d_bytes, d2h_bytes, step_plain = lv_arms(params_np, u0_np)
+    step_resident, step_e2e, steps_hs, h2d_bytes, d2h_bytes, step_plain, hint_active = lv_arms(params_np, u0_np)
 
     # Untimed spin-up on top of the W warm-up steps: a fresh process finds the GPU at idle clocks, and W = 3 passes
     # can end before the clocks have ramped -- a whole run then reads ~30 % slow. Keep the device busy for at least
     # 0.75 s and until three consecutive passes agree within 3 % (at most 400 passes) before anything is timed.
+    # The clock sampler (an `nvidia-smi -lms 100` child) starts BEFORE the spin-up: its start-up (a new client attaching
+    # to the GPU) stalled whichever kernel was running for 10-15 ms -- once, ~100 ms after the fork, which used to be
+    # the second timed step (r2o: 16.95, 30.90, 16.87, 16.87, 16.86 ms). Its periodic queries do not show in the times.
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     spin_t0, spinup, spin_ms = time.perf_counter(), 0, []
     while spinup < 400:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -568,13 +573,11 @@ def run_ours(args) -> None:
         if time.perf_counter() - spin_t0 >= 0.75 and settled:
             break
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ms_res, sol = timed(step_resident, args.steps, args.warmup, "resident")
     k1_launches = 1  # one persistent loop kernel per solve (the cost model and the sort are torch kernels)
     launches += args.steps * k1_launches
     ms_plain = None
-    if not args.no_cost_hint:
+    if hint_active:
         ms_plain, _ = timed(step_plain, args.steps, args.warmup, "resident_no_hint")
         launches += args.steps * k1_launches
     steps_pass = int(sol.num_steps.sum().item())
@@ -731,10 +734,14 @@ def run_ours(args) -> None:
             "rejection_ratio": 1.0 - steps_all / max(attempts_all, 1), "failed_instances": bad,
             "attempts_per_s": attempts_all / kernel_s,
             "schedule": {
-                "cost_hint": not args.no_cost_hint,
-                "what": "every timed step evaluates a quadratic cost model of (params, u0) for its shard and serves the "
-                        "instances longest-predicted-first (solve(..., cost_hint=) -> pdeq_problem.order). The model was "
-                        "fitted in set-up (untimed) on a pilot solve of the shard's first %d instances" % PILOT,
+                "cost_hint": hint_active,
+                "what": ("every timed step evaluates a quadratic cost model of (params, u0) for its shard and serves the "
+                         "instances longest-predicted-first (solve(..., cost_hint=) -> pdeq_problem.order; a lane's first "
+                         "ticket is its thread index, so a warp starts on 32 neighbours of that order). The model was "
+                         "fitted in set-up (untimed) on a pilot solve of the shard's first %d instances" % PILOT)
+                        if hint_active else
+                        "index order: with more than %d instances per resident lane the solver ignores a cost hint "
+                        "(ivpsolve.cost_hint_is_used), so none is computed" % ivpsolve.COST_HINT_MAX_ROUNDS,
                 "no_hint": None if ms_plain is None else {
                     "value": steps_all / (ms_plain * 1e-3), "ms_per_step": ms_plain,
                     "what": "the same solve in index order on the full grid (round 1's schedule)"},

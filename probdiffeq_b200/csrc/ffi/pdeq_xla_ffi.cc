@@ -1,8 +1,10 @@
 // XLA FFI shim: one handler per C-ABI loop entry point, so that the reference can call the kernels from inside
 // jax.jit with jax.ffi.ffi_call (see INTEGRATION.md section 4 for the reference-side Python).
 //
-// NOT compiled by probdiffeq_b200/build.py and NOT tested in this repository: JAX (hence xla/ffi/api/ffi.h) is not
-// available in the build or GPU images. Build it where JAX is installed:
+// NOT compiled by probdiffeq_b200/build.py and never RUN in this repository: JAX (hence xla/ffi/api/ffi.h) is not
+// available in the build or GPU images. What is checked here (tests/test_ffi_shim_compiles.py) is that it compiles
+// against a local stand-in of the xla::ffi names it uses (tests/stubs/xla/ffi/api/ffi.h): every pdeq_* call matches
+// include/probdiffeq_b200.h and every handler's signature equals its binding. Build it where JAX is installed:
 //
 //   g++ -O2 -std=c++17 -fPIC -shared -DPDEQ_WITH_XLA_FFI -I"$(python -c 'import jax; print(jax.ffi.include_dir())')" \
 //       -I include -I /usr/local/cuda/include probdiffeq_b200/csrc/ffi/pdeq_xla_ffi.cc \

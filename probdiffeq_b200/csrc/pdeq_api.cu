@@ -133,6 +133,15 @@ static const LoopEntry* select_loop(const pdeq_config* c) {
     const LoopEntry* e = find_loop({c->vf_id, c->num_derivatives, fact, 0, ts0, fp});
     if (e != nullptr) return e;
   }
+  // K3S: dense factorisation with a smoother, CTA per instance, all matrices in shared memory: 4 N^2 work buffer,
+  // two N x N factors, two stored conditionals (pdeq_smooth_dense.cuh: DenseSmootherLoop::smem_doubles)
+  if (fact == PDEQ_FACT_DENSE && fp) {
+    const size_t N = (size_t)(c->num_derivatives + 1) * c->ode_dim;
+    if ((10 * N * N + 12 * N) * sizeof(double) + 4096 <= 227 * 1024) {
+      const LoopEntry* e = find_loop({c->vf_id, c->num_derivatives, fact, 0, ts0, 1});
+      if (e != nullptr) return e;
+    }
+  }
   // K3: dense factorisation, CTA per instance, filter only; the work buffer must fit in shared memory
   if (fact == PDEQ_FACT_DENSE && !fp) {
     const DenseSmemLayout lay = DenseSmemLayout::make(c->num_derivatives + 1, c->ode_dim, vf_info(c->vf_id)->order, true);

@@ -4,6 +4,13 @@
 
 #include <cstddef>
 
+#ifndef PDEQ_K3_TPC2_MAX_N
+#define PDEQ_K3_TPC2_MAX_N 48
+#endif
+#ifndef PDEQ_K3_MIN_BLOCKS
+#define PDEQ_K3_MIN_BLOCKS 3
+#endif
+
 namespace pdeq {
 
 constexpr int K2_MAX_DPL = 4;        // dimensions per lane in CTA mode (pdeq_loop_group.cuh)
@@ -13,7 +20,8 @@ constexpr int K2_CTA_THREADS = 256;  // upper bound of a CTA-mode block
 struct DenseSmemLayout {
   int N, d;
   size_t off_Lfrom, off_Lif, off_vec, total;
-  __host__ __device__ static constexpr int tpc(int N) { return N <= 48 ? 2 : 4; }
+  // lanes per column of the dense kernel: 2 up to PDEQ_K3_TPC2_MAX_N state coefficients, else 4
+  __host__ __device__ static constexpr int tpc(int N) { return N <= PDEQ_K3_TPC2_MAX_N ? 2 : 4; }
   __host__ __device__ static constexpr int rows_per_thread(int N) { return (2 * N + tpc(N) - 1) / tpc(N); }
   __host__ __device__ static constexpr int rpad(int N) { return (rows_per_thread(N) + 1) / 2 * 2; }
   __host__ __device__ static constexpr int threads(int N, int d) { return (tpc(N) * (N + d) + 31) / 32 * 32; }

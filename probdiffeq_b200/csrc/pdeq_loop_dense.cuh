@@ -790,7 +790,7 @@ struct DenseLoop {
 };
 
 template <class VF, int NU, bool TS0>
-__global__ void __launch_bounds__(DenseSmemLayout::threads((NU + 1) * VF::fixed_dim, VF::fixed_dim), 3)
+__global__ void __launch_bounds__(DenseSmemLayout::threads((NU + 1) * VF::fixed_dim, VF::fixed_dim), PDEQ_K3_MIN_BLOCKS)
     k3_loop_kernel(const __grid_constant__ LoopArgs a) {
   extern __shared__ double smem_k3[];
   DenseLoop<VF, NU, TS0>::run(a, smem_k3);

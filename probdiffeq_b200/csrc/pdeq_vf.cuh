@@ -184,8 +184,15 @@ struct Pleiades {
     for (int j = 0; j < 7; ++j) {
       if (j == body) continue;
       const T dx = u(0, j) - xi, dy = u(0, 7 + j) - yi;
-      const T r3 = pow_three_halves(dx * dx + dy * dy);
-      acc = acc + double(j + 1) * ((is_x ? dx : dy) / r3);
+      if constexpr (std::is_same<T, double>::value) {
+        // step loops: 1 / r^3 from one reciprocal square root (MUFU seed + one correction, within an ulp) instead of
+        // a square root and a division -- both with slow-path branches, six times per lane and attempt
+        const double ir = fast_rsqrt(dx * dx + dy * dy);
+        acc = fma(double(j + 1) * (is_x ? dx : dy), (ir * ir) * ir, acc);
+      } else {
+        const T r3 = pow_three_halves(dx * dx + dy * dy);
+        acc = acc + double(j + 1) * ((is_x ? dx : dy) / r3);
+      }
     }
     return acc;
   }

@@ -102,19 +102,32 @@ def _lower(prior, solver, error, control, clip_dt, max_attempts=0) -> _lib.Confi
     return cfg
 
 
+def cost_hint_is_used(B, device) -> bool:
+    """Whether `solve(..., cost_hint=)` reorders an ensemble of B instances on this device (callers that would have to
+    COMPUTE a hint can skip that work when it is not)."""
+    lanes = torch.cuda.get_device_properties(device).multi_processor_count * 384
+    return 0 < B <= COST_HINT_MAX_ROUNDS * lanes
+
+
 def _service_order(cost_hint, B, device):
     """`cost_hint` (B,): any positive proxy of how expensive each instance is (a previous solve's `num_attempts`, a
-    model of the parameters, ...). The persistent kernels then serve the instances longest-first, which evens out the
-    end of a solve with few instances per lane (pdeq_problem.order). Results do not depend on it."""
+    model of the parameters, ...). The persistent kernels then serve the instances longest-first (pdeq_problem.order),
+    which evens out the end of a solve with few instances per lane; and because a lane's first ticket is its thread
+    index, the 32 lanes of a warp start on 32 neighbours of the order -- equally long instances -- and keep finishing
+    (and refilling) together. Results do not depend on it.
+
+    Measured on the thread-per-instance kernel (scripts/sweep_k1_order.py, 2^17 instances = 2.3 per lane): index order
+    2.64 ms, longest-first 2.37 ms; with 18 per lane the sort costs more than it gains -- many rounds even out by
+    themselves -- hence COST_HINT_MAX_ROUNDS. (A planned queue that reserves the cheapest instances for the lanes that
+    must serve one instance more than the others looked 7 % better in a lane-level simulation and measured 7 % worse
+    than longest-first; it was removed.)"""
     hint = torch.as_tensor(cost_hint, device=device).reshape(-1)
     if hint.shape[0] != B:
         raise ValueError("cost_hint must have one entry per ensemble member.")
-    # Measured on the thread-per-instance kernel (scripts/sweep_k1_order.py): with 2.3 instances per lane the order
-    # is worth 7 %, with 18 per lane the sort costs more than it gains -- many rounds even out by themselves.
-    lanes = torch.cuda.get_device_properties(device).multi_processor_count * 384
-    if B > COST_HINT_MAX_ROUNDS * lanes:
+    if not cost_hint_is_used(B, device):
         return None
-    return torch.argsort(hint, descending=True).to(torch.int32)
+    # only the coarse ranking matters: float32 keys halve the radix passes of the sort
+    return torch.argsort(hint.to(torch.float32), descending=True).to(torch.int32)
 
 
 def _problem(prior, vf, cost_hint=None):
@@ -161,8 +174,6 @@ def _alloc_solution(prior, T, want_chol=True, trace_capacity=0, want_posterior=F
     if trace_capacity > 0:
         bufs["trace"] = torch.full((B, trace_capacity, 4), float("nan"), **f64)
     if want_posterior:
-        if fact == "dense" and d > 1:
-            raise ValueError("the dense factorisation has no smoother on device; no posterior to return")
         bufs["bw_gain"] = torch.zeros(chol_shape, **f64)
         bufs["bw_mean"] = torch.zeros((B, T, n, d), **f64)
         bufs["bw_chol"] = torch.zeros(chol_shape, **f64)
@@ -186,6 +197,8 @@ def _want_posterior(flag, solver, prior, T, want_chol):
     if flag is not None:
         return bool(flag)
     B, n, d = prior.tcoeffs.shape
+    if prior.factorisation == "dense":
+        return 8 * B * T * (2 * (n * d) ** 2 + n * d) <= POSTERIOR_AUTO_BYTES
     blocks = 1 if prior.factorisation == "isotropic" else d
     return 8 * B * T * (2 * blocks * n * n + n * d) <= POSTERIOR_AUTO_BYTES
 

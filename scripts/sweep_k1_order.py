@@ -5,7 +5,8 @@ the headline solve is timed
   plain    index order, full grid (what round 1 measured);
   hint     `cost_hint` from a quadratic cost model fitted on a 4096-instance pilot solve (sharding.QuadraticCostModel):
            longest-first service; the model evaluation and the sort are inside the timed region;
-  oracle   the same with the TRUE attempt counts of a previous solve as the hint (what a perfect predictor would give);
+  hintall  as hint, also beyond COST_HINT_MAX_ROUNDS instances per lane (where `solve` otherwise ignores the hint);
+  oracle   hintall with the TRUE attempt counts of a previous solve as the hint (what a perfect predictor would give);
 and every output is compared byte for byte with the plain run: where and when an instance runs must not change a bit.
 `strong_eff_vs_2^20` = throughput relative to the 2^20-instance run of the same setting.
 
@@ -44,6 +45,7 @@ def main() -> None:
     ssm = probdiffeq.state_space_model_isotropic()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     base = {}
+    default_rounds = ivpsolve.COST_HINT_MAX_ROUNDS
     for B in [int(x) for x in args.sizes.split(",")]:
         idx = perm[:B]  # the first rank's shard of the permuted ensemble when 2^20 / B GPUs split it
         params = torch.from_numpy(params_np[idx]).to(dev)
@@ -65,9 +67,10 @@ def main() -> None:
         rank_err = float((model.predict(inputs) - true_cost).std().item())
 
         def run(mode):
+            ivpsolve.COST_HINT_MAX_ROUNDS = 64 if mode in ("hintall", "oracle") else default_rounds
             if mode == "plain":
                 return solve(prior, **kw)
-            if mode == "hint":
+            if mode in ("hint", "hintall"):
                 return solve(prior, cost_hint=model.predict(inputs), **kw)
             return solve(prior, cost_hint=true_cost, **kw)
 
