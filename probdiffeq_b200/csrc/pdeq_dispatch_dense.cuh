@@ -73,10 +73,12 @@ struct K3Registrar {
   explicit K3Registrar(int vf_id = VF::id) {
     register_loop({{vf_id, NU, PDEQ_FACT_DENSE, 0, 1, 0}, &k3_launch<VF, NU, true>, &ws, "dense"});
     register_loop({{vf_id, NU, PDEQ_FACT_DENSE, 0, 0, 0}, &k3_launch<VF, NU, false>, &ws, "dense"});
+#ifndef PDEQ_K3_NO_SMOOTHER  // (SASS inspection builds of the filter kernels only)
     register_loop({{vf_id, NU, PDEQ_FACT_DENSE, 0, 1, 1}, &k3s_launch<VF, NU, true>, &k3s_workspace<VF, NU, true>,
                    "dense-smoother"});
     register_loop({{vf_id, NU, PDEQ_FACT_DENSE, 0, 0, 1}, &k3s_launch<VF, NU, false>, &k3s_workspace<VF, NU, false>,
                    "dense-smoother"});
+#endif
   }
 };
 #define PDEQ_INSTANTIATE_K3(VF, NU) static K3Registrar<VF, NU> _k3_##VF##_##NU;

@@ -7,11 +7,16 @@
 //
 // Mapping. A column of the stack lives in the REGISTERS of TPC (2 or 4) adjacent lanes, rows dealt round-robin
 // (row r -> lane part r % TPC, register r / TPC); the CTA holds N "state" columns and d "observation" columns.
-// One reflector step: the lanes that own the pivot column reduce its norm with a shuffle, form the reflector
-// (LAPACK dlarfg convention, see pdeq_blockops.cuh) and publish it -- zero outside its row extent, v0 at the pivot
-// row, so that nobody needs a run-time register index -- in one of two shared-memory buffers; ONE block barrier;
-// every lane of a trailing column forms its part of v^T c from broadcast reads of that buffer and its own registers,
-// meets its partners with a shuffle and updates its registers. The trailing matrix is never read or written in shared
+// One reflector step: the lanes that own the pivot column publish it RAW -- its part below the pivot, zero outside its
+// row extent so that nobody needs a run-time register index, and the pivot element apart -- in one of two
+// shared-memory buffers; ONE block barrier; every lane then reads its row part of that buffer once and forms, from the
+// same numbers in the same order as every other lane, the column's norm, the reflector scalars (LAPACK dlarfg
+// convention, see pdeq_blockops.cuh) and its part of v^T c, meets its partners with a shuffle and updates its
+// registers. Nobody waits for an owner: round 2's first version had the owning warp reduce the norm, form the
+// reflector and publish it (and clear its registers) -- ~295 instructions of one warp per pivot, with the other three
+// at the barrier, against ~85 for the update; now a pivot costs ~45 (publish) + ~145 (everything else) instructions
+// of the busiest warp (ncu: config 4a 3.57 -> 3.10 s; what remains is the issue rate of ONE warp per instance,
+// ~5 cycles per instruction whatever the instruction, with three instances per SM). The trailing matrix is never read or written in shared
 // memory (round 1's kernel did both for every column and was bound by exactly that: ~2600 cycles per column with
 // four instances per SM), the reflector loop is ROLLED (a few hundred instructions, so the kernel lives in the
 // instruction cache), and the shared memory per instance drops from 55 KB to the packed accepted factor plus vectors.
@@ -109,9 +114,10 @@ struct DenseLoop {
   // passed barrier j + 1, which every reader of step j reaches only after its reads). The pivots are taken in blocks
   // of eight, unrolled, so that inside a block the rows a reflector can touch are known at compile time (row_class):
   // a step costs what its rows cost, not what the whole column costs, with run-time tests only for the eight rows
-  // around the pivots. Nothing in a step diverges inside a warp: every lane of the owning warp forms "its" reflector
-  // (the owner's is the one published), and a lane whose column is finished updates it with weight zero -- shuffles
-  // under a diverged mask go through a slow path that cost more than the arithmetic they saved.
+  // around the pivots. Nothing in a step diverges inside a warp except the owner's stores: every lane forms the
+  // reflector, a lane whose column is finished updates it with weight zero (shuffles under a diverged mask go through
+  // a slow path that cost more than the arithmetic they saved), and the eliminated entries of the pivot columns stay
+  // where they are until one clearing pass at the end.
   template <int M, int NPOS, int CSPLIT, int SA, class FirstLane>
   PDEQ_DI static void column_qr(double (&col)[RPT], int mypos, int h, FirstLane first_lane, double* rbuf) {
     constexpr int RM = (M + TPC - 1) / TPC;  // registers in use for an M-row stack
@@ -122,23 +128,41 @@ struct DenseLoop {
       constexpr int J1 = imin(J0 + BS, NPOS);
       for (int j = J0; j < J1; ++j) {
         double* buf = rbuf + (j & 1) * RB;
-        if ((first_lane(j) >> 5) == warp) {  // warp-uniform: this warp holds the pivot column
-          double ss0 = 0.0, ss1 = 0.0, alpha = 0.0;
+        if (mypos == j) {  // publish the RAW pivot column: its part below the pivot, and the pivot element apart
           static_for<0, RM>([&](auto ic_) {
             constexpr int i = decltype(ic_)::value;
             constexpr int cls = reg_class(i, J0, J1, M, CSPLIT, SA);
             if constexpr (cls == 1) {
-              if constexpr (i & 1) ss1 = fma(col[i], col[i], ss1);
-              else ss0 = fma(col[i], col[i], ss0);
+              buf[h * RPAD + i] = col[i];
             } else if constexpr (cls == 2) {
               const int r = i * TPC + h;
-              const double x = col[i];
-              ss0 = row_in(r, j, CSPLIT, SA) ? fma(x, x, ss0) : ss0;
-              alpha = (r == j) ? x : alpha;
+              buf[h * RPAD + i] = row_in(r, j, CSPLIT, SA) ? col[i] : 0.0;
+              if (r == j) buf[TPC * RPAD] = col[i];
             }
           });
+        }
+        __syncthreads();
+        if (__any_sync(0xffffffffu, mypos >= j)) {  // warp-uniform: this warp still holds the pivot or a trailing column
+          const double* v = buf + h * RPAD;
+          const double alpha = buf[TPC * RPAD];
+          double w0 = 0.0, w1 = 0.0, ss0 = 0.0, ss1 = 0.0, cj = 0.0;
+          static_for<0, RM>([&](auto ic_) {
+            constexpr int i = decltype(ic_)::value;
+            constexpr int cls = reg_class(i, J0, J1, M, CSPLIT, SA);
+            if constexpr (cls != 0) {
+              const double x = v[i];
+              if constexpr (i & 1) w1 = fma(x, col[i], w1);
+              else w0 = fma(x, col[i], w0);
+              if constexpr (cls == 1 && (i & 1)) ss1 = fma(x, x, ss1);
+              else ss0 = fma(x, x, ss0);
+              if constexpr (cls == 2) cj = (i * TPC + h == j) ? col[i] : cj;
+            }
+          });
+          // every lane forms the reflector from the published column -- the same arithmetic on the same numbers in
+          // every lane, so nobody waits for an owner: dlarfg, as in the owner-computes scheme
           const double ss = group_sum(ss0 + ss1, 0xffffffffu);
-          alpha = group_sum(alpha, 0xffffffffu);
+          const double wd = group_sum(w0 + w1, 0xffffffffu);
+          cj = group_sum(cj, 0xffffffffu);
           const bool live = ss != 0.0;  // dlarfg: xnorm == 0 -> tau = 0, H = I
           const double tt = fma(alpha, alpha, ss);
           const double y = fast_rsqrt(live ? tt : 1.0);
@@ -147,42 +171,27 @@ struct DenseLoop {
           const double v0 = alpha + sgn_nrm;
           const double tp = live ? fast_rcp(fma(nrm, fabs(alpha), tt)) : 0.0;
           const double beta = live ? -sgn_nrm : alpha;
-          if (mypos == j) {
-            static_for<0, RM>([&](auto ic_) {
-              constexpr int i = decltype(ic_)::value;
-              constexpr int cls = reg_class(i, J0, J1, M, CSPLIT, SA);
-              if constexpr (cls == 1) {
-                buf[h * RPAD + i] = col[i];
-                col[i] = 0.0;
-              } else if constexpr (cls == 2) {
-                const int r = i * TPC + h;
-                const bool below = row_in(r, j, CSPLIT, SA);
-                buf[h * RPAD + i] = (r == j) ? v0 : (below ? col[i] : 0.0);
-                col[i] = (r == j) ? beta : (below ? 0.0 : col[i]);
-              }
-            });
-            if (h == 0) buf[TPC * RPAD] = tp;
-          }
-        }
-        __syncthreads();
-        if (__any_sync(0xffffffffu, mypos > j)) {  // warp-uniform: some column of this warp is still active
-          const double tp = (mypos > j) ? buf[TPC * RPAD] : 0.0;
-          const double* v = buf + h * RPAD;
-          double w0 = 0.0, w1 = 0.0;
+          const double w = (mypos > j) ? fma(v0, cj, wd) * tp : 0.0;
+          const double wv0 = w * v0;
+          const bool own = mypos == j;
           static_for<0, RM>([&](auto ic_) {
             constexpr int i = decltype(ic_)::value;
-            if constexpr (reg_class(i, J0, J1, M, CSPLIT, SA) != 0) {
-              if constexpr (i & 1) w1 = fma(v[i], col[i], w1);
-              else w0 = fma(v[i], col[i], w0);
+            constexpr int cls = reg_class(i, J0, J1, M, CSPLIT, SA);
+            if constexpr (cls == 1) {
+              col[i] = fma(-w, v[i], col[i]);
+            } else if constexpr (cls == 2) {
+              const double upd = fma(-w, v[i], col[i]);
+              col[i] = (i * TPC + h == j) ? (own ? beta : col[i] - wv0) : upd;
             }
-          });
-          const double w = group_sum(w0 + w1, 0xffffffffu) * tp;
-          static_for<0, RM>([&](auto ic_) {
-            constexpr int i = decltype(ic_)::value;
-            if constexpr (reg_class(i, J0, J1, M, CSPLIT, SA) != 0) col[i] = fma(-w, v[i], col[i]);
           });
         }
       }
+    });
+    // the eliminated part of every pivot column, left in place by the steps above (later reflectors pass over a
+    // finished column with weight zero), is cleared once
+    static_for<0, RM>([&](auto ic_) {
+      constexpr int i = decltype(ic_)::value;
+      col[i] = (mypos >= 0 && mypos < NPOS && i * TPC + h > mypos) ? 0.0 : col[i];
     });
     __syncthreads();  // the last buffer may be rewritten by whatever comes next
   }
