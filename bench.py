@@ -606,7 +606,7 @@ def run_ours(args) -> None:
     weak = None
     if world > 1 and not args.no_weak:
         wp, wu = lv_ensemble(B_total, seed=rank)
-        w_resident, _w_e2e, _sh, _a, _b, _w_plain = lv_arms(wp, wu)
+        w_resident, _w_e2e, _sh, _a, _b, _w_plain, _w_hint = lv_arms(wp, wu)
         ms_w, wsol = timed(w_resident, max(2, args.steps // 2), 2, "weak")
         launches += max(2, args.steps // 2) * k1_launches
         (ms_w,) = reduce_max(ms_w)
