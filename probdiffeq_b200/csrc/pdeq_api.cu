@@ -121,10 +121,16 @@ static const LoopEntry* select_loop(const pdeq_config* c) {
   if (fact == PDEQ_FACT_DENSE && c->ode_dim == 1) fact = PDEQ_FACT_ISOTROPIC;
   const int ts0 = c->constraint == PDEQ_CONSTRAINT_TS0;
   const int fp = c->strategy != PDEQ_STRATEGY_FILTER;  // both smoothers run on the conditional-carrying kernels
-  // K1: thread per instance, compile-time d, filter only
+  // K1: thread per instance, compile-time d, filter only. Without step clipping every lane parks its interp_from state
+  // (mean, factor, t: ThreadLoop::IF_SLOTS doubles) in shared memory; a block-diagonal model of d >= 6 at high order
+  // does not fit there, and the lane-per-dimension kernel takes it instead
   if (!fp) {
-    const LoopEntry* e = find_loop({c->vf_id, c->num_derivatives, fact, c->ode_dim, ts0, 0});
-    if (e != nullptr) return e;
+    const size_t n = (size_t)c->num_derivatives + 1, blocks = fact == PDEQ_FACT_BLOCKDIAG ? (size_t)c->ode_dim : 1;
+    const size_t interp_smem = c->clip_dt ? 0 : (n * c->ode_dim + blocks * n * n + 1) * 128 * sizeof(double);
+    if (interp_smem <= 227 * 1024) {
+      const LoopEntry* e = find_loop({c->vf_id, c->num_derivatives, fact, c->ode_dim, ts0, 0});
+      if (e != nullptr) return e;
+    }
   }
   // K2: lane per dimension, run-time d <= 1024, filter and fixed-point smoother
   //     (several dimensions per lane only for the block-diagonal filter; otherwise d <= 256)

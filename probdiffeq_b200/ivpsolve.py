@@ -132,6 +132,11 @@ def _service_order(cost_hint, B, device):
 
 def _problem(prior, vf, cost_hint=None):
     B = prior.tcoeffs.shape[0]
+    dev = prior.tcoeffs.device
+    if dev.type == "cuda" and dev.index != torch.cuda.current_device():
+        # kernels are launched on the current stream of the CURRENT device, scratch is allocated beside the inputs
+        raise ValueError(f"the ensemble lives on {dev} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                         f"wrap the solve in `with torch.cuda.device({dev.index}):`")
     params, pstride = vf.params_on_device(B)
     pr = _lib.Problem()
     pr.num_instances = B
