@@ -2,6 +2,7 @@
 // step size, terminal-value log-marginal-likelihood. All are generic in the ODE dimension d.
 #include <cuda_runtime.h>
 
+#include "pdeq_aux_dense.cuh"
 #include "pdeq_aux_kernels.cuh"
 
 namespace pdeq {
@@ -334,6 +335,18 @@ AuxRegistrar<Linear> aux_linear;
 AuxRegistrar<Burgers> aux_burgers;
 }  // namespace
 
+// Shared-memory opt-in of a dense auxiliary kernel (pdeq_aux_dense.cuh); -10 when the state does not fit.
+template <class Kern>
+static int auxd_prepare(Kern kern, size_t smem_bytes, const char* what) {
+  if (smem_bytes > 227 * 1024)
+    return api_fail(-10, "%s: the dense state does not fit in shared memory (%zu bytes needed)", what, smem_bytes);
+  if (smem_bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return api_cuda_fail(e, what);
+  }
+  return 0;
+}
+
 extern "C" {
 
 int pdeq_taylor_init(const pdeq_config* cfg, int64_t num_instances, const double* u0, const double* params,
@@ -429,8 +442,19 @@ int pdeq_lml_timeseries(const pdeq_config* cfg, int64_t num_instances, int32_t n
   if (tcoeff_index < 0 || tcoeff_index > cfg->num_derivatives) return api_fail(-5, "bad tcoeff_index");
   int fact = cfg->factorisation;
   if (fact == PDEQ_FACT_DENSE && cfg->ode_dim == 1) fact = PDEQ_FACT_ISOTROPIC;
-  if (fact == PDEQ_FACT_DENSE) return api_fail(-10, "lml_timeseries: dense factorisation with d > 1 not built");
   if (num_instances == 0) return 0;
+  if (fact == PDEQ_FACT_DENSE) {  // CTA per instance, run-time dimensions (pdeq_aux_dense.cuh)
+    const int n = cfg->num_derivatives + 1, d = cfg->ode_dim;
+    const size_t smem = auxd_lml_smem_doubles(n * d, d) * sizeof(double);
+    rc = auxd_prepare(lml_timeseries_dense_kernel, smem, "lml_timeseries (dense)");
+    if (rc != 0) return rc;
+    lml_timeseries_dense_kernel<<<(unsigned)num_instances, AUXD_THREADS, smem, (cudaStream_t)stream>>>(
+        num_gridpoints, n, d, tcoeff_index, average_pdfs, mean, chol, bw_gain, bw_mean, bw_chol, data, data_stride,
+        std, std_stride, out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return api_cuda_fail(e, "lml_timeseries (dense)");
+    return 0;
+  }
   const int64_t total = num_instances * (int64_t)cfg->ode_dim;
   if (workspace == nullptr || workspace_bytes < (size_t)total * sizeof(double))
     return api_fail(-24, "lml_timeseries needs %zu workspace bytes (num_instances * ode_dim doubles)",
@@ -477,8 +501,17 @@ int pdeq_sample_posterior(const pdeq_config* cfg, int64_t num_instances, int32_t
   if (num_gridpoints < 1) return api_fail(-23, "num_gridpoints must be >= 1");
   int fact = cfg->factorisation;
   if (fact == PDEQ_FACT_DENSE && cfg->ode_dim == 1) fact = PDEQ_FACT_ISOTROPIC;
-  if (fact == PDEQ_FACT_DENSE) return api_fail(-10, "sample_posterior: dense factorisation with d > 1 not built");
   if (num_instances == 0 || num_samples == 0) return 0;
+  if (fact == PDEQ_FACT_DENSE) {  // CTA per (instance, sample); base is [B][S][T][n d]
+    const int N = (cfg->num_derivatives + 1) * cfg->ode_dim;
+    if (N > 128) return api_fail(-10, "sample_posterior: dense factorisation supports (nu + 1) d <= 128");
+    sample_dense_kernel<<<(unsigned)(num_instances * num_samples), 64, 2 * N * sizeof(double),
+                          (cudaStream_t)stream>>>(num_samples, num_gridpoints, N, mean, chol, bw_gain, bw_mean,
+                                                  bw_chol, base, out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return api_cuda_fail(e, "sample_posterior (dense)");
+    return 0;
+  }
   const int64_t total = num_instances * (int64_t)num_samples * cfg->ode_dim;
   const int threads = 128;
   const int nblocks = (int)((total + threads - 1) / threads);
@@ -526,8 +559,20 @@ int pdeq_offgrid_marginals(const pdeq_config* cfg, int64_t num_instances, int32_
     return api_fail(-22, "a smoothing solution needs its filtering marginals (filt_mean / filt_chol)");
   int fact = cfg->factorisation;
   if (fact == PDEQ_FACT_DENSE && cfg->ode_dim == 1) fact = PDEQ_FACT_ISOTROPIC;
-  if (fact == PDEQ_FACT_DENSE) return api_fail(-10, "offgrid_marginals: dense factorisation with d > 1 not built");
   if (num_instances == 0 || num_queries == 0) return 0;
+  if (fact == PDEQ_FACT_DENSE) {  // CTA per (instance, query), run-time dimensions (pdeq_aux_dense.cuh)
+    const int N = (cfg->num_derivatives + 1) * cfg->ode_dim;
+    if (cfg->ode_dim > 64) return api_fail(-10, "offgrid_marginals: dense factorisation supports ode_dim <= 64");
+    const size_t smem = auxd_offgrid_smem_doubles(N, smooth) * sizeof(double);
+    rc = auxd_prepare(offgrid_dense_kernel, smem, "offgrid_marginals (dense)");
+    if (rc != 0) return rc;
+    offgrid_dense_kernel<<<(unsigned)(num_instances * num_queries), AUXD_THREADS, smem, (cudaStream_t)stream>>>(
+        *cfg, num_gridpoints, num_queries, smooth ? 1 : 0, grid, queries, mean, chol, filt_mean, filt_chol,
+        output_scale, prior_scale, prior_scale_stride, out_mean, out_chol);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return api_cuda_fail(e, "offgrid_marginals (dense)");
+    return 0;
+  }
   const int64_t total = num_instances * (int64_t)num_queries * cfg->ode_dim;
   const int threads = 64;
   const int nblocks = (int)((total + threads - 1) / threads);

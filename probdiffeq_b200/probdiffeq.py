@@ -677,7 +677,8 @@ class MarkovSequence:
         ``key`` seeds a `torch.Generator` on the device (an int, or a Generator) -- the reference's JAX PRNG stream
         is not reproduced, the arithmetic given the normal draws is. Alternatively pass the draws as ``base``:
         (B, *shape, T, n) for the isotropic model (one draw per coefficient shared by all dimensions, like
-        `IsotropicNormal.sample_flat`), (B, *shape, T, d, n) for the block-diagonal one. Returns a list over Taylor
+        `IsotropicNormal.sample_flat`), (B, *shape, T, d, n) for the block-diagonal one, (B, *shape, T, n d) for the
+        dense one (coefficient-major, like the flat state). Returns a list over Taylor
         coefficients of tensors (B, *shape, T, d); the B axis is absent for an unbatched posterior."""
         mean, chol = self.marginal.mean_flat, self.marginal.cholesky_flat
         gain, cmean, cchol = self.conditional.gain, self.conditional.mean, self.conditional.cholesky
@@ -687,7 +688,7 @@ class MarkovSequence:
         B, n, d = mean.shape
         T = cmean.shape[1]
         fact = self.marginal.factorisation
-        core = (T, n) if fact == "isotropic" else (T, d, n)
+        core = {"isotropic": (T, n), "blockdiag": (T, d, n)}.get(fact, (T, n * d))  # dense: one draw per state entry
         if base is None:
             gen = key if isinstance(key, torch.Generator) else torch.Generator(device=mean.device)
             if not isinstance(key, torch.Generator):
