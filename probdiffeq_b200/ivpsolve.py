@@ -116,9 +116,10 @@ def _service_order(cost_hint, B, device):
     index, the 32 lanes of a warp start on 32 neighbours of the order -- equally long instances -- and keep finishing
     (and refilling) together. Results do not depend on it.
 
-    Measured on the thread-per-instance kernel (scripts/sweep_k1_order.py, 2^17 instances = 2.3 per lane): index order
-    2.64 ms, longest-first 2.37 ms; with 18 per lane the sort costs more than it gains -- many rounds even out by
-    themselves -- hence COST_HINT_MAX_ROUNDS. (A planned queue that reserves the cheapest instances for the lanes that
+    Measured on the thread-per-instance kernel with a fitted quadratic cost model (scripts/sweep_k1_order.py,
+    profiles/r2w_sweep_k1_order.jsonl): 2^17 instances (2.3 per lane) 2.63 -> 2.31 ms, 2^18: 4.71 -> 4.41, 2^19 (9.2
+    per lane): 8.82 -> 8.59; at 2^20 (18 per lane) evaluating and sorting the hint costs more than the order gains
+    (16.89 -> 17.01) -- many rounds even out by themselves -- hence COST_HINT_MAX_ROUNDS. (A planned queue that reserves the cheapest instances for the lanes that
     must serve one instance more than the others looked 7 % better in a lane-level simulation and measured 7 % worse
     than longest-first; it was removed.)"""
     hint = torch.as_tensor(cost_hint, device=device).reshape(-1)
@@ -154,7 +155,7 @@ def _problem(prior, vf, cost_hint=None):
     return pr, (params, order)
 
 
-COST_HINT_MAX_ROUNDS = 8  # instances per resident lane above which `cost_hint` is ignored
+COST_HINT_MAX_ROUNDS = 12  # instances per resident lane above which `cost_hint` is ignored (9.2: -2.6 %, 18.4: +0.7 %)
 POSTERIOR_AUTO_BYTES = 2 << 30  # smoothers return their backward conditionals by default up to this size
 
 
