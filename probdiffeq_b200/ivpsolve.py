@@ -159,21 +159,29 @@ COST_HINT_MAX_ROUNDS = 12  # instances per resident lane above which `cost_hint`
 POSTERIOR_AUTO_BYTES = 2 << 30  # smoothers return their backward conditionals by default up to this size
 
 
-def _alloc_solution(prior, T, want_chol=True, trace_capacity=0, want_posterior=False):
+def _alloc_solution(prior, T, want_chol=True, trace_capacity=0, want_posterior=False, nan_fill=True):
+    """Output buffers of one solve. `nan_fill`: an instance that gives up (status MAX_ATTEMPTS) leaves its remaining
+    checkpoints unwritten in the lane-per-dimension and dense kernels, so those read NaN instead of whatever the
+    allocator handed out; the thread-per-instance kernel writes the NaNs itself (pdeq_loop_thread.cuh: emit_nan), and
+    its callers skip the fill -- for the headline ensemble it would be a 190 MB memset per solve."""
     B, n, d = prior.tcoeffs.shape
     dev = prior.tcoeffs.device
     fact = prior.factorisation
     f64 = dict(dtype=torch.float64, device=dev)
+
+    def fresh(shape):
+        return torch.full(shape, float("nan"), **f64) if nan_fill else torch.empty(shape, **f64)
+
     chol_shape = {"isotropic": (B, T, n, n), "blockdiag": (B, T, d, n, n), "dense": (B, T, n * d, n * d)}[fact]
     if fact == "dense" and d == 1:
         chol_shape = (B, T, n, n)
     scale_shape = (B, T, d) if fact == "blockdiag" else (B, T)
     bufs = dict(
-        t=torch.empty((B, T), **f64),
-        mean=torch.empty((B, T, n, d), **f64),
-        chol=torch.empty(chol_shape, **f64) if want_chol else None,
-        output_scale=torch.empty(scale_shape, **f64),
-        num_steps=torch.empty((B, T), dtype=torch.int32, device=dev),
+        t=fresh((B, T)),
+        mean=fresh((B, T, n, d)),
+        chol=fresh(chol_shape) if want_chol else None,
+        output_scale=fresh(scale_shape),
+        num_steps=(torch.zeros if nan_fill else torch.empty)((B, T), dtype=torch.int32, device=dev),
         num_attempts=torch.empty((B,), dtype=torch.int32, device=dev),
         status=torch.empty((B,), dtype=torch.int32, device=dev),
     )
@@ -263,8 +271,14 @@ def _run_adaptive(prior, solver, error, control, clip_dt, save_at, atol, rtol, d
     if dt0_t.shape[0] not in (1, B):
         raise ValueError("dt0 must be a scalar or have one entry per ensemble member.")
     pr, keep = _problem(prior, solver.constraint.ode, cost_hint)
+    # the thread-per-instance kernel (filters of a compile-time d <= 8, not dense) fills abandoned checkpoints itself
+    _, n_, d_ = prior.tcoeffs.shape
+    interp_bytes = 0 if clip_dt else (n_ * d_ + (d_ if prior.factorisation == "blockdiag" else 1) * n_ * n_ + 1) * 1024
+    on_k1 = (solver.strategy.kind == "filter" and prior.factorisation != "dense" and d_ <= 8
+             and interp_bytes <= 227 * 1024)  # pdeq_api.cu: select_loop
     so, bufs = _alloc_solution(prior, T, want_chol, trace_capacity,
-                               _want_posterior(want_posterior, solver, prior, T, want_chol) and not terminal)
+                               _want_posterior(want_posterior, solver, prior, T, want_chol) and not terminal,
+                               nan_fill=not on_k1)
     if B > 0:  # an empty ensemble returns empty arrays (there is nothing to launch)
         ws, nbytes = _workspace(cfg, B, T, prior.tcoeffs.device)
         rc = _lib.load().pdeq_solve_adaptive_save_at(

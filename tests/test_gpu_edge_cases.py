@@ -141,6 +141,23 @@ def test_attempt_guard_reports_status(cuda):
     assert np.all(sol.status.cpu().numpy() == 2) and np.all(sol.num_attempts.cpu().numpy() == 5)
 
 
+@pytest.mark.parametrize("fact,strategy", [("isotropic", "filter"), ("blockdiag", "fixedpoint"), ("dense", "filter"),
+                                           ("dense", "fixedpoint")])  # fmt: skip
+def test_abandoned_checkpoints_read_nan_not_garbage(cuda, fact, strategy):
+    """An instance that hits max_attempts reports status 2, and the checkpoints it never reached are NaN in every
+    kernel (thread-per-instance: written by the kernel; lane-per-dimension and dense: the host pre-fills)."""
+    s = H.spec(fact=fact, strategy=strategy, clip_dt=False, error="residual_std", control="i")
+    params, u0 = H.lv_ensemble(4, seed=9)
+    p_pdq, p_ivp, vf, ssm, solver, err, ctrl = H.product_build(s, params)
+    tcoeffs, _ = p_pdq.jetexpand_ode_padded_scan(num=4)(vf, (u0,), t=0.0)
+    solve = p_ivp.solve_adaptive_save_at(solver=solver, error=err, control=ctrl, max_attempts=6, warn=False)
+    sol = solve(ssm.prior_wiener_integrated(tcoeffs), save_at=np.linspace(0.0, 50.0, 6), atol=1e-8, rtol=1e-6)
+    assert np.all(sol.status.cpu().numpy() == 2) and np.all(sol.num_attempts.cpu().numpy() == 6)
+    mean = sol.u.mean_flat.cpu().numpy()
+    assert np.all(np.isfinite(mean[:, 0])) and np.all(np.isnan(mean[:, -1]))
+    assert np.all(np.isnan(sol.t[:, -1].cpu().numpy()))
+
+
 def test_dt0_adaptive_matches_oracle(cuda):
     params, u0 = H.lv_ensemble(16, seed=8)
     p_pdq, p_ivp, vf, *_ = H.product_build(H.spec(), params)
