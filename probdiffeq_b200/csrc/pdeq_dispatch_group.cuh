@@ -60,7 +60,8 @@ cudaError_t k2_plan(const pdeq_config& cfg, int64_t B, int32_t T, bool needs_int
   } else {
     // warp per instance: 4, 2 or 1 instances per CTA -- whichever keeps the most instances resident per SM (the
     // smoother's 40+ KB per instance fit five times into an SM only as single-warp CTAs)
-    const size_t per_group = GL::smem_doubles_per_group(d, needs_interp, true) * sizeof(double);
+    plan->wk_global = FP && PDEQ_K2_WARP_WK_GLOBAL;
+    const size_t per_group = GL::smem_doubles_per_group(d, needs_interp, !plan->wk_global) * sizeof(double);
     if (per_group > kSmemMax) return cudaErrorInvalidValue;
     int best_groups = 0;
     for (int gpc = 4; gpc >= 1; gpc /= 2) {

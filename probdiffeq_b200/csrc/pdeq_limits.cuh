@@ -7,6 +7,12 @@
 #ifndef PDEQ_K3_TPC2_MAX_N
 #define PDEQ_K3_TPC2_MAX_N 48
 #endif
+// Where the warp-per-instance smoother keeps its working columns: 1 = an L2-resident global slot per resident warp
+// (24 KB of shared memory per instance, 8 warps per SM -- the register limit), 0 = shared memory (44 KB, 5 warps per
+// SM). Config 3 on B200: 2.19 s -> 1.73 s with 1.
+#ifndef PDEQ_K2_WARP_WK_GLOBAL
+#define PDEQ_K2_WARP_WK_GLOBAL 1
+#endif
 #ifndef PDEQ_K3_MIN_BLOCKS
 #define PDEQ_K3_MIN_BLOCKS 3
 #endif

@@ -252,8 +252,8 @@ struct GroupLoop {
   // is overstepped) lives in an L2-resident global scratch slot instead of shared memory: it halves the shared
   // memory per instance and doubles the number of resident warps (4 -> 8 per SM for Pleiades).
   static constexpr bool IF_GLOBAL = FP;
-  // wk_smem: the smoother's working columns live in shared memory (always in warp mode; in CTA mode only when they
-  // fit, otherwise in an L2-resident global slot per resident group).
+  // wk_smem: the smoother's working columns live in shared memory (warp mode: per PDEQ_K2_WARP_WK_GLOBAL; CTA mode:
+  // when they fit), otherwise in an L2-resident global slot per resident group.
   PDEQ_HDI static constexpr size_t smem_doubles_per_group(int d, bool needs_interp, bool wk_smem = true) {
     return (size_t)((needs_interp && !IF_GLOBAL) ? 2 : 1) * NF * d + (size_t)q * d + 32 +
            (wk_smem ? (size_t)NFW * d : 0);
@@ -294,9 +294,16 @@ struct GroupLoop {
     double* st_if = IF_GLOBAL ? if_scratch + group_slot * (size_t)NF * d : base + NF * d;
     double* exch = base + ((needs_interp && !IF_GLOBAL) ? 2 : 1) * NF * d;
     g.red = exch + q * d;
-    // (warp mode: always shared memory -- said so at compile time, so that the accesses are LDS / STS, not generic)
+    // The smoother's working columns: shared memory, or an L2-resident global slot per resident group. Which one is
+    // said at compile time for the warp mode (pdeq_limits.cuh: PDEQ_K2_WARP_WK_GLOBAL), so that its accesses are
+    // LDS / STS or LDG / STG, never generic; the CTA mode goes global only when shared memory cannot hold them.
+#if PDEQ_K2_WARP_WK_GLOBAL
+    double* wk = !FP ? nullptr
+                     : ((!CTA || wk_scratch != nullptr) ? wk_scratch + group_slot * (size_t)NFW * d : g.red + 32);
+#else
     double* wk = !FP ? nullptr
                      : ((CTA && wk_scratch != nullptr) ? wk_scratch + group_slot * (size_t)NFW * d : g.red + 32);
+#endif
     // global scratch ring for the per-checkpoint conditionals of the instance this group is working on
     double* ring = FP ? cond_ring + group_slot * (size_t)T * NFC * d : nullptr;
 
