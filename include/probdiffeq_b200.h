@@ -168,6 +168,9 @@ int pdeq_vf_dim(int vf_id);
    instantiation macros, which registers its launchers under this id when loaded (probdiffeq_b200/plugins.py).
    The reference takes any Python callable (`probdiffeq.ode`, problems.py:283-312); this is the device-side equivalent. */
 int pdeq_register_vf(const char* name, int32_t ode_order, int32_t num_params, int32_t fixed_dim);
+/* Drop every kernel registered under a run-time vector-field id (returns how many loop kernels went): called before a
+   NAME is given a different right-hand side, so that no kernel of the old code can be selected for it any more. */
+int pdeq_vf_clear_kernels(int vf_id);
 
 /* 0 if (cfg) is a combination the library has a kernel for, negative otherwise (see pdeq_last_error). */
 int pdeq_config_supported(const pdeq_config* cfg);

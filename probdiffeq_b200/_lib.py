@@ -96,6 +96,7 @@ SYMBOLS = {
     "pdeq_vf_ode_order": (C.c_int, [C.c_int]),
     "pdeq_vf_dim": (C.c_int, [C.c_int]),
     "pdeq_register_vf": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, C.c_int32]),
+    "pdeq_vf_clear_kernels": (C.c_int, [C.c_int]),
     "pdeq_config_supported": (C.c_int, [_P(Config)]),
     "pdeq_workspace_bytes": (C.c_size_t, [_P(Config), C.c_int64, C.c_int32]),
     "pdeq_taylor_init": (

@@ -206,6 +206,27 @@ int pdeq_register_vf(const char* name, int32_t ode_order, int32_t num_params, in
   return (int)vf_table().size() - 1;
 }
 
+int pdeq_vf_clear_kernels(int vf_id) {
+  if (vf_info(vf_id) == nullptr) return fail(-2, "unknown vf_id %d", vf_id);
+  if (vf_id < 6) return fail(-2, "the kernels of the built-in vector field '%s' cannot be dropped", vf_info(vf_id)->name);
+  auto& loops = loop_table();
+  int dropped = 0;
+  for (size_t i = 0; i < loops.size();) {
+    if (loops[i].key.vf == vf_id) {
+      loops.erase(loops.begin() + (long)i);
+      ++dropped;
+    } else {
+      ++i;
+    }
+  }
+  auto& aux = aux_registry();
+  for (size_t i = 0; i < aux.size();) {
+    if (aux[i].vf_id == vf_id) aux.erase(aux.begin() + (long)i);
+    else ++i;
+  }
+  return dropped;
+}
+
 int pdeq_config_supported(const pdeq_config* cfg) {
   int rc = validate(cfg);
   if (rc != 0) return rc;

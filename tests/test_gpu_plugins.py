@@ -202,3 +202,38 @@ def test_plugin_jacobian_by_forward_mode_differentiation(cuda):
     assert np.allclose(a[:, :, 0], h[:, :, 0], rtol=1e-11, atol=1e-13)
     assert np.allclose(a, h, rtol=1e-6, atol=1e-9)
     assert np.allclose(sol_auto.u.std_flat.cpu().numpy(), sol_hand.u.std_flat.cpu().numpy(), rtol=1e-6, atol=1e-12)
+
+
+def test_reregistering_a_name_with_new_code_replaces_every_kernel(cuda):
+    """The same name registered twice with different bodies (same signature): the second plug-in's kernels must serve
+    the step loop AND the Taylor initialisation / dt0 -- register_loop replaces an entry with an equal key, as
+    register_aux does (the loop used to keep the first functor while the auxiliaries took the second)."""
+    import torch
+
+    from probdiffeq_b200 import plugins
+
+    rng = np.random.Generator(np.random.PCG64(75))
+    B = 4
+    params = np.stack([rng.uniform(0.5, 1.5, size=B), rng.uniform(2.0, 5.0, size=B)], axis=1)
+    u0 = rng.uniform(0.1, 1.0, size=(B, 1))
+    save_at = np.linspace(0.0, 2.0, 9)
+
+    def exact(rate_factor):
+        k, r = params[:, 1:2], rate_factor * params[:, 0:1]
+        return k / (1.0 + (k / u0 - 1.0) * np.exp(-r * save_at[None, :]))
+
+    vf1 = plugins.ode_from_cuda("logistic_swap", params=params, **plugins.LOGISTIC)
+    _, _, sol1 = _solve(vf1, u0)
+    vf2 = plugins.ode_from_cuda("logistic_swap", params=params, **plugins.LOGISTIC_DOUBLED)
+    assert vf2.vf_id == vf1.vf_id
+    tc2, _, sol2 = _solve(vf2, u0)
+    torch.cuda.synchronize()
+    got1, got2 = sol1.u.mean_flat[:, :, 0, 0].cpu().numpy(), sol2.u.mean_flat[:, :, 0, 0].cpu().numpy()
+    assert np.allclose(got1, exact(1.0), rtol=1e-3)
+    assert np.allclose(got2, exact(2.0), rtol=1e-3) and not np.allclose(got2, exact(1.0), rtol=1e-2)
+    f0 = 2.0 * params[:, 0] * u0[:, 0] * (1.0 - u0[:, 0] / params[:, 1])  # first Taylor coefficient of the new body
+    assert np.allclose(tc2[:, 1, 0].cpu().numpy(), f0, rtol=1e-13)
+    # and back again: the first plug-in is already loaded, its registrars must run again
+    vf3 = plugins.ode_from_cuda("logistic_swap", params=params, **plugins.LOGISTIC)
+    _, _, sol3 = _solve(vf3, u0)
+    assert torch.equal(sol3.u.mean_flat, sol1.u.mean_flat)
