@@ -521,6 +521,7 @@ def run_ours(args) -> None:
         ms = [a.elapsed_time(b) for a, b in evs]
         if tag and tag != "cfg":
             per_step[tag] = [round(x, 3) for x in ms]
+        per_step["_last"] = ms
         return sum(ms) / len(ms), last
 
     def timed_pipelined(fn, steps, warmup):
@@ -722,7 +723,15 @@ def run_ours(args) -> None:
                 dev_in = {k: v.to(dev) for k, v in pinned.items()}
                 run = spec["make"](dev_in)
                 ms_c, (csol, extra) = timed(run, args.config_steps, 1, "cfg")
-                launches += args.config_steps * spec["launches"]
+                n_passes = args.config_steps
+                launches += n_passes * spec["launches"]
+                if reduce_max(ms_c)[0] < 200.0:  # decided collectively: every rank must time the same passes
+                    # a short pass (configs 4b, 5): one 10-20 ms hiccup of the box (seen about once per 40 launches, also
+                    # in the headline's per-step list) would be most of it -- time more passes and report their median
+                    n_passes = max(args.config_steps, min(15, int(600.0 / max(reduce_max(ms_c)[0], 1.0))))
+                    _, (csol, extra) = timed(run, n_passes, 1, "cfg")
+                    launches += n_passes * spec["launches"]
+                    ms_c = statistics.median(per_step["_last"])
                 Bl = csol.num_steps.shape[0]
                 c_steps = int(csol.num_steps.reshape(Bl, -1)[:, -1].sum().item())
                 c_att = int(csol.num_attempts.sum().item())
@@ -755,7 +764,8 @@ def run_ours(args) -> None:
                     "ms_per_pass": ms_c, "value": c_steps / (ms_c * 1e-3), "unit": UNIT,
                     "attempts_per_s": c_att / (ms_c * 1e-3), "accepted_steps_per_pass": c_steps,
                     "attempts_per_pass": c_att, "rejection_ratio": 1.0 - c_steps / max(c_att, 1),
-                    "failed_instances": c_bad, "timed_passes": args.config_steps,
+                    "failed_instances": c_bad, "timed_passes": n_passes,
+                    "statistic": "mean over the timed passes" if n_passes == args.config_steps else "median over the timed passes",
                     "timed_region": "H2D-resident u0/params -> Taylor init, dt0, solve" + (", lml" if spec.get("lml") else ""),
                     "roofline": {"bound": "fp64", "achieved": tfl, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
                                  "frac": tfl / fp64_peak_tflops, "flops_per_attempt": fl, "flops_model": spec["flops_model"],
@@ -868,7 +878,7 @@ def run_ours(args) -> None:
                         "peak_source": "MEASURED_PEAKS.json" if peaks_path.exists() else "fallback 6.65 TB/s"},
             },
             "clocks": clocks,
-            "ms_steps": per_step,
+            "ms_steps": {k: v for k, v in per_step.items() if not k.startswith("_")},
         }  # fmt: skip
         if weak is not None:
             line["weak"] = weak
