@@ -491,15 +491,17 @@ def run_ours(args) -> None:
         # Warm-up holds the previous step's result while the next one is produced, exactly as the timed loop below does
         # (`last`): both sets of output buffers then sit in torch's caching allocator, and no timed step pays for a
         # cudaMalloc (which would stall the launch behind it for tens of milliseconds).
-        held = None
+        held = cur = None
         host_ms = 0.0
-        for _ in range(max(warmup, 2) if tag != "cfg" else warmup):
+        for _ in range(max(warmup, 2)):
             h0 = time.perf_counter()
             cur = fn()
             host_ms = (time.perf_counter() - h0) * 1e3  # how long the HOST takes to enqueue one step
             flush.fill_(1)
             held = cur
-        del held
+        # BOTH names go: a surviving `cur` kept a third set of output buffers alive, and the second timed step then
+        # paid for a cudaMalloc with the device idle inside its event pair (r2o, r2y: 16.9, 41.7, 16.9, ... ms)
+        del held, cur
         barrier()
         if tag != "cfg" and os.environ.get("PDEQ_BENCH_NO_PRIME") != "1":
             # A shard's step is a few milliseconds at N = 8 -- the order of what Python needs to enqueue it (with eight
