@@ -1,0 +1,185 @@
+"""Generate tests/golden/reference_numpy_backend.npz: outputs of the REFERENCE's own step loop.
+
+JAX cannot be installed here, but the reference touches JAX only through `probdiffeq/backend/`; `oracle/refshim`
+supplies that interface on NumPy, so the reference's unmodified modules (`/root/reference/probdiffeq/_ivpsolve`,
+`_probdiffeq`, `util`) run as they are.  This script runs them on the cases below, compares every output with the
+oracle (it must agree, or the script fails), and writes the reference's outputs as fixtures; the tests then hold the
+oracle (CPU) and the CUDA path (GPU) against them:
+
+    python tests/golden/make_reference_golden.py           # needs /root/reference; ~2 minutes
+
+What the fixtures are: results of the reference's algorithm code, line for line, in NumPy float64 arithmetic with
+SciPy's LAPACK.  What they are not: bit-for-bit XLA output (operation fusion, XLA's own QR).  Taylor coefficients of
+the initial condition are an INPUT (the reference computes them with `jax.experimental.jet`, which the shim does not
+reproduce; they come from the oracle's truncated-series arithmetic and are stored in the fixtures).
+"""
+
+import json
+import pathlib
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import pdeq_test_helpers as H  # noqa: E402
+from oracle import problems as o_problems  # noqa: E402
+from oracle import probdiffeq as o_pdq  # noqa: E402
+from oracle import refshim  # noqa: E402
+
+OUT = pathlib.Path(__file__).resolve().parent / "reference_numpy_backend.npz"
+
+LV = dict(vf="lotka_volterra", nu=4, params=[0.55, 0.045, 0.52, 0.055], u0=[21.0, 19.0])
+CASES = []
+
+
+def case(name, kind, grid, atol=None, rtol=None, dt0=0.1, problem=LV, **spec):
+    CASES.append(dict(name=name, kind=kind, grid=list(map(float, grid)), atol=atol, rtol=rtol, dt0=dt0,
+                      problem=problem, spec=H.spec(vf=problem["vf"], **spec)))  # fmt: skip
+
+
+# BASELINE configs[0/1]: one instance of the headline ensemble at its full horizon
+case("lv_iso_ts0_terminal_t50", "terminal", [0.0, 50.0], 1e-8, 1e-6)
+for fact in ("isotropic", "blockdiag", "dense"):
+    # adaptive save_at without step clipping (interpolation at the checkpoints), three solver / error combinations
+    case(f"lv_{fact}_solver_residual_i", "save_at", np.linspace(0.0, 4.0, 9), 1e-7, 1e-5, fact=fact, clip_dt=False,
+         error="residual_std", control="i")  # fmt: skip
+    case(f"lv_{fact}_dynamic_residual_i", "save_at", np.linspace(0.0, 4.0, 9), 1e-7, 1e-5, fact=fact, clip_dt=False,
+         solver="solver_dynamic", error="residual_std", control="i")  # fmt: skip
+    case(f"lv_{fact}_mle_state_pi_ts1", "save_at", np.linspace(0.0, 4.0, 9), 1e-7, 1e-5, fact=fact, clip_dt=False,
+         solver="solver_mle", constraint="ts1")  # fmt: skip
+    # fixed-point smoother
+    case(f"lv_{fact}_fixedpoint_mle", "save_at", np.linspace(0.0, 3.0, 7), 1e-5, 1e-4, fact=fact, clip_dt=False,
+         strategy="fixedpoint", solver="solver_mle", error="residual_std", control="i")  # fmt: skip
+    # fixed grid: filter and fixed-interval smoother
+    case(f"lv_{fact}_fixedgrid_filter", "fixed", np.linspace(0.0, 1.0, 21), fact=fact)
+    case(f"lv_{fact}_fixedgrid_fixedinterval_mle", "fixed", np.linspace(0.0, 1.0, 21), fact=fact,
+         strategy="fixedinterval", solver="solver_mle")  # fmt: skip
+# BASELINE configs[3]: HIRES, dense ts1, dynamic calibration, residual error, PI, at BASELINE's tolerances (a short
+# horizon; at looser tolerances the step-size sequence of this stiff problem is not reproducible to the last step even
+# between the oracle and its own 1-ulp perturbation)
+case("hires_dense_ts1_dynamic", "terminal", [0.0, 2.0], 1e-11, 1e-8, dt0=1e-4,
+     problem=dict(vf="hires", nu=5, params=[], u0=list(o_problems.hires_u0())),
+     fact="dense", constraint="ts1", solver="solver_dynamic", error="residual_std")  # fmt: skip
+# BASELINE configs[2]: Pleiades, block-diagonal ts0, fixed-point smoother (a short horizon)
+case("pleiades_blockdiag_fixedpoint", "save_at", np.linspace(0.0, 0.3, 4), 1e-9, 1e-6, dt0="dt0()",
+     problem=dict(vf="pleiades", nu=5, params=[], u0=list(o_problems.pleiades_u0())),
+     fact="blockdiag", strategy="fixedpoint", solver="solver_dynamic", error="residual_std", control="i",
+     clip_dt=False)  # fmt: skip
+
+
+def reference_vf(pdq, problem):
+    fn, order, _np_, _default = o_problems._REGISTRY[problem["vf"]]
+    p = tuple(problem["params"])
+    jac = pdq.jacobian_materialize()
+    if order == 1:
+        return pdq.ode(lambda y, /, *, t: fn(o_problems._NumpyOps, p, t, y), jacobian=jac)
+    return pdq.ode_order_two(lambda y, dy, /, *, t: fn(o_problems._NumpyOps, p, t, y, dy), jacobian=jac)
+
+
+def run_reference(c):
+    ivp, pdq = refshim.load()
+    s, prob = c["spec"], c["problem"]
+    vf = reference_vf(pdq, prob)
+    ssm, solver, err, ctrl = H._build(pdq, ivp, s, vf)
+    tcoeffs = [np.asarray(x) for x in c["tcoeffs"]]
+    prior = ssm.prior_wiener_integrated(tcoeffs)
+    grid = np.asarray(c["grid"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if c["kind"] == "terminal":
+            solve = ivp.solve_adaptive_terminal_values(solver=solver, error=err, control=ctrl, clip_dt=s["clip_dt"])
+            return solve(prior, t0=grid[0], t1=grid[1], atol=c["atol"], rtol=c["rtol"], dt0=c["dt0"])
+        if c["kind"] == "save_at":
+            solve = ivp.solve_adaptive_save_at(solver=solver, error=err, control=ctrl, clip_dt=s["clip_dt"], warn=False)
+            return solve(prior, save_at=grid, atol=c["atol"], rtol=c["rtol"], dt0=c["dt0"])
+        return ivp.solve_fixed_grid(solver=solver)(prior, grid=grid)
+
+
+def run_oracle(c):
+    s, prob = c["spec"], c["problem"]
+    params = np.asarray(prob["params"]) if prob["params"] else None
+    tc = np.asarray(c["tcoeffs"])
+    grid = np.asarray(c["grid"])
+    if c["kind"] == "fixed":
+        return H.oracle_solve_fixed(s, tc, params, grid)
+    sol, _ = H.oracle_solve_save_at(s, tc, params, grid, c["atol"], c["rtol"], dt0=c["dt0"])
+    return sol.terminal() if c["kind"] == "terminal" else sol
+
+
+def _cov(L):
+    L = np.asarray(L)
+    return L @ np.swapaxes(L, -1, -2)
+
+
+def reference_arrays(sol):
+    """t, num_steps, output_scale, mean and covariance in the reference's own flat layouts (mean_flat / cholesky_flat:
+    isotropic (n, d) / (n, n); block-diagonal (d, n) / (d, n, n); dense (n d,) / (n d, n d); leading T if any)."""
+    return dict(t=np.asarray(sol.t), num_steps=np.asarray(sol.num_steps), output_scale=np.asarray(sol.output_scale),
+                mean=np.asarray(sol.u.mean_flat), cov=_cov(sol.u.cholesky_flat))  # fmt: skip
+
+
+def oracle_arrays(osol, batched):
+    u = osol.u
+    if isinstance(u, list):
+        mean, cov = np.stack([r.mean for r in u]), np.stack([_cov(r.chol) for r in u])
+    else:
+        mean, cov = np.asarray(u.mean), _cov(u.chol)
+    return dict(t=np.asarray(osol.t), num_steps=np.asarray(osol.num_steps), mean=mean, cov=cov,
+                output_scale=np.asarray(osol.output_scale))  # fmt: skip
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def main():
+    if not refshim.available():
+        raise SystemExit("needs the reference sources under /root/reference")
+    out, report = {}, []
+    for c in CASES:
+        prob = c["problem"]
+        ovf = o_pdq.ode(prob["vf"], np.asarray(prob["params"]) if prob["params"] else None)
+        inits = [np.asarray(prob["u0"])] if ovf.order == 1 else [np.asarray(prob["u0"]), np.zeros(len(prob["u0"]))]
+        c["tcoeffs"] = np.asarray(ovf.taylor_coefficients(inits, c["grid"][0], prob["nu"]))
+        if c["dt0"] == "dt0()":  # ivpsolve.dt0 (stepsize_initialisers.py:7-21), evaluated by the oracle
+            from oracle import ivpsolve as o_ivp
+
+            c["dt0"] = float(o_ivp.dt0(ovf, tuple(inits), t=c["grid"][0]))
+        ref = reference_arrays(run_reference(c))
+        # the reference's OWN sensitivity to a one-ulp change of its input (dt0, or the Taylor coefficients on a fixed
+        # grid): the yardstick for every quantity the tests compare (tolerance = max(stated, 100 x this))
+        eps = 2.3e-16
+        pert = dict(c, tcoeffs=c["tcoeffs"] * (1.0 + eps)) if c["kind"] == "fixed" else dict(c, dt0=c["dt0"] * (1.0 + eps))
+        prt = reference_arrays(run_reference(pert))
+        same_seq = bool(np.array_equal(prt["num_steps"], ref["num_steps"]))
+        sens = dict(mean=rel(prt["mean"], ref["mean"]), cov=rel(prt["cov"], ref["cov"]),
+                    output_scale=rel(prt["output_scale"], ref["output_scale"]), same_step_counts=same_seq)  # fmt: skip
+        ora = oracle_arrays(run_oracle(c), c["kind"] != "terminal")
+        # the reference returns the initial point as part of save_at / fixed-grid solutions; the oracle likewise
+        assert ref["mean"].shape == ora["mean"].shape, (c["name"], ref["mean"].shape, ora["mean"].shape)
+        same_steps = bool(np.array_equal(ref["num_steps"], ora["num_steps"]))
+        row = dict(case=c["name"], steps=int(np.max(ref["num_steps"])), same_step_counts=same_steps,
+                   rel_t=rel(ref["t"], ora["t"]), rel_mean=rel(ref["mean"], ora["mean"]),
+                   rel_cov=rel(ref["cov"], ora["cov"]), rel_scale=rel(ref["output_scale"], ora["output_scale"]))  # fmt: skip
+        report.append(row)
+        print(json.dumps(row), flush=True)
+        assert same_steps, row
+        for k, v in ref.items():
+            out[f"{c['name']}/{k}"] = v
+        out[f"{c['name']}/tcoeffs"] = c["tcoeffs"]
+        meta = {k: c[k] for k in ("name", "kind", "grid", "atol", "rtol", "dt0", "problem", "spec")}
+        meta["reference_one_ulp_sensitivity"] = sens
+        row["reference_one_ulp_sensitivity"] = sens
+        out[f"{c['name']}/meta"] = np.asarray(json.dumps(meta))
+    np.savez_compressed(OUT, **out)
+    (OUT.with_suffix(".report.json")).write_text(json.dumps(report, indent=1))
+    print("wrote", OUT, OUT.stat().st_size, "bytes")
+
+
+if __name__ == "__main__":
+    main()
