@@ -387,12 +387,23 @@ class _ProbabilisticSolver:
         """The optional Bayes update at t0 (solvers.py:361-372, 526-537, 670-680): linearise `constraint_init` at the
         initial state and condition on a zero residual, the gain through the minimum-norm least-squares solve
         (`linalg.lstsq_svd`) because the initial observation factor may be singular (exact Taylor coefficients)."""
+        u0, posterior, _rms = self._init_update_and_rms(u_pred, prediction, t=t, damp=damp)
+        return u0, posterior
+
+    def _init_update_and_rms(self, u_pred, prediction, *, t, damp):
+        """... and the whitened RMS residual of that update, which `solver_mle` takes as the first term of its running
+        calibration (solvers.py:361-374: `bayes_rule_and_residual_whitened_rms_tree`, `num_data = 1.0`). The residual
+        is whitened by a plain triangular solve with the observed factor (ssm_impl_isotropic.py:203-207), not by the
+        least-squares solve of the gain: a singular observed factor gives NaN there, as in the reference."""
         if self.constraint_init is None:
-            return u_pred, prediction
+            return u_pred, prediction, None
         fx_init, _ = self.constraint_init.linearize(u_pred, self.constraint_init.init_linearization(), damp=damp, t=t)
-        _, reverted = fx_init.revert(u_pred, solve=linalg.lstsq_triu)
-        updates = reverted.apply_flat(np.zeros_like(fx_init.noise.mean))
-        return self.strategy.apply_updates(prediction, updates=updates)
+        observed, reverted = fx_init.revert(u_pred, solve=linalg.lstsq_triu)
+        zeros = np.zeros_like(fx_init.noise.mean)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rms = fx_init.alg.residual_whitened_rms(observed, zeros)
+        updates = reverted.apply_flat(zeros)
+        return (*self.strategy.apply_updates(prediction, updates=updates), rms)
 
     @property
     def is_suitable_for_save_at(self):
@@ -516,10 +527,13 @@ class solver_mle(_ProbabilisticSolver):
     def init(self, t, u, *, damp):
         prior = u
         u_pred, prediction = self.strategy.init_posterior(u=prior.init)
-        u0, posterior = self._init_update(u_pred, prediction, t=t, damp=damp)
+        u0, posterior, rms0 = self._init_update_and_rms(u_pred, prediction, t=t, damp=damp)
         output_scale_prior = np.ones_like(prior.alg.prototype_output_scale(u_pred))
         fx = self._zeros_like_fx(u_pred, t, damp)
-        auxiliary = (None, np.zeros_like(output_scale_prior), 0.0)
+        if rms0 is None:
+            auxiliary = (None, np.zeros_like(output_scale_prior), 0.0)
+        else:  # solvers.py:366-374: the update at t0 is the first datum of the calibration
+            auxiliary = (None, rms0 * np.ones_like(output_scale_prior), 1.0)
         return ProbabilisticSolution(
             t=t, u=u0, solution_full=posterior, auxiliary=auxiliary,
             output_scale=output_scale_prior, num_steps=0, fun_evals=fx, prior=prior,

@@ -38,10 +38,43 @@ class _AtIndex:
         return self.arr[self.idx]
 
 
+def _is_int_scalar(i):
+    return isinstance(i, (int, _np.integer)) or (isinstance(i, _np.ndarray) and i.ndim == 0 and i.dtype.kind in "iu")
+
+
 class Arr(_np.ndarray):
     @property
     def at(self):
         return _At(self)
+
+    def __iter__(self):
+        # ndarray iterates by calling __getitem__ until IndexError; with the clamping below that would never end
+        if self.ndim == 0:
+            raise TypeError("iteration over a 0-d array")
+        return iter([_np.ndarray.__getitem__(self, i) for i in range(self.shape[0])])
+
+    def __getitem__(self, idx):
+        """NumPy indexing, except that an out-of-range INTEGER index is clamped to the last (first) entry instead of
+        raising: JAX's gather semantics, which the reference relies on in `offgrid_marginals` (solvers.py:173-185
+        indexes every leaf of the solution with the interval index -- also leaves that have no time axis, whose
+        value is then unused -- and `output_scale[T - 1]` of T - 1 entries for the last interval)."""
+        try:
+            return super().__getitem__(idx)
+        except IndexError:
+            items = idx if isinstance(idx, tuple) else (idx,)
+            clamped, axis = [], 0
+            for i in items:
+                if _is_int_scalar(i) and axis < self.ndim:
+                    size = self.shape[axis]
+                    i = int(i)
+                    i = i + size if i < 0 else i  # one wrap-around, then clamp (jax.numpy indexing)
+                    i = min(max(i, 0), size - 1)
+                if i is Ellipsis:
+                    axis = self.ndim  # integer indices after an ellipsis are not touched
+                elif i is not None:
+                    axis += 1
+                clamped.append(i)
+            return super().__getitem__(tuple(clamped))
 
 
 def to_arr(x):

@@ -509,6 +509,13 @@ struct DenseLoop {
           linearise_at(cx, m_from, t, params);
           revert_stack(cx, col, a.damp);
           apply_gain(cx, col, m_from, m_new, true);
+          if (cfg.solver == PDEQ_SOLVER_MLE) {
+            // solver_mle.init (solvers.py:361-374): the update at t0 is the first datum of the running calibration
+            if (tid == 0) bc[2] = whiten(cx, false);
+            __syncthreads();
+            run_scale = bc[2];
+            ndata = 1.0;
+          }
           for (int e = tid; e < N; e += G) m_from[e] = m_new[e];
           store_factor(cx, col, Lfrom, d);
           __syncthreads();

@@ -401,6 +401,11 @@ struct GroupLoop {
 #pragma unroll
             for (int i = 0; i < n; ++i) m[i] = (ry0 == 0.0) ? m[i] : fma(-gain0[i], mobs, m[i]);
             if (active) st_store(st_from, d, j, m, Ln0);
+            if (cfg_solver == PDEQ_SOLVER_MLE) {
+              // solver_mle.init (solvers.py:361-374): the update at t0 is the first datum of the running calibration
+              const double term0 = whitened(g, mobs * fast_rcp(ry0), active, inv_sqrt_d);
+              if (active) st_from[F_RUN * d + j] = term0;
+            }
           }
           g.sync();
         }
@@ -414,7 +419,7 @@ struct GroupLoop {
         }
         dt = adaptive ? a.dt0[b * a.dt0_stride] : 0.0;
         ctrl_lprev = 0.0;
-        ndata = 0.0;
+        ndata = (cfg.constraint_init != 0 && cfg_solver == PDEQ_SOLVER_MLE) ? 1.0 : 0.0;
         nsteps = 0;
         nattempts = 0;
         status = 0;

@@ -351,18 +351,24 @@ struct ThreadLoop {
         if (!SP && cfg.constraint_init != 0) {
           // solver.init with constraint_init (solvers.py:361-372, 526-537, 670-680): condition the initial state on a
           // zero residual of the constraint linearised at it; a zero observed factor gives a zero gain (lstsq_svd)
-          double h0[NB][q + 1], mobs0[D], gain0[NB][n];
+          double h0[NB][q + 1], mobs0[D], gain0[NB][n], ry0[NB];
           linearise(m, params, t, h0, mobs0);
 #pragma unroll
           for (int k = 0; k < NB; ++k) {
-            double ry0, Ln0[n][n];
-            revert_obs<n, q, TS0>(L[k], h0[k], damp, ry0, gain0[k], Ln0);
+            double Ln0[n][n];
+            revert_obs<n, q, TS0>(L[k], h0[k], damp, ry0[k], gain0[k], Ln0);
 #pragma unroll
             for (int i = 0; i < n; ++i) {
-              gain0[k][i] = (ry0 == 0.0) ? 0.0 : gain0[k][i];
+              gain0[k][i] = (ry0[k] == 0.0) ? 0.0 : gain0[k][i];
 #pragma unroll
               for (int j = 0; j <= i; ++j) L[k][i][j] = Ln0[i][j];
             }
+          }
+          if (cfg_solver == PDEQ_SOLVER_MLE) {
+            // solver_mle.init (solvers.py:361-374): the update at t0 is the first datum of the running calibration;
+            // the residual is whitened by a plain division (a singular observed factor reads NaN, as there)
+            whitened_rms(mobs0, ry0, run_scale);
+            ndata = 1.0;
           }
 #pragma unroll
           for (int j = 0; j < D; ++j) {

@@ -453,6 +453,13 @@ struct DenseSmootherLoop {
           copy(c.Lp, c.L, NN);
           __syncthreads();
           correct(c, a.damp, true, c.m, c.mnew, true);
+          if (cfg.solver == PDEQ_SOLVER_MLE) {
+            // solver_mle.init (solvers.py:361-374): the update at t0 is the first datum of the running calibration
+            if (tid == 0) c.bc[2] = whiten(c, false);
+            __syncthreads();
+            run_scale = c.bc[2];
+            ndata = 1.0;
+          }
           copy(c.m, c.mnew, N);
           take_corrected_factor(c, c.L);
         }

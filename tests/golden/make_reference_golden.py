@@ -36,9 +36,10 @@ LV = dict(vf="lotka_volterra", nu=4, params=[0.55, 0.045, 0.52, 0.055], u0=[21.0
 CASES = []
 
 
-def case(name, kind, grid, atol=None, rtol=None, dt0=0.1, problem=LV, **spec):
+def case(name, kind, grid, atol=None, rtol=None, dt0=0.1, problem=LV, diffuse_start=False, **spec):
     CASES.append(dict(name=name, kind=kind, grid=list(map(float, grid)), atol=atol, rtol=rtol, dt0=dt0,
-                      problem=problem, spec=H.spec(vf=problem["vf"], **spec)))  # fmt: skip
+                      problem=problem, diffuse_start=diffuse_start,
+                      spec=H.spec(vf=problem["vf"], **spec)))  # fmt: skip
 
 
 # BASELINE configs[0/1]: one instance of the headline ensemble at its full horizon
@@ -71,6 +72,56 @@ case("pleiades_blockdiag_fixedpoint", "save_at", np.linspace(0.0, 0.3, 4), 1e-9,
      clip_dt=False)  # fmt: skip
 
 
+# BASELINE configs[3], second half: Van der Pol (mu = 1e3, second order), dense ts1, dynamic calibration, state error,
+# integral control, at BASELINE's tolerances (bench.py's config 4b; a short horizon)
+case("vanderpol_dense_ts1_dynamic_state_i", "terminal", [0.0, 0.5], 1e-11, 1e-8, dt0=1e-4,
+     problem=dict(vf="vanderpol", nu=4, params=[1e3], u0=[2.0]),
+     fact="dense", constraint="ts1", solver="solver_dynamic", control="i")  # fmt: skip
+# BASELINE configs[4]: Burgers semi-discretisation (a small resolution), block-diagonal ts0, solver + state error + PI
+case("burgers_blockdiag_ts0_d16", "terminal", [0.0, 0.2], 1e-6, 1e-4, dt0=1e-3,
+     problem=dict(vf="burgers", nu=3, params=[0.01], u0=list(o_problems.burgers_u0(16))),
+     fact="blockdiag")  # fmt: skip
+# the remaining options of the error estimate and of the step-size loop
+# (with ts0 the first derivative is observed exactly, so derivative_idx = 1 would estimate a zero error)
+case("lv_isotropic_state_deriv2_unitstep_rms_then_scale", "terminal", [0.0, 5.0], 1e-6, 1e-4,
+     derivative_idx=2, error_per_unit_step=True, error_norm="rms_then_scale")  # fmt: skip
+case("lv_blockdiag_residual_unitstep_clipped_save_at", "save_at", np.linspace(0.0, 4.0, 9), 1e-6, 1e-4,
+     fact="blockdiag", error="residual_std", error_per_unit_step=True, clip_dt=True)  # fmt: skip
+# constraint_init: exact initial value, diffuse derivatives, one Bayes update at t0 (solvers.py:361-372, 526-537, 670-680)
+case("lv_isotropic_constraint_init_fixedgrid", "fixed", np.linspace(0.0, 0.5, 21), diffuse_start=True,
+     constraint_init=True)  # fmt: skip
+case("lv_dense_ts1_constraint_init_fixedgrid_mle", "fixed", np.linspace(0.0, 0.5, 21), diffuse_start=True,
+     fact="dense", constraint="ts1", solver="solver_mle", constraint_init=True)  # fmt: skip
+case("lv_blockdiag_ts1_constraint_init_adaptive_dynamic", "terminal", [0.0, 2.0], 1e-8, 1e-6, dt0=1e-3,
+     diffuse_start=True, fact="blockdiag", constraint="ts1", solver="solver_dynamic", error="residual_std",
+     control="i", constraint_init=True)  # fmt: skip
+# ... with solver_mle the update at t0 is the first datum of the running calibration (solvers.py:366-374); one case per
+# kernel family of the CUDA path (thread-per-instance, lane-per-dimension smoother, dense, dense smoother)
+case("lv_isotropic_constraint_init_mle_adaptive", "terminal", [0.0, 2.0], 1e-8, 1e-6, dt0=1e-3,
+     diffuse_start=True, solver="solver_mle", error="residual_std", control="i", constraint_init=True)  # fmt: skip
+case("lv_blockdiag_constraint_init_fixedpoint_mle", "save_at", np.linspace(0.0, 2.0, 5), 1e-7, 1e-5, dt0=1e-3,
+     diffuse_start=True, fact="blockdiag", strategy="fixedpoint", solver="solver_mle", error="residual_std",
+     control="i", clip_dt=False, constraint_init=True)  # fmt: skip
+case("lv_dense_constraint_init_fixedinterval_mle", "fixed", np.linspace(0.0, 0.5, 21), diffuse_start=True,
+     fact="dense", strategy="fixedinterval", solver="solver_mle", constraint_init=True)  # fmt: skip
+
+
+def diffuse_std(c):
+    """Standard deviations of the diffuse start (0 for the initial value, 1 for every derivative) in the layout the
+    oracle and the product take: (n,) isotropic, (n, d) otherwise."""
+    n, d = c["problem"]["nu"] + 1, len(c["problem"]["u0"])
+    std = np.ones((n,) if c["spec"]["fact"] == "isotropic" else (n, d))
+    std[0] = 0.0
+    return std
+
+
+def reference_prior(ssm, c):
+    tcoeffs = [np.asarray(x) for x in c["tcoeffs"]]
+    if not c.get("diffuse_start"):
+        return ssm.prior_wiener_integrated(tcoeffs)
+    return ssm.prior_wiener_integrated_diffuse(tcoeffs, [np.asarray(x) for x in diffuse_std(c)])
+
+
 def reference_vf(pdq, problem):
     fn, order, _np_, _default = o_problems._REGISTRY[problem["vf"]]
     p = tuple(problem["params"])
@@ -85,8 +136,7 @@ def run_reference(c):
     s, prob = c["spec"], c["problem"]
     vf = reference_vf(pdq, prob)
     ssm, solver, err, ctrl = H._build(pdq, ivp, s, vf)
-    tcoeffs = [np.asarray(x) for x in c["tcoeffs"]]
-    prior = ssm.prior_wiener_integrated(tcoeffs)
+    prior = reference_prior(ssm, c)
     grid = np.asarray(c["grid"])
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
@@ -104,9 +154,10 @@ def run_oracle(c):
     params = np.asarray(prob["params"]) if prob["params"] else None
     tc = np.asarray(c["tcoeffs"])
     grid = np.asarray(c["grid"])
+    init_std = diffuse_std(c) if c.get("diffuse_start") else None
     if c["kind"] == "fixed":
-        return H.oracle_solve_fixed(s, tc, params, grid)
-    sol, _ = H.oracle_solve_save_at(s, tc, params, grid, c["atol"], c["rtol"], dt0=c["dt0"])
+        return H.oracle_solve_fixed(s, tc, params, grid, init_std=init_std)
+    sol, _ = H.oracle_solve_save_at(s, tc, params, grid, c["atol"], c["rtol"], dt0=c["dt0"], init_std=init_std)
     return sol.terminal() if c["kind"] == "terminal" else sol
 
 
@@ -145,7 +196,9 @@ def main():
         prob = c["problem"]
         ovf = o_pdq.ode(prob["vf"], np.asarray(prob["params"]) if prob["params"] else None)
         inits = [np.asarray(prob["u0"])] if ovf.order == 1 else [np.asarray(prob["u0"]), np.zeros(len(prob["u0"]))]
-        c["tcoeffs"] = np.asarray(ovf.taylor_coefficients(inits, c["grid"][0], prob["nu"]))
+        c["tcoeffs"] = np.asarray(ovf.taylor_coefficients(inits, c["grid"][0], prob["nu"] + 1 - ovf.order))
+        if c["diffuse_start"]:  # only the initial value is known
+            c["tcoeffs"][len(inits):] = 0.0
         if c["dt0"] == "dt0()":  # ivpsolve.dt0 (stepsize_initialisers.py:7-21), evaluated by the oracle
             from oracle import ivpsolve as o_ivp
 
@@ -172,7 +225,7 @@ def main():
         for k, v in ref.items():
             out[f"{c['name']}/{k}"] = v
         out[f"{c['name']}/tcoeffs"] = c["tcoeffs"]
-        meta = {k: c[k] for k in ("name", "kind", "grid", "atol", "rtol", "dt0", "problem", "spec")}
+        meta = {k: c[k] for k in ("name", "kind", "grid", "atol", "rtol", "dt0", "problem", "spec", "diffuse_start")}
         meta["reference_one_ulp_sensitivity"] = sens
         row["reference_one_ulp_sensitivity"] = sens
         out[f"{c['name']}/meta"] = np.asarray(json.dumps(meta))

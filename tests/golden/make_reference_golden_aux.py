@@ -1,0 +1,201 @@
+"""Generate tests/golden/reference_numpy_backend_aux.npz: outputs of the REFERENCE's own code for the functions either
+side of the step loop -- `ivpsolve.dt0` / `dt0_adaptive` (stepsize_initialisers.py:7-78), `loss_lml_terminal_values` and
+`loss_lml_timeseries` (estimators_and_losses.py:20-105), `solver.offgrid_marginals` (solvers.py:149-203).
+
+Same mechanism as make_reference_golden.py (which holds the step-loop cases): the reference's unmodified modules run
+from /root/reference on the NumPy array backend of oracle/refshim; the oracle is compared on the spot and the
+reference's outputs are written as fixtures for the CPU (oracle) and GPU (CUDA path) tests:
+
+    python tests/golden/make_reference_golden_aux.py       # needs /root/reference; a few seconds
+
+Each case is a step-loop case in make_reference_golden.py's format (`base`) plus the inputs of the function applied to
+its solution.  `offgrid_marginals` relies on JAX clamping out-of-range integer indices (solvers.py:173-185: for a time
+in the LAST interval of a save_at solution it reads `output_scale[T - 1]` of T - 1 entries, and it indexes solution
+leaves that have no time axis); the shim's array type reproduces that clamping (oracle/refshim/backend/_array.py), the
+oracle restates it (oracle/probdiffeq.py:419-422), and the off-grid times below include the last interval.
+"""
+
+import importlib.util
+import json
+import pathlib
+import sys
+import warnings
+
+import numpy as np
+
+HERE = pathlib.Path(__file__).resolve().parent
+ROOT = HERE.parents[1]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import pdeq_test_helpers as H  # noqa: E402
+from oracle import ivpsolve as o_ivp  # noqa: E402
+from oracle import probdiffeq as o_pdq  # noqa: E402
+from oracle import problems as o_problems  # noqa: E402
+from oracle import refshim  # noqa: E402
+
+_spec = importlib.util.spec_from_file_location("make_reference_golden", HERE / "make_reference_golden.py")
+mk = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(mk)
+
+OUT = HERE / "reference_numpy_backend_aux.npz"
+LV = mk.LV
+HIRES = dict(vf="hires", nu=5, params=[], u0=list(o_problems.hires_u0()))
+PLEIADES = dict(vf="pleiades", nu=5, params=[], u0=list(o_problems.pleiades_u0()))
+CASES = []
+
+
+def base(kind, grid, atol=None, rtol=None, dt0=0.1, problem=LV, **spec):
+    return dict(name="", kind=kind, grid=list(map(float, grid)), atol=atol, rtol=rtol, dt0=dt0, problem=problem,
+                diffuse_start=False, spec=H.spec(vf=problem["vf"], **spec))  # fmt: skip
+
+
+def aux(name, kind, b, **extra):
+    CASES.append(dict(name=name, aux=kind, base=b, **extra))
+
+
+for prob_name, prob in (("lv", LV), ("hires", HIRES), ("pleiades", PLEIADES)):
+    aux(f"dt0_{prob_name}", "dt0", base("terminal", [0.0, 1.0], problem=prob))
+aux("dt0_adaptive_lv", "dt0_adaptive", base("terminal", [0.0, 1.0]), error_contraction_rate=5, rtol=1e-6, atol=1e-8)
+aux("dt0_adaptive_hires", "dt0_adaptive", base("terminal", [0.0, 1.0], problem=HIRES), error_contraction_rate=6,
+    rtol=1e-8, atol=1e-11)  # fmt: skip
+for fact in ("isotropic", "blockdiag", "dense"):
+    aux(f"lml_terminal_{fact}", "lml_terminal",
+        base("terminal", [0.0, 2.0], 1e-6, 1e-4, fact=fact, solver="solver_mle"))  # fmt: skip
+    aux(f"lml_timeseries_{fact}_fixedpoint", "lml_timeseries",
+        base("save_at", np.linspace(0.0, 4.0, 13), 1e-4, 1e-4, fact=fact, strategy="fixedpoint", solver="solver_mle",
+             error="residual_std", control="i", clip_dt=False))  # fmt: skip
+    aux(f"lml_timeseries_{fact}_fixedinterval", "lml_timeseries",
+        base("fixed", np.linspace(0.0, 1.0, 17), fact=fact, strategy="fixedinterval", solver="solver_mle"))
+    aux(f"offgrid_{fact}_filter_save_at", "offgrid",
+        base("save_at", np.linspace(0.0, 3.0, 9), 1e-5, 1e-4, fact=fact, solver="solver_mle", error="residual_std",
+             control="i", clip_dt=False), ts=[0.01, 0.1875, 1.2345, 2.99])  # fmt: skip
+    aux(f"offgrid_{fact}_filter_dynamic_ts1", "offgrid",
+        base("save_at", np.linspace(0.0, 3.0, 9), 1e-5, 1e-4, fact=fact, solver="solver_dynamic", constraint="ts1",
+             error="residual_std", control="i", clip_dt=False), ts=[0.01, 0.1875, 1.2345, 2.99])  # fmt: skip
+    aux(f"offgrid_{fact}_fixedinterval", "offgrid",
+        base("fixed", np.linspace(0.0, 1.0, 17), fact=fact, strategy="fixedinterval", solver="solver_mle"),
+        ts=[0.01, 0.33, 0.46875, 0.97])  # fmt: skip
+
+
+def observations(c, mean_coeff, T=None):
+    """Deterministic 'data' around a solution's Taylor coefficient, and observation noise levels in the shape the model
+    expects: a scalar per time for the isotropic model, one entry per dimension otherwise."""
+    rng = np.random.Generator(np.random.PCG64(len(c["name"])))
+    mean_coeff = np.asarray(mean_coeff)
+    data = mean_coeff + 0.05 * rng.normal(size=mean_coeff.shape)
+    d = mean_coeff.shape[-1]
+    iso = c["base"]["spec"]["fact"] == "isotropic"
+    if T is None:
+        std = np.asarray(0.07) if iso else 0.07 * (1.0 + 0.5 * np.arange(d))
+    else:
+        sd = 0.05 + 0.01 * np.arange(T)
+        std = sd if iso else np.stack([sd * (1.0 + 0.5 * j) for j in range(d)], axis=1)
+    return data, std
+
+
+def solution_coefficient(sol_mean_flat, fact, n, d, i):
+    m = np.asarray(sol_mean_flat)
+    if fact == "isotropic":
+        return m[..., i, :]
+    if fact == "blockdiag":
+        return m[..., :, i]
+    return m.reshape(*m.shape[:-1], n, d)[..., i, :]
+
+
+def oracle_solver(b):
+    prob = b["problem"]
+    params = np.asarray(prob["params"]) if prob["params"] else None
+    return H._build(o_pdq, o_ivp, b["spec"], H.oracle_vf(b["spec"], params))[1]
+
+
+def rel(a, b):
+    return mk.rel(a, b)
+
+
+def run(c):
+    """Returns (fixture arrays, report row). Fails if the oracle disagrees with the reference."""
+    ivp, pdq = refshim.load()
+    b = c["base"]
+    prob, s = b["problem"], b["spec"]
+    n, d = prob["nu"] + 1, len(prob["u0"])
+    params = np.asarray(prob["params"]) if prob["params"] else None
+    ovf = o_pdq.ode(prob["vf"], params)
+    u0 = np.asarray(prob["u0"])
+    out, row = {}, dict(case=c["name"])
+    if c["aux"] in ("dt0", "dt0_adaptive"):
+        vf_r = mk.reference_vf(pdq, prob)
+        if c["aux"] == "dt0":
+            ref, ora = ivp.dt0(vf_r, (u0,), t=0.0), o_ivp.dt0(ovf, (u0,), t=0.0)
+        else:
+            kw = {k: c[k] for k in ("error_contraction_rate", "rtol", "atol")}
+            ref, ora = ivp.dt0_adaptive(vf_r, (u0,), 0.0, **kw), o_ivp.dt0_adaptive(ovf, (u0,), 0.0, **kw)
+        out["value"] = np.asarray(float(ref))
+        row["rel"] = rel(ora, ref)
+        assert row["rel"] < 1e-14, row
+        return out, row
+    b["tcoeffs"] = np.asarray(ovf.taylor_coefficients([u0], b["grid"][0], prob["nu"]))
+    out["tcoeffs"] = b["tcoeffs"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        rsol = mk.run_reference(b)
+        osol = mk.run_oracle(b)
+    assert np.array_equal(np.asarray(rsol.num_steps), np.asarray(osol.num_steps)), c["name"]
+    out["num_steps"] = np.asarray(rsol.num_steps)
+    if c["aux"] == "lml_terminal":
+        for idx in (0, 1):
+            data, std = observations(c, solution_coefficient(rsol.u.mean_flat, s["fact"], n, d, idx))
+            ref = pdq.loss_lml_terminal_values(tcoeff_index=idx)(data, marginals=rsol.u, std=std)
+            ora = o_pdq.loss_lml_terminal_values(tcoeff_index=idx)(data, marginals=osol.u, std=std)
+            out[f"data{idx}"], out[f"std{idx}"], out[f"lml{idx}"] = data, np.asarray(std), np.asarray(float(ref))
+            row[f"rel{idx}"] = rel(ora, ref)
+            assert row[f"rel{idx}"] < 1e-8, row
+    elif c["aux"] == "lml_timeseries":
+        T = len(b["grid"])
+        data, std = observations(c, solution_coefficient(rsol.u.mean_flat, s["fact"], n, d, 0), T=T)
+        out["data"], out["std"] = data, np.asarray(std)
+        opost = osol.solution_full.posterior.remove_filtering_distributions()
+        for key, avg in (("lml_avg", True), ("lml_sum", False)):
+            ref = pdq.loss_lml_timeseries(average_pdfs=avg)(data, posterior=rsol.solution_full.posterior, std=std)
+            ora = o_pdq.loss_lml_timeseries(average_pdfs=avg)(data, posterior=opost, std=std)
+            out[key] = np.asarray(float(ref))
+            row["rel_" + key] = rel(ora, ref)
+            assert row["rel_" + key] < 1e-8, row
+    elif c["aux"] == "offgrid":
+        _ssm, rslv, _e, _c = H._build(pdq, ivp, s, mk.reference_vf(pdq, prob))
+        oslv = oracle_solver(b)
+        means, covs, worst = [], [], 0.0
+        for t in c["ts"]:
+            rv = rslv.offgrid_marginals(np.asarray(t), solution=rsol)
+            orv = oslv.offgrid_marginals(t, solution=osol)
+            means.append(np.asarray(rv.mean_flat))
+            covs.append(mk._cov(rv.cholesky_flat))
+            worst = max(worst, rel(orv.mean, means[-1]), rel(mk._cov(orv.chol), covs[-1]))
+        out["ts"], out["mean"], out["cov"] = np.asarray(c["ts"]), np.stack(means), np.stack(covs)
+        row["rel"] = worst
+        assert worst < 1e-6, row
+    else:
+        raise ValueError(c["aux"])
+    return out, row
+
+
+def main():
+    if not refshim.available():
+        raise SystemExit("needs the reference sources under /root/reference")
+    out, report = {}, []
+    for c in CASES:
+        arrays, row = run(c)
+        report.append(row)
+        print(json.dumps(row), flush=True)
+        for k, v in arrays.items():
+            out[f"{c['name']}/{k}"] = v
+        meta = {k: v for k, v in c.items() if k != "base"}
+        meta["base"] = {k: v for k, v in c["base"].items() if k != "tcoeffs"}
+        out[f"{c['name']}/meta"] = np.asarray(json.dumps(meta))
+    np.savez_compressed(OUT, **out)
+    OUT.with_suffix(".report.json").write_text(json.dumps(report, indent=1))
+    print("wrote", OUT, OUT.stat().st_size, "bytes")
+
+
+if __name__ == "__main__":
+    main()

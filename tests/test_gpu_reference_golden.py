@@ -8,18 +8,24 @@ import numpy as np
 import pytest
 
 import pdeq_test_helpers as H
-from test_reference_golden import CASES, check_against_reference
+import test_reference_golden_aux as AUX
+from test_reference_golden import CASES, check_against_reference, diffuse_std
 
 pytestmark = pytest.mark.gpu
 
 
-def product_run(c):
+def product_solve(c):
+    """Run the case's solve on the device; returns (solution, solver, probdiffeq module, ivpsolve module, vf)."""
     import torch
 
     s, prob = c["spec"], c["problem"]
     params = np.asarray(prob["params"])[None, :] if prob["params"] else None
     p_pdq, p_ivp, vf, ssm, solver, err, ctrl = H.product_build(s, params)
-    prior = ssm.prior_wiener_integrated(torch.from_numpy(c["tcoeffs"][None]).cuda())
+    tcoeffs = torch.from_numpy(c["tcoeffs"][None]).cuda()
+    if c.get("diffuse_start"):
+        prior = ssm.prior_wiener_integrated_diffuse(tcoeffs, torch.from_numpy(diffuse_std(c)).cuda())
+    else:
+        prior = ssm.prior_wiener_integrated(tcoeffs)
     grid = np.asarray(c["grid"])
     if c["kind"] == "terminal":
         solve = p_ivp.solve_adaptive_terminal_values(solver=solver, error=err, control=ctrl, clip_dt=s["clip_dt"])
@@ -31,6 +37,12 @@ def product_run(c):
         sol = p_ivp.solve_fixed_grid(solver=solver)(prior, grid=grid)
     torch.cuda.synchronize()
     assert int(sol.status.abs().max()) == 0
+    return sol, solver, p_pdq, p_ivp, vf
+
+
+def product_run(c):
+    sol = product_solve(c)[0]
+    s = c["spec"]
     mean = sol.u.mean_flat[0].cpu().numpy()  # ([T,] n, d)
     L = sol.u.cholesky_flat[0].cpu().numpy()
     if s["fact"] == "blockdiag":
@@ -52,3 +64,49 @@ def product_run(c):
 @pytest.mark.parametrize("c", CASES, ids=[c["name"] for c in CASES])
 def test_cuda_path_reproduces_the_reference(cuda, c):
     check_against_reference(c, product_run(c))
+
+
+def product_aux_outputs(c):
+    """dt0 / dt0_adaptive / loss_lml_* / offgrid_marginals of the CUDA path, in the reference's layouts."""
+    import torch
+
+    prob, params, u0 = AUX.problem_of(c)
+    a = c["arrays"]
+    if c["aux"] in ("dt0", "dt0_adaptive"):
+        from probdiffeq_b200 import ivpsolve as p_ivp
+        from probdiffeq_b200 import probdiffeq as p_pdq
+
+        vf = p_pdq.ode(prob["vf"], params=None if params is None else params[None, :])
+        if c["aux"] == "dt0":
+            return dict(value=p_ivp.dt0(vf, (u0[None, :],), t=0.0).cpu().numpy()[0])
+        kw = {k: c[k] for k in ("error_contraction_rate", "rtol", "atol")}
+        return dict(value=p_ivp.dt0_adaptive(vf, (u0[None, :],), 0.0, **kw).cpu().numpy()[0])
+    b = dict(c["base"], tcoeffs=a["tcoeffs"])
+    sol, solver, p_pdq, _p_ivp, _vf = product_solve(b)
+    fact = b["spec"]["fact"]
+    steps, want = sol.num_steps[0].cpu().numpy(), a["num_steps"]
+    if steps.ndim == 1 and want.ndim == 1 and steps.shape[0] == want.shape[0] + 1:
+        steps = steps[1:]  # the product reports the initial point too
+    assert np.array_equal(np.ravel(steps), np.ravel(want)), (steps, want)
+    if c["aux"] == "lml_terminal":
+        return {f"lml{i}": p_pdq.loss_lml_terminal_values(tcoeff_index=i)(
+            a[f"data{i}"][None], marginals=sol.u, std=a[f"std{i}"].reshape(1, -1)).cpu().numpy()[0] for i in (0, 1)}  # fmt: skip
+    if c["aux"] == "lml_timeseries":
+        post = sol.solution_full.posterior
+        return {key: p_pdq.loss_lml_timeseries(average_pdfs=avg)(
+            a["data"][None], posterior=post, std=a["std"][None]).cpu().numpy()[0]
+            for key, avg in (("lml_avg", True), ("lml_sum", False))}  # fmt: skip
+    rv = solver.offgrid_marginals(a["ts"], solution=sol)
+    torch.cuda.synchronize()
+    mean = rv.mean_flat[0].cpu().numpy()  # (K, n, d)
+    L = rv.cholesky_flat[0].cpu().numpy()
+    if fact == "blockdiag":
+        mean = np.swapaxes(mean, -1, -2)
+    elif fact == "dense":
+        mean = mean.reshape(mean.shape[0], -1)
+    return dict(mean=mean, cov=AUX.cov(L))
+
+
+@pytest.mark.parametrize("c", AUX.CASES, ids=AUX.IDS)
+def test_cuda_path_reproduces_the_reference_either_side_of_the_loop(cuda, c):
+    AUX.check(c, product_aux_outputs(c))

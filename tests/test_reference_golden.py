@@ -72,14 +72,25 @@ def check_against_reference(c, got):
         assert rel(got[key], ref[key]) < tol, (c["name"], key, rel(got[key], ref[key]), tol)
 
 
+def diffuse_std(c):
+    """The diffuse start of the constraint_init cases: exact initial value, unit standard deviation on every derivative
+    ((n,) for the isotropic model, (n, d) otherwise) -- tests/golden/make_reference_golden.py:diffuse_std."""
+    n, d = c["problem"]["nu"] + 1, len(c["problem"]["u0"])
+    std = np.ones((n,) if c["spec"]["fact"] == "isotropic" else (n, d))
+    std[0] = 0.0
+    return std
+
+
 def oracle_run(c):
     s, prob = c["spec"], c["problem"]
     params = np.asarray(prob["params"]) if prob["params"] else None
     grid = np.asarray(c["grid"])
+    init_std = diffuse_std(c) if c.get("diffuse_start") else None
     if c["kind"] == "fixed":
-        sol = H.oracle_solve_fixed(s, c["tcoeffs"], params, grid)
+        sol = H.oracle_solve_fixed(s, c["tcoeffs"], params, grid, init_std=init_std)
     else:
-        sol, _ = H.oracle_solve_save_at(s, c["tcoeffs"], params, grid, c["atol"], c["rtol"], dt0=c["dt0"])
+        sol, _ = H.oracle_solve_save_at(s, c["tcoeffs"], params, grid, c["atol"], c["rtol"], dt0=c["dt0"],
+                                        init_std=init_std)  # fmt: skip
         if c["kind"] == "terminal":
             sol = sol.terminal()
     u = sol.u
@@ -93,12 +104,16 @@ def oracle_run(c):
 
 def test_fixtures_cover_the_strategy_factorisation_grid():
     names = {c["name"] for c in CASES}
-    assert len(CASES) >= 21
+    assert len(CASES) >= 28
     for fact in ("isotropic", "blockdiag", "dense"):
         for tail in ("solver_residual_i", "dynamic_residual_i", "mle_state_pi_ts1", "fixedpoint_mle",
                      "fixedgrid_filter", "fixedgrid_fixedinterval_mle"):  # fmt: skip
             assert f"lv_{fact}_{tail}" in names
-    assert {"lv_iso_ts0_terminal_t50", "hires_dense_ts1_dynamic", "pleiades_blockdiag_fixedpoint"} <= names
+    assert {"lv_iso_ts0_terminal_t50", "hires_dense_ts1_dynamic", "pleiades_blockdiag_fixedpoint",
+            "vanderpol_dense_ts1_dynamic_state_i", "burgers_blockdiag_ts0_d16",
+            "lv_isotropic_state_deriv2_unitstep_rms_then_scale", "lv_blockdiag_residual_unitstep_clipped_save_at",
+            "lv_isotropic_constraint_init_fixedgrid", "lv_dense_ts1_constraint_init_fixedgrid_mle",
+            "lv_blockdiag_ts1_constraint_init_adaptive_dynamic"} <= names  # fmt: skip
     report = json.loads((GOLDEN.with_suffix(".report.json")).read_text())
     assert all(r["same_step_counts"] for r in report)
 
