@@ -1,6 +1,7 @@
 """Function transformations on NumPy: jit is the identity, vmap is a loop over the mapped axis, and derivatives come
 from the complex-step method (exact to rounding for the analytic, NumPy-generic functions the step loop differentiates:
-derivative selectors, which are linear, and polynomial vector fields)."""
+derivative selectors, which are linear, and polynomial vector fields); Taylor-mode differentiation (`jet`) is provided
+for polynomial functions in exact rational arithmetic."""
 import functools
 
 import numpy as _np
@@ -143,5 +144,88 @@ def linear_transpose(func, *args):
     raise NotImplementedError("outside the path this shim serves")
 
 
+class _ExactSeries:
+    """A truncated power series in one variable with EXACT rational coefficients (every float64 is a rational number):
+    what `jet` below pushes through a polynomial vector field.  Independent of the oracle's float64 series arithmetic
+    (oracle/problems.py:Series) -- the results are the correctly rounded values of the exact Taylor coefficients."""
+
+    __array_ufunc__ = None  # NumPy scalars defer to the reflected operators below
+    __slots__ = ("c",)
+
+    def __init__(self, coeffs):
+        self.c = list(coeffs)
+
+    @staticmethod
+    def _lift(x, order):
+        import fractions
+
+        if isinstance(x, _ExactSeries):
+            return x
+        return _ExactSeries([fractions.Fraction(float(x))] + [fractions.Fraction(0)] * order)
+
+    def __add__(self, other):
+        other = self._lift(other, len(self.c) - 1)
+        return _ExactSeries([a + b for a, b in zip(self.c, other.c)])
+
+    __radd__ = __add__
+
+    def __neg__(self):
+        return _ExactSeries([-a for a in self.c])
+
+    def __sub__(self, other):
+        return self + (-self._lift(other, len(self.c) - 1))
+
+    def __rsub__(self, other):
+        return self._lift(other, len(self.c) - 1) - self
+
+    def __mul__(self, other):
+        other = self._lift(other, len(self.c) - 1)
+        n = len(self.c)
+        return _ExactSeries([sum(self.c[i] * other.c[k - i] for i in range(k + 1)) for k in range(n)])
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, other):  # by a constant only
+        import fractions
+
+        if isinstance(other, _ExactSeries):
+            return NotImplemented
+        return _ExactSeries([a / fractions.Fraction(float(other)) for a in self.c])
+
+
 def jet(func, /, primals, series, *, is_tcoeff=False):
-    raise NotImplementedError("Taylor-mode differentiation is not reproduced: pass Taylor coefficients in")
+    """`jax.experimental.jet.jet` for POLYNOMIAL functions, in exact rational arithmetic: push the paths
+    x_i(s) = primal_i + sum_k series_i[k] s^(k+1) / (k+1)!  (without the factorials if `is_tcoeff`, the reference's
+    `factorial_scaled=False`) through `func` and return (func(primals), [k-th derivative (or coefficient) of the image
+    path, k = 1..K]) rounded to float64.  Division, roots and transcendental functions are not provided: the Taylor
+    coefficients of the non-polynomial benchmark right-hand sides (Pleiades) stay an input of the fixtures."""
+    import fractions
+    import math
+
+    K = len(series[0])
+
+    def path(primal, terms):
+        primal = _np.asarray(primal, dtype=_np.float64)
+        terms = [_np.asarray(x, dtype=_np.float64) for x in terms]
+        out = _np.empty(primal.shape, dtype=object)
+        for idx in _np.ndindex(primal.shape):
+            coeffs = [fractions.Fraction(float(primal[idx]))]
+            for k, x in enumerate(terms, start=1):
+                scale = 1 if is_tcoeff else math.factorial(k)
+                coeffs.append(fractions.Fraction(float(x[idx])) / scale)
+            out[idx] = _ExactSeries(coeffs)
+        return out if out.ndim else out[()]
+
+    image = _np.asarray(func(*[path(p, s) for p, s in zip(primals, series)]), dtype=object)
+    lifted = _np.empty(image.shape, dtype=object)
+    for idx in _np.ndindex(image.shape):
+        lifted[idx] = _ExactSeries._lift(image[idx], K)
+
+    def coefficient(k):
+        scale = 1 if (is_tcoeff or k == 0) else math.factorial(k)
+        out = _np.empty(image.shape, dtype=_np.float64)
+        for idx in _np.ndindex(image.shape):
+            out[idx] = float(lifted[idx].c[k] * scale)
+        return out
+
+    return coefficient(0), [coefficient(k) for k in range(1, K + 1)]

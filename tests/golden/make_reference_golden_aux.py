@@ -1,6 +1,8 @@
 """Generate tests/golden/reference_numpy_backend_aux.npz: outputs of the REFERENCE's own code for the functions either
-side of the step loop -- `ivpsolve.dt0` / `dt0_adaptive` (stepsize_initialisers.py:7-78), `loss_lml_terminal_values` and
-`loss_lml_timeseries` (estimators_and_losses.py:20-105), `solver.offgrid_marginals` (solvers.py:149-203).
+side of the step loop -- Taylor-mode initialisation (`jetexpand_ode_padded_scan` / `jetexpand_ode_unroll`,
+jet_expansion_algorithms.py:49-152), `ivpsolve.dt0` / `dt0_adaptive` (stepsize_initialisers.py:7-78), `loss_lml_terminal_values` and
+`loss_lml_timeseries` (estimators_and_losses.py:20-105), `MarkovSequence.sample` (estimators_and_losses.py:233-271, given
+the draws), `solver.offgrid_marginals` (solvers.py:149-203).
 
 Same mechanism as make_reference_golden.py (which holds the step-loop cases): the reference's unmodified modules run
 from /root/reference on the NumPy array backend of oracle/refshim; the oracle is compared on the spot and the
@@ -59,6 +61,15 @@ for prob_name, prob in (("lv", LV), ("hires", HIRES), ("pleiades", PLEIADES)):
 aux("dt0_adaptive_lv", "dt0_adaptive", base("terminal", [0.0, 1.0]), error_contraction_rate=5, rtol=1e-6, atol=1e-8)
 aux("dt0_adaptive_hires", "dt0_adaptive", base("terminal", [0.0, 1.0], problem=HIRES), error_contraction_rate=6,
     rtol=1e-8, atol=1e-11)  # fmt: skip
+# Taylor-mode initialisation (jet_expansion_algorithms.py:49-152): the reference's recursion on the shim's exact-rational
+# `jet` (polynomial right-hand sides; the second-order problem starts with a non-zero velocity)
+VDP = dict(vf="vanderpol", nu=4, params=[1e3], u0=[2.0])
+BURGERS = dict(vf="burgers", nu=3, params=[0.01], u0=list(o_problems.burgers_u0(16)))
+for prob_name, prob, num, du0 in (("lv", LV, 4, None), ("hires", HIRES, 5, None), ("vanderpol", VDP, 3, [0.5]),
+                                  ("burgers_d16", BURGERS, 3, None)):  # fmt: skip
+    for alg in ("jetexpand_ode_padded_scan", "jetexpand_ode_unroll"):
+        aux(f"taylor_{prob_name}_{alg}", "taylor", base("terminal", [0.0, 1.0], problem=prob), alg=alg, num=num,
+            du0=du0, t=0.25)  # fmt: skip
 for fact in ("isotropic", "blockdiag", "dense"):
     aux(f"lml_terminal_{fact}", "lml_terminal",
         base("terminal", [0.0, 2.0], 1e-6, 1e-4, fact=fact, solver="solver_mle"))  # fmt: skip
@@ -67,6 +78,9 @@ for fact in ("isotropic", "blockdiag", "dense"):
              error="residual_std", control="i", clip_dt=False))  # fmt: skip
     aux(f"lml_timeseries_{fact}_fixedinterval", "lml_timeseries",
         base("fixed", np.linspace(0.0, 1.0, 17), fact=fact, strategy="fixedinterval", solver="solver_mle"))
+    aux(f"sample_{fact}_fixedpoint", "sample",
+        base("save_at", np.linspace(0.0, 3.0, 10), 1e-3, 1e-3, fact=fact, strategy="fixedpoint", solver="solver_mle",
+             error="residual_std", control="i", clip_dt=False))  # fmt: skip
     aux(f"offgrid_{fact}_filter_save_at", "offgrid",
         base("save_at", np.linspace(0.0, 3.0, 9), 1e-5, 1e-4, fact=fact, solver="solver_mle", error="residual_std",
              control="i", clip_dt=False), ts=[0.01, 0.1875, 1.2345, 2.99])  # fmt: skip
@@ -134,6 +148,16 @@ def run(c):
         row["rel"] = rel(ora, ref)
         assert row["rel"] < 1e-14, row
         return out, row
+    if c["aux"] == "taylor":
+        vf_r = mk.reference_vf(pdq, prob)
+        inits = (u0,) if c["du0"] is None else (u0, np.asarray(c["du0"]))
+        ref, _ = getattr(pdq, c["alg"])(num=c["num"])(vf_r, inits, t=c["t"])
+        ref = np.stack([np.asarray(x, dtype=np.float64) for x in ref])
+        ora = np.asarray(ovf.taylor_coefficients(list(inits), c["t"], c["num"]))
+        out["tcoeffs"] = ref
+        row["rel_per_coefficient"] = [rel(ora[i], ref[i]) for i in range(ref.shape[0])]
+        assert max(row["rel_per_coefficient"]) < 1e-14, row
+        return out, row
     b["tcoeffs"] = np.asarray(ovf.taylor_coefficients([u0], b["grid"][0], prob["nu"]))
     out["tcoeffs"] = b["tcoeffs"]
     with warnings.catch_warnings():
@@ -161,6 +185,70 @@ def run(c):
             out[key] = np.asarray(float(ref))
             row["rel_" + key] = rel(ora, ref)
             assert row["rel_" + key] < 1e-8, row
+    elif c["aux"] == "sample":
+        # MarkovSequence.sample (estimators_and_losses.py:233-271) with the shim's generator; the standard-normal
+        # numbers it draws are recorded in call order (terminal marginal first, then the conditionals backwards) and
+        # stored per grid point, so that the oracle and the CUDA path can be given the same draws
+        from oracle.refshim.backend import random as shim_random
+
+        draws, original = [], shim_random.normal
+
+        def recording(key, /, shape, dtype=None):
+            x = original(key, shape, dtype)
+            draws.append(np.asarray(x, dtype=np.float64))
+            return x
+
+        shim_random.normal = recording
+        try:
+            smp = rsol.solution_full.posterior.sample(shim_random.prng_key(seed=7))
+        finally:
+            shim_random.normal = original
+        # ... and once more with every draw set to zero: the sample is then the chain of conditional means, which does
+        # not depend on the sign convention of the factors
+        shim_random.normal = lambda key, /, shape, dtype=None: np.zeros(shape)
+        try:
+            smp0 = rsol.solution_full.posterior.sample(shim_random.prng_key(seed=7))
+        finally:
+            shim_random.normal = original
+        T = len(b["grid"])
+        assert len(draws) == T
+        base_draws = np.stack(draws[::-1])  # draws[0] belongs to the last grid point
+        ref = np.stack([np.asarray(x, dtype=np.float64) for x in smp], axis=1)  # (T, n, d)
+        states = osol.solution_full.posterior.sample(base_draws)
+        if s["fact"] == "isotropic":
+            ora = np.stack(states)
+        elif s["fact"] == "blockdiag":
+            ora = np.stack([x.T for x in states])
+        else:
+            ora = np.stack([x.reshape(n, d) for x in states])
+        out["base"], out["samples"] = base_draws, ref
+        # signs of the diagonals of the factors the reference drew with, per grid point: an implementation whose
+        # factors carry other column signs multiplies the draws by the ratio and must then reproduce the sample
+        from oracle.refshim.backend import tree as shim_tree
+
+        rpost = rsol.solution_full.posterior.remove_filtering_distributions()
+        signs = np.ones_like(base_draws)
+        signs[T - 1] = np.sign(np.diagonal(np.asarray(rpost.marginal.cholesky_flat), axis1=-2, axis2=-1))
+        for k in range(T - 2, -1, -1):
+            cond_k = shim_tree.tree_map(lambda x, k=k: x[k], rpost.conditional)
+            drawn_from = cond_k.apply_flat(rpost.marginal.mean_flat)
+            signs[k] = np.sign(np.diagonal(np.asarray(drawn_from.cholesky_flat), axis1=-2, axis2=-1))
+        out["factor_diag_sign"] = np.where(signs == 0.0, 1.0, signs)
+        out["samples_zero_draws"] = np.stack([np.asarray(x, dtype=np.float64) for x in smp0], axis=1)
+        states0 = osol.solution_full.posterior.sample(np.zeros_like(base_draws))
+        ora0 = np.stack([x if s["fact"] == "isotropic" else (x.T if s["fact"] == "blockdiag" else x.reshape(n, d))
+                         for x in states0])  # fmt: skip
+        row["rel_zero_draws"] = rel(ora0, out["samples_zero_draws"])
+        assert row["rel_zero_draws"] < 1e-8, row
+        row["rel"] = rel(ora, ref)
+        row["draw_shape"] = list(base_draws.shape)
+        # A sample is mean + factor @ draws, and the factor of a covariance is unique only up to the signs of its
+        # columns: the reference takes whatever signs LAPACK's QR returns (it never normalises them), so the sample
+        # for GIVEN draws is pinned only where those signs happen to agree with the oracle's Householder convention.
+        # Where they do not (the conditional means and covariances still agree, see the lml / offgrid cases), the
+        # fixture is kept as a record and marked; the tests then skip the value comparison.
+        c["factor_signs_agree"] = bool(row["rel"] < 1e-6)
+        row["factor_signs_agree"] = c["factor_signs_agree"]
     elif c["aux"] == "offgrid":
         _ssm, rslv, _e, _c = H._build(pdq, ivp, s, mk.reference_vf(pdq, prob))
         oslv = oracle_solver(b)

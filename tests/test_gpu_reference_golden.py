@@ -72,6 +72,13 @@ def product_aux_outputs(c):
 
     prob, params, u0 = AUX.problem_of(c)
     a = c["arrays"]
+    if c["aux"] == "taylor":
+        from probdiffeq_b200 import probdiffeq as p_pdq
+
+        vf = p_pdq.ode(prob["vf"], params=None if params is None else params[None, :])
+        inits = (u0[None, :],) if c["du0"] is None else (u0[None, :], np.asarray(c["du0"])[None, :])
+        tcoeffs, _ = getattr(p_pdq, c["alg"])(num=c["num"])(vf, inits, t=c["t"])
+        return dict(tcoeffs=tcoeffs[0].cpu().numpy())
     if c["aux"] in ("dt0", "dt0_adaptive"):
         from probdiffeq_b200 import ivpsolve as p_ivp
         from probdiffeq_b200 import probdiffeq as p_pdq
@@ -96,6 +103,17 @@ def product_aux_outputs(c):
         return {key: p_pdq.loss_lml_timeseries(average_pdfs=avg)(
             a["data"][None], posterior=post, std=a["std"][None]).cpu().numpy()[0]
             for key, avg in (("lml_avg", True), ("lml_sum", False))}  # fmt: skip
+    if c["aux"] == "sample":
+        post = sol.solution_full.posterior
+
+        def stacked(base):  # list over Taylor coefficients of (B, T, d) -> (T, n, d)
+            return np.stack([x[0].cpu().numpy() for x in post.sample(base=base[None])], axis=1)
+
+        # diagonals of the factors the device draws with: conditional k (k = 1 .. T-1) belongs to grid point k - 1
+        own = torch.cat([torch.diagonal(post.conditional.cholesky[0, 1:], dim1=-2, dim2=-1),
+                         torch.diagonal(post.marginal.cholesky_flat[0], dim1=-2, dim2=-1)[None]]).cpu().numpy()  # fmt: skip
+        base = AUX.draws_for(a, own)
+        return dict(samples=stacked(base), samples_zero_draws=stacked(0.0 * base))
     rv = solver.offgrid_marginals(a["ts"], solution=sol)
     torch.cuda.synchronize()
     mean = rv.mean_flat[0].cpu().numpy()  # (K, n, d)

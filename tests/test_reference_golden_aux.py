@@ -1,7 +1,9 @@
 """The oracle against outputs of the REFERENCE's own code for the functions either side of the step loop
 (tests/golden/reference_numpy_backend_aux.npz, written by tests/golden/make_reference_golden_aux.py from the unmodified
-reference on the NumPy backend of oracle/refshim): `dt0`, `dt0_adaptive` (stepsize_initialisers.py:7-78),
-`loss_lml_terminal_values`, `loss_lml_timeseries` (estimators_and_losses.py:20-105) and `solver.offgrid_marginals`
+reference on the NumPy backend of oracle/refshim): Taylor-mode initialisation (jet_expansion_algorithms.py:49-152,
+on an exact-rational `jet`), `dt0`, `dt0_adaptive` (stepsize_initialisers.py:7-78),
+`loss_lml_terminal_values`, `loss_lml_timeseries` (estimators_and_losses.py:20-105), `MarkovSequence.sample` given the
+draws (estimators_and_losses.py:233-271) and `solver.offgrid_marginals`
 (solvers.py:149-203) for all three factorisations."""
 
 import json
@@ -53,7 +55,12 @@ def check(c, got):
     sizes, log-likelihoods) to 1e-9; off-grid means to 1e-6 and covariances to 1e-5 (high Taylor coefficients carry the
     solve's own conditioning, tests/test_reference_golden.py)."""
     a = c["arrays"]
-    if c["aux"] in ("dt0", "dt0_adaptive"):
+    if c["aux"] == "taylor":
+        # every coefficient to 1e-13 of its own size (the exact coefficients, correctly rounded, are the fixture)
+        assert np.asarray(got["tcoeffs"]).shape == a["tcoeffs"].shape
+        for i in range(a["tcoeffs"].shape[0]):
+            assert rel(got["tcoeffs"][i], a["tcoeffs"][i]) < 1e-13, (c["name"], i)
+    elif c["aux"] in ("dt0", "dt0_adaptive"):
         assert rel(got["value"], a["value"]) < 1e-12
     elif c["aux"] == "lml_terminal":
         for idx in (0, 1):
@@ -61,6 +68,12 @@ def check(c, got):
     elif c["aux"] == "lml_timeseries":
         for key in ("lml_avg", "lml_sum"):
             assert rel(got[key], a[key]) < 1e-7, (c["name"], key, got[key], a[key])
+    elif c["aux"] == "sample":
+        # with all draws zero the sample is the chain of conditional means; with the recorded draws it also depends on
+        # the signs of the factors' columns, which the reference leaves to LAPACK: the implementation under test was
+        # given the draws times (sign of its own factor diagonals) x (sign of the reference's), `draws_for`
+        assert rel(got["samples_zero_draws"], a["samples_zero_draws"]) < 1e-8, c["name"]
+        assert rel(got["samples"], a["samples"]) < 1e-7, (c["name"], rel(got["samples"], a["samples"]))
     else:
         assert np.asarray(got["mean"]).shape == a["mean"].shape
         assert rel(got["mean"], a["mean"]) < 1e-6, (c["name"], rel(got["mean"], a["mean"]))
@@ -68,11 +81,22 @@ def check(c, got):
             assert rel(got["cov"][k], a["cov"][k]) < 1e-5, (c["name"], k)
 
 
+def draws_for(a, own_factor_diagonals):
+    """The fixture's draws with the column-sign convention of the reference's factors translated into the
+    implementation's: a factor of a covariance is unique up to the signs of its columns, and flipping a column's sign
+    together with its draw leaves the sample unchanged."""
+    own = np.sign(np.asarray(own_factor_diagonals)).reshape(a["base"].shape)
+    return a["base"] * np.where(own == 0.0, 1.0, own) * a["factor_diag_sign"]
+
+
 def oracle_outputs(c):
     b = dict(c["base"])
     prob, params, u0 = problem_of(c)
     s = b["spec"]
     ovf = o_pdq.ode(prob["vf"], params)
+    if c["aux"] == "taylor":
+        inits = [u0] if c["du0"] is None else [u0, np.asarray(c["du0"])]
+        return dict(tcoeffs=np.asarray(ovf.taylor_coefficients(inits, c["t"], c["num"])))
     if c["aux"] == "dt0":
         return dict(value=o_ivp.dt0(ovf, (u0,), t=0.0))
     if c["aux"] == "dt0_adaptive":
@@ -94,6 +118,19 @@ def oracle_outputs(c):
         post = sol.solution_full.posterior.remove_filtering_distributions()
         return {key: o_pdq.loss_lml_timeseries(average_pdfs=avg)(a["data"], posterior=post, std=a["std"])
                 for key, avg in (("lml_avg", True), ("lml_sum", False))}  # fmt: skip
+    if c["aux"] == "sample":
+        n, d = prob["nu"] + 1, len(prob["u0"])
+
+        def stacked(states):
+            return np.stack([x if s["fact"] == "isotropic" else (x.T if s["fact"] == "blockdiag" else x.reshape(n, d))
+                             for x in states])  # fmt: skip
+
+        post = sol.solution_full.posterior
+        seq = post.remove_filtering_distributions()
+        own = [np.diagonal(cnd.alg.preconditioner_apply(cnd).noise.chol, axis1=-2, axis2=-1) for cnd in seq.conditional]
+        own.append(np.diagonal(seq.marginal.chol, axis1=-2, axis2=-1))
+        base = draws_for(a, np.stack(own))
+        return dict(samples=stacked(post.sample(base)), samples_zero_draws=stacked(post.sample(0.0 * base)))
     slv = H._build(o_pdq, o_ivp, s, H.oracle_vf(s, params))[1]
     rvs = [slv.offgrid_marginals(float(t), solution=sol) for t in a["ts"]]
     return dict(mean=np.stack([rv.mean for rv in rvs]), cov=np.stack([cov(rv.chol) for rv in rvs]))
@@ -102,8 +139,11 @@ def oracle_outputs(c):
 def test_aux_fixtures_cover_every_function_and_factorisation():
     names = set(IDS)
     assert {"dt0_lv", "dt0_hires", "dt0_pleiades", "dt0_adaptive_lv", "dt0_adaptive_hires"} <= names
+    for prob in ("lv", "hires", "vanderpol", "burgers_d16"):
+        assert {f"taylor_{prob}_jetexpand_ode_padded_scan", f"taylor_{prob}_jetexpand_ode_unroll"} <= names
     for fact in ("isotropic", "blockdiag", "dense"):
         assert {f"lml_terminal_{fact}", f"lml_timeseries_{fact}_fixedpoint", f"lml_timeseries_{fact}_fixedinterval",
+                f"sample_{fact}_fixedpoint",
                 f"offgrid_{fact}_filter_save_at", f"offgrid_{fact}_filter_dynamic_ts1",
                 f"offgrid_{fact}_fixedinterval"} <= names  # fmt: skip
     # off-grid times include the last interval of a save_at solution (JAX's index clamping, solvers.py:185)
