@@ -1,9 +1,9 @@
 """Generate tests/golden/oracle_golden.npz from the oracle.
 
-The reference holds no golden outputs of the step loop (its only fixtures are pickled float32 jax.Arrays for
-unrelated problems) and cannot be run here (no JAX), so these vectors are produced by the ORACLE, after it has been
-pinned by the reference's known-answer tests and identities (tests/test_oracle_kats.py). They freeze the oracle:
-a CPU test re-derives them, and a GPU test compares the CUDA path with them.
+These vectors are produced by the ORACLE (not by the reference): they freeze the restatement as regression
+fixtures -- a CPU test re-derives them, and a GPU test compares the CUDA path with them. Outputs of the REFERENCE's own
+code are a separate set: reference_numpy_backend*.npz, written by make_reference_golden*.py (the unmodified reference
+on the NumPy backend of oracle/refshim); those are what pin the oracle.
 
     python tests/golden/make_golden.py
 """

@@ -29,3 +29,21 @@ def test_batched_taylor_coefficients_match_per_instance():
     for b in range(5):
         single = o_problems.Ode("lotka_volterra", params[b]).taylor_coefficients((u0[b],), 0.0, 4)
         assert np.allclose(batched[b], single, rtol=1e-14)
+
+
+def test_c_port_reproduces_the_reference_on_the_headline_configuration():
+    """The CPU baseline `bench.py` times (and its `--impl reference` arm) against the REFERENCE's own output for one
+    instance of BASELINE configs[1] at its full horizon (tests/golden/reference_numpy_backend.npz, produced by running
+    the unmodified reference on the NumPy backend of oracle/refshim): same accepted steps, terminal value to 1e-8."""
+    from test_reference_golden import CASES, rel
+
+    c = next(c for c in CASES if c["name"] == "lv_iso_ts0_terminal_t50")
+    params = np.asarray(c["problem"]["params"])[None, :]
+    res = c_port.solve_lv_terminal(c["tcoeffs"][None], params, t0=c["grid"][0], t1=c["grid"][1], atol=c["atol"],
+                                   rtol=c["rtol"], dt0=c["dt0"], num_threads=1)  # fmt: skip
+    assert int(res["num_steps"][0]) == int(c["ref"]["num_steps"])
+    assert rel(res["mean"][0][0], c["ref"]["mean"][0]) < 1e-8
+    sens = c["reference_one_ulp_sensitivity"]
+    assert rel(res["mean"][0], c["ref"]["mean"]) < max(1e-6, 100 * sens["mean"])
+    cov = res["chol"][0] @ res["chol"][0].T
+    assert rel(cov, c["ref"]["cov"]) < max(1e-5, 100 * sens["cov"])
