@@ -49,6 +49,12 @@ def case(name, kind, grid, atol=None, rtol=None, dt0=0.1, problem=LV, diffuse_st
 
 # BASELINE configs[0/1]: one instance of the headline ensemble at its full horizon
 case("lv_iso_ts0_terminal_t50", "terminal", [0.0, 50.0], 1e-8, 1e-6)
+# ... and the first six instances of the ensemble bench.py times (PCG64 seed 0, one (B, 6) uniform
+# draw on [0.8, 1.2], parameters then initial values -- H.lv_ensemble / bench.lv_ensemble), same solver, full horizon
+_params, _u0 = H.lv_ensemble(1 << 20, seed=0)
+for _k in range(6):
+    case(f"lv_bench_ensemble_instance_{_k}_t50", "terminal", [0.0, 50.0], 1e-8, 1e-6,
+         problem=dict(vf="lotka_volterra", nu=4, params=list(map(float, _params[_k])), u0=list(map(float, _u0[_k]))))
 for fact in ("isotropic", "blockdiag", "dense"):
     # adaptive save_at without step clipping (interpolation at the checkpoints), three solver / error combinations
     case(f"lv_{fact}_solver_residual_i", "save_at", np.linspace(0.0, 4.0, 9), 1e-7, 1e-5, fact=fact, clip_dt=False,
