@@ -70,6 +70,11 @@ for prob_name, prob, num, du0 in (("lv", LV, 4, None), ("hires", HIRES, 5, None)
     for alg in ("jetexpand_ode_padded_scan", "jetexpand_ode_unroll"):
         aux(f"taylor_{prob_name}_{alg}", "taylor", base("terminal", [0.0, 1.0], problem=prob), alg=alg, num=num,
             du0=du0, t=0.25)  # fmt: skip
+# BASELINE configs[4] (the variant bench.py runs: Burgers, block-diagonal ts0, solver + state error + PI, t in [0, 1],
+# rtol 1e-4, atol 1e-7, then the log-marginal-likelihood of terminal-value data) at d = 64, full horizon (935 steps)
+aux("lml_terminal_burgers_d64_config5_full_horizon", "lml_terminal",
+    base("terminal", [0.0, 1.0], 1e-7, 1e-4, dt0=1.7584139942631142e-3, fact="blockdiag",
+         problem=dict(vf="burgers", nu=3, params=[0.01], u0=list(o_problems.burgers_u0(64)))))  # fmt: skip
 for fact in ("isotropic", "blockdiag", "dense"):
     aux(f"lml_terminal_{fact}", "lml_terminal",
         base("terminal", [0.0, 2.0], 1e-6, 1e-4, fact=fact, solver="solver_mle"))  # fmt: skip
