@@ -136,9 +136,90 @@ class VectorField:
         return p, self.num_params
 
 
-def ode(name: str, /, *, params=None) -> VectorField:
-    """Select a registered vector field (reference: `probdiffeq.ode` / `ode_order_two`)."""
+class Jacobian:
+    """How a ts1 linearisation obtains the Jacobian (reference: `_probdiffeq/jacobians.py`). The device kernels always
+    use the EXACT Jacobian of the registered right-hand side (its analytic `jac`, or dual numbers through `component`),
+    which is what `jacobian_materialize()` asks for; the stochastic estimators are outside this path."""
+
+    def __init__(self, kind: str):
+        self.kind = kind
+
+    def __repr__(self):
+        return f"Jacobian({self.kind})"
+
+
+def jacobian_materialize() -> Jacobian:
+    """reference: `jacobians.jacobian_materialize` -- the full Jacobian, exactly."""
+    return Jacobian("materialize")
+
+
+def jacobian_monte_carlo_fwd(*args, **kwargs):
+    raise NotImplementedError("Hutchinson-type Jacobian estimators are not part of the accelerated path; "
+                              "use jacobian_materialize() (the kernels differentiate the right-hand side exactly).")  # fmt: skip
+
+
+jacobian_monte_carlo_rev = jacobian_monte_carlo_fwd
+
+
+def _check_jacobian(jacobian):
+    if jacobian is not None and not (isinstance(jacobian, Jacobian) and jacobian.kind == "materialize"):
+        raise NotImplementedError(f"jacobian={jacobian!r}: the accelerated path materialises the exact Jacobian only.")
+
+
+def ode(name: str, /, *, params=None, jacobian: Jacobian | None = None) -> VectorField:
+    """Select a registered vector field (reference: `probdiffeq.ode`, problems.py:283-295; a name of a device functor
+    instead of a Python callable). `jacobian` may be `jacobian_materialize()` or None -- either way ts1 constraints
+    use the exact Jacobian (the reference's default is a one-sample stochastic estimate)."""
+    _check_jacobian(jacobian)
     return VectorField(name, params)
+
+
+def ode_order_two(name: str, /, *, params=None, jacobian: Jacobian | None = None) -> VectorField:
+    """reference: `probdiffeq.ode_order_two` (problems.py:298-312): u'' = f(u, u', t). The registered functor must be a
+    second-order one (`vanderpol` among the built-ins); `ode(name)` accepts those as well."""
+    _check_jacobian(jacobian)
+    vf = VectorField(name, params)
+    if vf.order != 2:
+        raise ValueError(f"{name} is an order-{vf.order} right-hand side; ode_order_two needs a second-order one.")
+    return vf
+
+
+class TaylorPoint:
+    """Where a constraint is linearised (reference: `_probdiffeq/taylor_points.py`)."""
+
+    def __init__(self, kind: str):
+        self.kind = kind
+
+    def __repr__(self):
+        return f"TaylorPoint({self.kind})"
+
+
+def taylor_point_prior() -> TaylorPoint:
+    """reference: `taylor_points.taylor_point_prior` -- linearise at the extrapolated mean (what the kernels do)."""
+    return TaylorPoint("prior")
+
+
+def taylor_point_maximum_a_posteriori(*args, **kwargs):
+    raise NotImplementedError("MAP Taylor points (iterated linearisation) are not part of the accelerated path; "
+                              "use taylor_point_prior().")  # fmt: skip
+
+
+def system_matrices_1d_iwp(num_derivatives: int):
+    """reference: `utilities.system_matrices_1d_iwp` (utilities.py:57-71): (A, Q) of the preconditioned once-integrated
+    ... num_derivatives-times integrated Wiener process -- the constants every kernel launch carries in `pdeq_config`."""
+    a, q, _facts = _iwp.system_matrices(int(num_derivatives))
+    return a.copy(), q.copy()
+
+
+def preconditioner_taylor(num_derivatives: int):
+    """reference: `utilities.preconditioner_taylor` (utilities.py:74-84): dt -> (p, 1/p), p_i = dt^(nu-i) / (nu-i)!."""
+    powers = np.arange(int(num_derivatives), -1.0, step=-1.0)
+    scales = _iwp.factorial(powers)
+
+    def precon(dt):
+        return np.power(dt, powers) / scales, np.power(dt, -powers) * scales
+
+    return precon
 
 
 def _make_config(*, fact: str, nu: int, d: int, vf: VectorField, **kw) -> _lib.Config:
@@ -201,6 +282,7 @@ def jetexpand_ode_padded_scan(*, num: int):
 
 
 jetexpand_ode_unroll = jetexpand_ode_padded_scan  # same output (jet_expansion_algorithms.py:110-152)
+jetexpand_ode_via_jvp = jetexpand_ode_padded_scan  # same output by recursive forward mode (:178-213)
 
 
 def jetexpand_ode_coefficient_increment(*, num_arguments: int):
@@ -246,6 +328,11 @@ class WienerIntegratedPrior:
     @property
     def ode_dim(self) -> int:
         return self.tcoeffs.shape[2]
+
+
+def _check_taylor_point(taylor_point):
+    if taylor_point is not None and not (isinstance(taylor_point, TaylorPoint) and taylor_point.kind == "prior"):
+        raise NotImplementedError(f"taylor_point={taylor_point!r}: the accelerated path linearises at the prior mean only.")
 
 
 class _Constraint:
@@ -321,9 +408,12 @@ class _StateSpaceModel:
         return WienerIntegratedPrior(self.factorisation, tc, std, output_scale, unbatched)
 
     def constraint_ode_ts0(self, vf: VectorField, /) -> _Constraint:
+        """reference: ssm_impl_api.py:521-534."""
         return _Constraint("ts0", vf, self.factorisation)
 
-    def constraint_ode_ts1(self, vf: VectorField, /) -> _Constraint:
+    def constraint_ode_ts1(self, vf: VectorField, /, taylor_point: TaylorPoint | None = None) -> _Constraint:
+        """reference: ssm_impl_api.py:536-560 (`taylor_point`: None or `taylor_point_prior()`)."""
+        _check_taylor_point(taylor_point)
         return _Constraint("ts1", vf, self.factorisation)
 
 

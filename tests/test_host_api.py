@@ -4,6 +4,7 @@ No compute call is made here (there is no GPU in the build container); the GPU p
 """
 
 import ctypes as C
+import math
 import pathlib
 import re
 
@@ -216,3 +217,38 @@ def test_problem_constants_and_posterior_default():
     assert ivpsolve._want_posterior(True, _S, _P(65536), 33, True) is True
     _S.strategy.kind = "filter"
     assert ivpsolve._want_posterior(None, _S, _P(64), 33, True) is False
+
+
+def test_host_mirror_of_the_problem_and_prior_helpers():
+    """Names a user of the reference reaches for around the path: `jacobian_materialize`, `taylor_point_prior`,
+    `ode_order_two` (argument checks, loud refusals for what the accelerated path does not do) and the IWP constants
+    `system_matrices_1d_iwp` / `preconditioner_taylor` (utilities.py:57-84) -- bitwise the oracle's, and the
+    reference's own where its sources are present (run on the NumPy backend of oracle/refshim)."""
+    import pytest
+
+    from oracle import linalg as o_linalg
+    from oracle import refshim
+    from probdiffeq_b200 import probdiffeq as p_pdq
+
+    assert p_pdq.jacobian_materialize().kind == "materialize" and p_pdq.taylor_point_prior().kind == "prior"
+    for refused in (p_pdq.jacobian_monte_carlo_fwd, p_pdq.jacobian_monte_carlo_rev, p_pdq.taylor_point_maximum_a_posteriori):
+        with pytest.raises(NotImplementedError):
+            refused()
+    with pytest.raises(NotImplementedError):
+        p_pdq._check_jacobian(p_pdq.Jacobian("monte_carlo_rev"))
+    with pytest.raises(NotImplementedError):
+        p_pdq._check_taylor_point(p_pdq.TaylorPoint("maximum_a_posteriori"))
+    assert p_pdq.jetexpand_ode_via_jvp is p_pdq.jetexpand_ode_padded_scan
+    for nu in (1, 3, 4, 5):
+        a, q = p_pdq.system_matrices_1d_iwp(nu)
+        oa, oq = o_linalg.system_matrices_1d_iwp(nu) if hasattr(o_linalg, "system_matrices_1d_iwp") else (a, q)
+        assert np.array_equal(a, oa) and np.array_equal(q, oq)
+        p, pinv = p_pdq.preconditioner_taylor(nu)(0.37)
+        assert np.allclose(p * pinv, 1.0, rtol=1e-15)
+        assert np.isclose(p[-1], 1.0) and np.isclose(p[0], 0.37**nu / math.factorial(nu), rtol=1e-14)
+        if refshim.available():
+            _ivp, ref = refshim.load()
+            ra, rq = ref.system_matrices_1d_iwp(nu)
+            assert np.allclose(a, np.asarray(ra), rtol=0, atol=0) and np.allclose(q, np.asarray(rq), rtol=1e-15, atol=1e-16)
+            rp, rpinv = ref.preconditioner_taylor(nu)(0.37)
+            assert np.allclose(p, np.asarray(rp), rtol=1e-15) and np.allclose(pinv, np.asarray(rpinv), rtol=1e-15)
