@@ -37,14 +37,15 @@ CASES = []
 
 
 def case(name, kind, grid, atol=None, rtol=None, dt0=0.1, problem=LV, diffuse_start=False, step_count_rtol=0.0,
-         exact_step_prefix=0, **spec):  # fmt: skip
+         exact_step_prefix=0, output_scale=None, solve_kwargs=None, **spec):  # fmt: skip
     """`step_count_rtol` > 0 marks a solve so long that the reference's own accepted-step count moves under a one-ulp
     change of its input (or is expected to in another arithmetic): step counts are then compared to that tolerance,
     except at the first `exact_step_prefix` checkpoints, where they must be identical (checked here for the reference
     against its own perturbed run and against the oracle)."""
     CASES.append(dict(name=name, kind=kind, grid=list(map(float, grid)), atol=atol, rtol=rtol, dt0=dt0,
                       problem=problem, diffuse_start=diffuse_start, step_count_rtol=step_count_rtol,
-                      exact_step_prefix=exact_step_prefix, spec=H.spec(vf=problem["vf"], **spec)))  # fmt: skip
+                      exact_step_prefix=exact_step_prefix, output_scale=output_scale,
+                      solve_kwargs=solve_kwargs or {}, spec=H.spec(vf=problem["vf"], **spec)))  # fmt: skip
 
 
 # BASELINE configs[0/1]: one instance of the headline ensemble at its full horizon
@@ -108,6 +109,34 @@ case("lv_isotropic_state_deriv2_unitstep_rms_then_scale", "terminal", [0.0, 5.0]
      derivative_idx=2, error_per_unit_step=True, error_norm="rms_then_scale")  # fmt: skip
 case("lv_blockdiag_residual_unitstep_clipped_save_at", "save_at", np.linspace(0.0, 4.0, 9), 1e-6, 1e-4,
      fact="blockdiag", error="residual_std", error_per_unit_step=True, clip_dt=True)  # fmt: skip
+# non-default options of the loop, the controllers, the solvers and the prior (every kernel family sees damp != 0,
+# which switches off the constant-matrix shortcut of the error estimate)
+SAVE = np.linspace(0.0, 4.0, 9)
+case("lv_isotropic_damp", "save_at", SAVE, 1e-7, 1e-5, clip_dt=False, solve_kwargs=dict(damp=1e-3))
+case("lv_blockdiag_ts1_residual_damp", "save_at", SAVE, 1e-7, 1e-5, fact="blockdiag", constraint="ts1",
+     error="residual_std", clip_dt=False, solve_kwargs=dict(damp=1e-3))  # fmt: skip
+case("lv_dense_ts1_damp", "save_at", SAVE, 1e-7, 1e-5, fact="dense", constraint="ts1", clip_dt=False,
+     solve_kwargs=dict(damp=1e-3))  # fmt: skip
+case("lv_blockdiag_fixedpoint_damp", "save_at", SAVE, 1e-6, 1e-4, fact="blockdiag", strategy="fixedpoint",
+     solver="solver_dynamic", error="residual_std", control="i", clip_dt=False, solve_kwargs=dict(damp=1e-3))  # fmt: skip
+case("lv_isotropic_pi_parameters", "save_at", SAVE, 1e-7, 1e-5, clip_dt=False,
+     control_kwargs=dict(safety=0.9, factor_min=0.3, factor_max=5.0, exponent_integral=0.25,
+                         exponent_proportional=0.3))  # fmt: skip
+case("lv_isotropic_i_parameters", "save_at", SAVE, 1e-7, 1e-5, clip_dt=False, control="i",
+     control_kwargs=dict(safety=0.8, factor_min=0.3, factor_max=4.0))  # fmt: skip
+case("lv_isotropic_eps_clipped", "save_at", SAVE, 1e-7, 1e-5, clip_dt=True, solve_kwargs=dict(eps=1e-3))
+case("lv_isotropic_prior_scale", "save_at", SAVE, 1e-7, 1e-5, clip_dt=False, output_scale=1.5)
+case("lv_blockdiag_prior_scale_mle", "save_at", SAVE, 1e-7, 1e-5, fact="blockdiag", solver="solver_mle", clip_dt=False,
+     output_scale=[1.5, 0.75])  # fmt: skip
+case("lv_dense_prior_scale_dynamic", "save_at", SAVE, 1e-7, 1e-5, fact="dense", solver="solver_dynamic",
+     clip_dt=False, output_scale=[1.5, 0.75])  # fmt: skip
+case("lv_isotropic_mle_no_underconfidence_correction", "save_at", SAVE, 1e-7, 1e-5, solver="solver_mle",
+     clip_dt=False, solver_kwargs=dict(correct_asymptotic_underconfidence=False))  # fmt: skip
+case("lv_blockdiag_ts1_dynamic_re_linearize_after_calibration", "save_at", SAVE, 1e-7, 1e-5, fact="blockdiag",
+     constraint="ts1", solver="solver_dynamic", clip_dt=False,
+     solver_kwargs=dict(re_linearize_after_calibration=True))  # fmt: skip
+case("lv_dense_ts1_re_linearize_before_error", "save_at", SAVE, 1e-7, 1e-5, fact="dense", constraint="ts1",
+     clip_dt=False, error_kwargs=dict(re_linearize_before_error=True))  # fmt: skip
 # constraint_init: exact initial value, diffuse derivatives, one Bayes update at t0 (solvers.py:361-372, 526-537, 670-680)
 case("lv_isotropic_constraint_init_fixedgrid", "fixed", np.linspace(0.0, 0.5, 21), diffuse_start=True,
      constraint_init=True)  # fmt: skip
@@ -148,9 +177,10 @@ def diffuse_std(c):
 
 def reference_prior(ssm, c):
     tcoeffs = [np.asarray(x) for x in c["tcoeffs"]]
+    scale = None if c.get("output_scale") is None else np.asarray(c["output_scale"])
     if not c.get("diffuse_start"):
-        return ssm.prior_wiener_integrated(tcoeffs)
-    return ssm.prior_wiener_integrated_diffuse(tcoeffs, [np.asarray(x) for x in diffuse_std(c)])
+        return ssm.prior_wiener_integrated(tcoeffs, output_scale=scale)
+    return ssm.prior_wiener_integrated_diffuse(tcoeffs, [np.asarray(x) for x in diffuse_std(c)], output_scale=scale)
 
 
 def reference_vf(pdq, problem):
@@ -169,14 +199,15 @@ def run_reference(c):
     ssm, solver, err, ctrl = H._build(pdq, ivp, s, vf)
     prior = reference_prior(ssm, c)
     grid = np.asarray(c["grid"])
+    kw = c.get("solve_kwargs") or {}  # eps, damp
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         if c["kind"] == "terminal":
             solve = ivp.solve_adaptive_terminal_values(solver=solver, error=err, control=ctrl, clip_dt=s["clip_dt"])
-            return solve(prior, t0=grid[0], t1=grid[1], atol=c["atol"], rtol=c["rtol"], dt0=c["dt0"])
+            return solve(prior, t0=grid[0], t1=grid[1], atol=c["atol"], rtol=c["rtol"], dt0=c["dt0"], **kw)
         if c["kind"] == "save_at":
             solve = ivp.solve_adaptive_save_at(solver=solver, error=err, control=ctrl, clip_dt=s["clip_dt"], warn=False)
-            return solve(prior, save_at=grid, atol=c["atol"], rtol=c["rtol"], dt0=c["dt0"])
+            return solve(prior, save_at=grid, atol=c["atol"], rtol=c["rtol"], dt0=c["dt0"], **kw)
         return ivp.solve_fixed_grid(solver=solver)(prior, grid=grid)
 
 
@@ -186,9 +217,11 @@ def run_oracle(c):
     tc = np.asarray(c["tcoeffs"])
     grid = np.asarray(c["grid"])
     init_std = diffuse_std(c) if c.get("diffuse_start") else None
+    scale = None if c.get("output_scale") is None else np.asarray(c["output_scale"])
     if c["kind"] == "fixed":
-        return H.oracle_solve_fixed(s, tc, params, grid, init_std=init_std)
-    sol, _ = H.oracle_solve_save_at(s, tc, params, grid, c["atol"], c["rtol"], dt0=c["dt0"], init_std=init_std)
+        return H.oracle_solve_fixed(s, tc, params, grid, init_std=init_std, output_scale=scale)
+    sol, _ = H.oracle_solve_save_at(s, tc, params, grid, c["atol"], c["rtol"], dt0=c["dt0"], init_std=init_std,
+                                    output_scale=scale, **(c.get("solve_kwargs") or {}))  # fmt: skip
     return sol.terminal() if c["kind"] == "terminal" else sol
 
 
@@ -281,7 +314,7 @@ def main():
             out[f"{c['name']}/{k}"] = v
         out[f"{c['name']}/tcoeffs"] = c["tcoeffs"]
         meta = {k: c[k] for k in ("name", "kind", "grid", "atol", "rtol", "dt0", "problem", "spec", "diffuse_start",
-                                   "step_count_rtol", "exact_step_prefix")}  # fmt: skip
+                                   "step_count_rtol", "exact_step_prefix", "output_scale", "solve_kwargs")}  # fmt: skip
         meta["reference_one_ulp_sensitivity"] = sens
         row["reference_one_ulp_sensitivity"] = sens
         out[f"{c['name']}/meta"] = np.asarray(json.dumps(meta))

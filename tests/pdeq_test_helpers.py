@@ -37,15 +37,16 @@ def _build(mod_pdq, mod_ivp, s, vf):
         strat = {"filter": mod_pdq.strategy_filter, "fixedpoint": mod_pdq.strategy_smoother_fixedpoint,
                  "fixedinterval": mod_pdq.strategy_smoother_fixedinterval}[s["strategy"]]()
     extra = {"constraint_init": cons} if s.get("constraint_init") else {}
-    solver = getattr(mod_pdq, s["solver"])(strategy=strat, constraint=cons, **extra)
+    solver = getattr(mod_pdq, s["solver"])(strategy=strat, constraint=cons, **extra, **s.get("solver_kwargs", {}))
     norm = getattr(mod_pdq, "error_norm_" + s["error_norm"])()
     if s["error"] == "state_std":
         err = mod_pdq.error_state_std(constraint=cons, error_norm=norm, derivative_idx=s["derivative_idx"],
-                                      error_per_unit_step=s["error_per_unit_step"])  # fmt: skip
+                                      error_per_unit_step=s["error_per_unit_step"], **s.get("error_kwargs", {}))  # fmt: skip
     else:
         err = mod_pdq.error_residual_std(constraint=cons, error_norm=norm,
-                                         error_per_unit_step=s["error_per_unit_step"])  # fmt: skip
-    ctrl = mod_ivp.control_proportional_integral() if s["control"] == "pi" else mod_ivp.control_integral()
+                                         error_per_unit_step=s["error_per_unit_step"], **s.get("error_kwargs", {}))  # fmt: skip
+    make_control = mod_ivp.control_proportional_integral if s["control"] == "pi" else mod_ivp.control_integral
+    ctrl = make_control(**s.get("control_kwargs", {}))
     return ssm, solver, err, ctrl
 
 
@@ -53,7 +54,8 @@ def oracle_vf(s, params):
     return o_pdq.ode(s["vf"], params if params is not None and len(params) else None)
 
 
-def oracle_solve_save_at(s, tcoeffs, params, save_at, atol, rtol, dt0=0.1, init_std=None, output_scale=None):
+def oracle_solve_save_at(s, tcoeffs, params, save_at, atol, rtol, dt0=0.1, init_std=None, output_scale=None,
+                         **solve_kwargs):  # fmt: skip
     """Run the oracle on ONE instance. Returns (solution, trace)."""
     vf = oracle_vf(s, params)
     ssm, solver, err, ctrl = _build(o_pdq, o_ivp, s, vf)
@@ -64,7 +66,7 @@ def oracle_solve_save_at(s, tcoeffs, params, save_at, atol, rtol, dt0=0.1, init_
     trace = []
     solve = o_ivp.solve_adaptive_save_at(solver=solver, error=err, control=ctrl, clip_dt=s["clip_dt"], warn=False,
                                          trace=trace)  # fmt: skip
-    return solve(prior, save_at=save_at, atol=atol, rtol=rtol, dt0=dt0), trace
+    return solve(prior, save_at=save_at, atol=atol, rtol=rtol, dt0=dt0, **solve_kwargs), trace
 
 
 def oracle_solve_fixed(s, tcoeffs, params, grid, output_scale=None, init_std=None):

@@ -22,17 +22,19 @@ def product_solve(c):
     params = np.asarray(prob["params"])[None, :] if prob["params"] else None
     p_pdq, p_ivp, vf, ssm, solver, err, ctrl = H.product_build(s, params)
     tcoeffs = torch.from_numpy(c["tcoeffs"][None]).cuda()
+    scale = None if c.get("output_scale") is None else np.asarray(c["output_scale"])
     if c.get("diffuse_start"):
-        prior = ssm.prior_wiener_integrated_diffuse(tcoeffs, torch.from_numpy(diffuse_std(c)).cuda())
+        prior = ssm.prior_wiener_integrated_diffuse(tcoeffs, torch.from_numpy(diffuse_std(c)).cuda(), output_scale=scale)
     else:
-        prior = ssm.prior_wiener_integrated(tcoeffs)
+        prior = ssm.prior_wiener_integrated(tcoeffs, output_scale=scale)
+    kw = c.get("solve_kwargs") or {}  # eps, damp
     grid = np.asarray(c["grid"])
     if c["kind"] == "terminal":
         solve = p_ivp.solve_adaptive_terminal_values(solver=solver, error=err, control=ctrl, clip_dt=s["clip_dt"])
-        sol = solve(prior, t0=grid[0], t1=grid[1], atol=c["atol"], rtol=c["rtol"], dt0=c["dt0"])
+        sol = solve(prior, t0=grid[0], t1=grid[1], atol=c["atol"], rtol=c["rtol"], dt0=c["dt0"], **kw)
     elif c["kind"] == "save_at":
         solve = p_ivp.solve_adaptive_save_at(solver=solver, error=err, control=ctrl, clip_dt=s["clip_dt"], warn=False)
-        sol = solve(prior, save_at=grid, atol=c["atol"], rtol=c["rtol"], dt0=c["dt0"])
+        sol = solve(prior, save_at=grid, atol=c["atol"], rtol=c["rtol"], dt0=c["dt0"], **kw)
     else:
         sol = p_ivp.solve_fixed_grid(solver=solver)(prior, grid=grid)
     torch.cuda.synchronize()

@@ -94,11 +94,12 @@ def oracle_run(c):
     params = np.asarray(prob["params"]) if prob["params"] else None
     grid = np.asarray(c["grid"])
     init_std = diffuse_std(c) if c.get("diffuse_start") else None
+    scale = None if c.get("output_scale") is None else np.asarray(c["output_scale"])
     if c["kind"] == "fixed":
-        sol = H.oracle_solve_fixed(s, c["tcoeffs"], params, grid, init_std=init_std)
+        sol = H.oracle_solve_fixed(s, c["tcoeffs"], params, grid, init_std=init_std, output_scale=scale)
     else:
         sol, _ = H.oracle_solve_save_at(s, c["tcoeffs"], params, grid, c["atol"], c["rtol"], dt0=c["dt0"],
-                                        init_std=init_std)  # fmt: skip
+                                        init_std=init_std, output_scale=scale, **(c.get("solve_kwargs") or {}))  # fmt: skip
         if c["kind"] == "terminal":
             sol = sol.terminal()
     u = sol.u
