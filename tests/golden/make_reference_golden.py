@@ -37,7 +37,7 @@ CASES = []
 
 
 def case(name, kind, grid, atol=None, rtol=None, dt0=0.1, problem=LV, diffuse_start=False, step_count_rtol=0.0,
-         exact_step_prefix=0, output_scale=None, solve_kwargs=None, **spec):  # fmt: skip
+         exact_step_prefix=0, output_scale=None, solve_kwargs=None, prior_kwargs=None, **spec):  # fmt: skip
     """`step_count_rtol` > 0 marks a solve so long that the reference's own accepted-step count moves under a one-ulp
     change of its input (or is expected to in another arithmetic): step counts are then compared to that tolerance,
     except at the first `exact_step_prefix` checkpoints, where they must be identical (checked here for the reference
@@ -45,7 +45,8 @@ def case(name, kind, grid, atol=None, rtol=None, dt0=0.1, problem=LV, diffuse_st
     CASES.append(dict(name=name, kind=kind, grid=list(map(float, grid)), atol=atol, rtol=rtol, dt0=dt0,
                       problem=problem, diffuse_start=diffuse_start, step_count_rtol=step_count_rtol,
                       exact_step_prefix=exact_step_prefix, output_scale=output_scale,
-                      solve_kwargs=solve_kwargs or {}, spec=H.spec(vf=problem["vf"], **spec)))  # fmt: skip
+                      solve_kwargs=solve_kwargs or {}, prior_kwargs=prior_kwargs or {},
+                      spec=H.spec(vf=problem["vf"], **spec)))  # fmt: skip
 
 
 # BASELINE configs[0/1]: one instance of the headline ensemble at its full horizon
@@ -137,6 +138,16 @@ case("lv_blockdiag_ts1_dynamic_re_linearize_after_calibration", "save_at", SAVE,
      solver_kwargs=dict(re_linearize_after_calibration=True))  # fmt: skip
 case("lv_dense_ts1_re_linearize_before_error", "save_at", SAVE, 1e-7, 1e-5, fact="dense", constraint="ts1",
      clip_dt=False, error_kwargs=dict(re_linearize_before_error=True))  # fmt: skip
+# an initial condition known to 1e-3 only (prior_wiener_integrated(is_exact=False, inexact_eps=...))
+case("lv_blockdiag_inexact_initial_values", "save_at", SAVE, 1e-7, 1e-5, fact="blockdiag", solver="solver_mle",
+     clip_dt=False, prior_kwargs=dict(is_exact=False, inexact_eps=1e-3))  # fmt: skip
+# a second-order problem in the isotropic and the block-diagonal model (Van der Pol, mu = 5: not stiff, so ts0 works)
+VDP5 = dict(vf="vanderpol", nu=4, params=[5.0], u0=[2.0])
+case("vanderpol5_isotropic_ts0_mle", "save_at", np.linspace(0.0, 3.0, 7), 1e-7, 1e-5, dt0=1e-2, problem=VDP5,
+     solver="solver_mle", clip_dt=False)  # fmt: skip
+case("vanderpol5_blockdiag_ts1_dynamic_residual", "save_at", np.linspace(0.0, 3.0, 7), 1e-7, 1e-5, dt0=1e-2,
+     problem=VDP5, fact="blockdiag", constraint="ts1", solver="solver_dynamic", error="residual_std", control="i",
+     clip_dt=False)  # fmt: skip
 # constraint_init: exact initial value, diffuse derivatives, one Bayes update at t0 (solvers.py:361-372, 526-537, 670-680)
 case("lv_isotropic_constraint_init_fixedgrid", "fixed", np.linspace(0.0, 0.5, 21), diffuse_start=True,
      constraint_init=True)  # fmt: skip
@@ -179,7 +190,7 @@ def reference_prior(ssm, c):
     tcoeffs = [np.asarray(x) for x in c["tcoeffs"]]
     scale = None if c.get("output_scale") is None else np.asarray(c["output_scale"])
     if not c.get("diffuse_start"):
-        return ssm.prior_wiener_integrated(tcoeffs, output_scale=scale)
+        return ssm.prior_wiener_integrated(tcoeffs, output_scale=scale, **(c.get("prior_kwargs") or {}))
     return ssm.prior_wiener_integrated_diffuse(tcoeffs, [np.asarray(x) for x in diffuse_std(c)], output_scale=scale)
 
 
@@ -220,6 +231,10 @@ def run_oracle(c):
     scale = None if c.get("output_scale") is None else np.asarray(c["output_scale"])
     if c["kind"] == "fixed":
         return H.oracle_solve_fixed(s, tc, params, grid, init_std=init_std, output_scale=scale)
+    if c.get("prior_kwargs"):  # is_exact=False: every Taylor coefficient known to inexact_eps only
+        assert c["prior_kwargs"].get("is_exact") is False and init_std is None
+        n, d = tc.shape
+        init_std = np.full((n,) if s["fact"] == "isotropic" else (n, d), c["prior_kwargs"]["inexact_eps"])
     sol, _ = H.oracle_solve_save_at(s, tc, params, grid, c["atol"], c["rtol"], dt0=c["dt0"], init_std=init_std,
                                     output_scale=scale, **(c.get("solve_kwargs") or {}))  # fmt: skip
     return sol.terminal() if c["kind"] == "terminal" else sol
@@ -314,7 +329,8 @@ def main():
             out[f"{c['name']}/{k}"] = v
         out[f"{c['name']}/tcoeffs"] = c["tcoeffs"]
         meta = {k: c[k] for k in ("name", "kind", "grid", "atol", "rtol", "dt0", "problem", "spec", "diffuse_start",
-                                   "step_count_rtol", "exact_step_prefix", "output_scale", "solve_kwargs")}  # fmt: skip
+                                   "step_count_rtol", "exact_step_prefix", "output_scale", "solve_kwargs",
+                                   "prior_kwargs")}  # fmt: skip
         meta["reference_one_ulp_sensitivity"] = sens
         row["reference_one_ulp_sensitivity"] = sens
         out[f"{c['name']}/meta"] = np.asarray(json.dumps(meta))

@@ -26,7 +26,7 @@ def product_solve(c):
     if c.get("diffuse_start"):
         prior = ssm.prior_wiener_integrated_diffuse(tcoeffs, torch.from_numpy(diffuse_std(c)).cuda(), output_scale=scale)
     else:
-        prior = ssm.prior_wiener_integrated(tcoeffs, output_scale=scale)
+        prior = ssm.prior_wiener_integrated(tcoeffs, output_scale=scale, **(c.get("prior_kwargs") or {}))
     kw = c.get("solve_kwargs") or {}  # eps, damp
     grid = np.asarray(c["grid"])
     if c["kind"] == "terminal":

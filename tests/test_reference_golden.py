@@ -95,6 +95,9 @@ def oracle_run(c):
     grid = np.asarray(c["grid"])
     init_std = diffuse_std(c) if c.get("diffuse_start") else None
     scale = None if c.get("output_scale") is None else np.asarray(c["output_scale"])
+    if c.get("prior_kwargs"):  # is_exact=False: every Taylor coefficient known to inexact_eps only
+        n, d = c["tcoeffs"].shape
+        init_std = np.full((n,) if s["fact"] == "isotropic" else (n, d), c["prior_kwargs"]["inexact_eps"])
     if c["kind"] == "fixed":
         sol = H.oracle_solve_fixed(s, c["tcoeffs"], params, grid, init_std=init_std, output_scale=scale)
     else:
