@@ -138,6 +138,19 @@ case("lv_blockdiag_ts1_dynamic_re_linearize_after_calibration", "save_at", SAVE,
      solver_kwargs=dict(re_linearize_after_calibration=True))  # fmt: skip
 case("lv_dense_ts1_re_linearize_before_error", "save_at", SAVE, 1e-7, 1e-5, fact="dense", constraint="ts1",
      clip_dt=False, error_kwargs=dict(re_linearize_before_error=True))  # fmt: skip
+# the interpolation branches of the loop (solvers_via_adaptive_steps.py:241-247, 323-375): the fixed-point smoother
+# with clipped steps (interp_at_t1 only), several checkpoints inside ONE step (interp_beyond_t1 repeatedly) for the
+# filter and for the fixed-point smoother, and a clipped solve on the same dense grid
+for fact in ("isotropic", "blockdiag", "dense"):
+    case(f"lv_{fact}_fixedpoint_clipped_dynamic", "save_at", SAVE, 1e-6, 1e-4, fact=fact, strategy="fixedpoint",
+         solver="solver_dynamic", error="residual_std", control="i", clip_dt=True)  # fmt: skip
+DENSE_GRID = np.linspace(0.0, 2.0, 41)
+case("lv_isotropic_many_checkpoints_per_step", "save_at", DENSE_GRID, 1e-4, 1e-2, clip_dt=False)
+case("lv_isotropic_many_checkpoints_clipped", "save_at", DENSE_GRID, 1e-4, 1e-2, clip_dt=True)
+case("lv_blockdiag_fixedpoint_many_checkpoints_per_step", "save_at", DENSE_GRID, 1e-4, 1e-2, fact="blockdiag",
+     strategy="fixedpoint", solver="solver_mle", clip_dt=False)  # fmt: skip
+case("lv_dense_fixedpoint_many_checkpoints_per_step", "save_at", DENSE_GRID, 1e-4, 1e-2, fact="dense",
+     strategy="fixedpoint", solver="solver_dynamic", error="residual_std", control="i", clip_dt=False)  # fmt: skip
 # an initial condition known to 1e-3 only (prior_wiener_integrated(is_exact=False, inexact_eps=...))
 case("lv_blockdiag_inexact_initial_values", "save_at", SAVE, 1e-7, 1e-5, fact="blockdiag", solver="solver_mle",
      clip_dt=False, prior_kwargs=dict(is_exact=False, inexact_eps=1e-3))  # fmt: skip
