@@ -9,6 +9,9 @@ modules from `/root/reference` on top of it.  What runs is then the reference's 
 reproduced is XLA's arithmetic (operation fusion, its LAPACK calls) and JAX's autodiff -- results agree with JAX at
 rounding level, not bit for bit.
 
+The backend is validated by the reference's OWN test-suite: `python -m oracle.refshim.run_reference_tests` runs the
+modules of `/root/reference/tests` that collect without `pytest_cases` on it (38 pass; tests/test_refshim_backend.py).
+
 Used by `tests/golden/make_reference_golden.py` (which only runs where `/root/reference` exists, i.e. in the build
 container) to write `tests/golden/reference_numpy_backend.npz`: outputs of the reference's own step loop that pin the
 oracle and the CUDA path.  Nothing under `probdiffeq_b200/` imports this.

@@ -163,7 +163,28 @@ class _ExactSeries:
             return x
         return _ExactSeries([fractions.Fraction(float(x))] + [fractions.Fraction(0)] * order)
 
+    # scalar-like array methods a right-hand side may call on a component
+    def reshape(self, *shape):
+        shape = shape[0] if len(shape) == 1 and isinstance(shape[0], (tuple, list)) else shape
+        out = _np.empty(tuple(shape), dtype=object)
+        for idx in _np.ndindex(out.shape):
+            out[idx] = self
+        return out
+
+    def squeeze(self):
+        return self
+
+    @staticmethod
+    def _broadcast(op, array):
+        """`series (op) array`: element by element, as an object array."""
+        out = _np.empty(array.shape, dtype=object)
+        for idx in _np.ndindex(array.shape):
+            out[idx] = op(array[idx])
+        return out
+
     def __add__(self, other):
+        if isinstance(other, _np.ndarray) and other.ndim > 0:
+            return self._broadcast(lambda o: self + o, other)
         other = self._lift(other, len(self.c) - 1)
         return _ExactSeries([a + b for a, b in zip(self.c, other.c)])
 
@@ -173,12 +194,18 @@ class _ExactSeries:
         return _ExactSeries([-a for a in self.c])
 
     def __sub__(self, other):
+        if isinstance(other, _np.ndarray) and other.ndim > 0:
+            return self._broadcast(lambda o: self - o, other)
         return self + (-self._lift(other, len(self.c) - 1))
 
     def __rsub__(self, other):
+        if isinstance(other, _np.ndarray) and other.ndim > 0:
+            return self._broadcast(lambda o: o - self, other)
         return self._lift(other, len(self.c) - 1) - self
 
     def __mul__(self, other):
+        if isinstance(other, _np.ndarray) and other.ndim > 0:
+            return self._broadcast(lambda o: self * o, other)
         other = self._lift(other, len(self.c) - 1)
         n = len(self.c)
         return _ExactSeries([sum(self.c[i] * other.c[k - i] for i in range(k + 1)) for k in range(n)])

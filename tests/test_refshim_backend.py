@@ -73,3 +73,25 @@ def test_complex_step_derivatives_are_exact_to_rounding_for_polynomials():
     jac = np.asarray([[u[1] - 2.0, u[0]], [u[1] ** 2, 2 * u[0] * u[1]]])
     assert np.allclose(np.asarray(tangent), jac @ v, rtol=1e-15, atol=1e-16)
     assert np.allclose(np.asarray(func.jacfwd(f)(u)), jac, rtol=1e-15, atol=1e-16)
+
+
+def test_the_references_own_tests_pass_on_this_backend():
+    """Where the reference's sources exist (the build container): those modules of the reference's OWN test-suite that
+    collect without `pytest_cases` and concern this path -- solver vs an independent integrator on a pytree-valued
+    Lotka-Volterra problem, fixed grid == adaptive grid, dense == isotropic == block-diagonal, dynamic vs MLE
+    calibration, the second-order harmonic oscillator, the IWP known answers, the controllers, the Cholesky utilities
+    -- run on the NumPy backend the parity fixtures were produced on (oracle/refshim/run_reference_tests.py; the record
+    is profiles/r3k_reference_own_tests_on_numpy_backend.txt)."""
+    import os
+    import subprocess
+    import sys
+
+    from oracle import refshim
+
+    if not refshim.available():
+        pytest.skip("the reference sources are not on this machine")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    run = subprocess.run([sys.executable, "-m", "oracle.refshim.run_reference_tests"], cwd=root, capture_output=True,
+                         text=True, env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1"), timeout=600)  # fmt: skip
+    last = run.stdout.strip().splitlines()[-1]
+    assert run.returncode == 0 and "38 passed" in last and "failed" not in last, run.stdout[-2000:]
