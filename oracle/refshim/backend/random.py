@@ -7,7 +7,12 @@ def prng_key(*, seed):
 
 
 def split(key, num):
-    return [_np.random.Generator(_np.random.PCG64(int(key.integers(0, 2**31)))) for _ in range(num)]
+    """`num` independent generators, as an ARRAY of generators (JAX returns an array of keys, and the reference maps
+    over it with vmap in `MarkovSequence.sample`)."""
+    out = _np.empty((num,), dtype=object)
+    for i in range(num):
+        out[i] = _np.random.Generator(_np.random.PCG64(int(key.integers(0, 2**31))))
+    return out
 
 
 def normal(key, /, shape, dtype=None):

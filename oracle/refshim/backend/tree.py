@@ -207,7 +207,17 @@ def _transpose(list_of_trees):
 
 
 def _is_array_list(x):
-    return isinstance(x, list) and len(x) > 0 and isinstance(x[0], (_np.ndarray, _np.generic, float, int))
+    return isinstance(x, list) and len(x) > 0 and isinstance(x[0], (_np.ndarray, _np.generic, float, int,
+                                                                     _np.random.Generator))  # fmt: skip
+
+
+def _stack_leaves(xs, combine):
+    if isinstance(xs[0], _np.random.Generator):  # PRNG state carried by a stochastic Jacobian: an array of generators
+        out = _np.empty((len(xs),), dtype=object)
+        for i, x in enumerate(xs):
+            out[i] = x
+        return out
+    return combine([_np.asarray(x) for x in xs])
 
 
 def tree_array_concatenate(list_of_trees):
@@ -216,8 +226,7 @@ def tree_array_concatenate(list_of_trees):
 
 
 def tree_array_stack(list_of_trees):
-    return tree_map(lambda xs: _np.stack([_np.asarray(x) for x in xs]), _transpose(list_of_trees),
-                    is_leaf=_is_array_list)  # fmt: skip
+    return tree_map(lambda xs: _stack_leaves(xs, _np.stack), _transpose(list_of_trees), is_leaf=_is_array_list)
 
 
 def tree_array_prepend(y, X, /):

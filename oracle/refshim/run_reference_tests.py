@@ -1,5 +1,7 @@
-"""Run those of the REFERENCE's own tests (/root/reference/tests) that do not need `pytest_cases` on the NumPy backend
-of oracle/refshim: the reference's test-suite is what validates the backend the parity fixtures were produced on.
+"""Run the REFERENCE's own tests (/root/reference/tests) that concern this path on the NumPy backend of oracle/refshim
+(`pytest_cases`, which the suite is built on, is not installed: backend/testing.py carries a small stand-in; modules
+that need `diffeqzoo` or exercise parts outside the path -- MAP Taylor points, jet-lifted residuals, the other priors,
+matrix-free models -- are not in the list): the reference's test-suite is what validates the backend the parity fixtures were produced on.
 TEST INFRASTRUCTURE; needs the reference's sources, so it runs in the build container only.
 
     python -m oracle.refshim.run_reference_tests [extra pytest arguments]
@@ -24,6 +26,23 @@ MODULES = (
     "test_probdiffeq/test_priors/test_wiener_integrated.py",
     "test_probdiffeq/test_strategies/test_warnings_for_wrong_strategies.py",
     "test_util/test_cholesky_util.py",
+    # ... and, through the small stand-in for pytest_cases in backend/testing.py (fixture / case /
+    # parametrize_with_cases), the modules built on case functions:
+    "test_ivpsolve/test_solve_adaptive_save_at.py",
+    "test_ivpsolve/test_pytree_output_structure.py",
+    "test_probdiffeq/test_calibration/test_mle.py",
+    "test_probdiffeq/test_losses/test_lml_terminal_values.py",
+    "test_probdiffeq/test_losses/test_lml_timeseries.py",
+    "test_probdiffeq/test_strategies/test_smoother_fixedinterval_vs_fixedpoint.py",
+    "test_probdiffeq/test_strategies/test_filter_vs_smoother.py",
+    "test_probdiffeq/test_dense_output/test_interpolate_filter.py",
+    "test_probdiffeq/test_dense_output/test_interpolate_smoother.py",
+    "test_probdiffeq/test_dense_output/test_offgrid_marginals_vs_solve_and_save_at.py",
+    "test_probdiffeq/test_dense_output/test_behaviour_close_to_t1.py",
+    "test_probdiffeq/test_priors/test_is_exact.py",
+    "test_probdiffeq/test_priors/test_output_scales.py",
+    "test_probdiffeq/test_priors/test_diffuse_derivatives.py",
+    "test_probdiffeq/test_sample.py",
 )
 
 

@@ -76,12 +76,13 @@ def test_complex_step_derivatives_are_exact_to_rounding_for_polynomials():
 
 
 def test_the_references_own_tests_pass_on_this_backend():
-    """Where the reference's sources exist (the build container): those modules of the reference's OWN test-suite that
-    collect without `pytest_cases` and concern this path -- solver vs an independent integrator on a pytree-valued
-    Lotka-Volterra problem, fixed grid == adaptive grid, dense == isotropic == block-diagonal, dynamic vs MLE
-    calibration, the second-order harmonic oscillator, the IWP known answers, the controllers, the Cholesky utilities
-    -- run on the NumPy backend the parity fixtures were produced on (oracle/refshim/run_reference_tests.py; the record
-    is profiles/r3k_reference_own_tests_on_numpy_backend.txt)."""
+    """Where the reference's sources exist (the build container): the modules of the reference's OWN test-suite that
+    concern this path -- solver vs an independent integrator on a pytree-valued Lotka-Volterra problem, save_at (55
+    tests), fixed grid == adaptive grid, dense == isotropic == block-diagonal, filter vs smoother, fixed-interval vs
+    fixed-point smoother, dynamic and MLE calibration, both log-marginal-likelihood losses, sampling, dense output,
+    priors (is_exact, output scales, diffuse derivatives), the second-order harmonic oscillator, the IWP known
+    answers, the controllers, the Cholesky utilities -- run on the NumPy backend the parity fixtures were produced on
+    (oracle/refshim/run_reference_tests.py; the record is profiles/r3k_reference_own_tests_on_numpy_backend.txt)."""
     import os
     import subprocess
     import sys
@@ -94,4 +95,4 @@ def test_the_references_own_tests_pass_on_this_backend():
     run = subprocess.run([sys.executable, "-m", "oracle.refshim.run_reference_tests"], cwd=root, capture_output=True,
                          text=True, env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1"), timeout=600)  # fmt: skip
     last = run.stdout.strip().splitlines()[-1]
-    assert run.returncode == 0 and "38 passed" in last and "failed" not in last, run.stdout[-2000:]
+    assert run.returncode == 0 and "204 passed" in last and "failed" not in last, run.stdout[-2000:]
