@@ -252,3 +252,32 @@ def test_host_mirror_of_the_problem_and_prior_helpers():
             assert np.allclose(a, np.asarray(ra), rtol=0, atol=0) and np.allclose(q, np.asarray(rq), rtol=1e-15, atol=1e-16)
             rp, rpinv = ref.preconditioner_taylor(nu)(0.37)
             assert np.allclose(p, np.asarray(rp), rtol=1e-15) and np.allclose(pinv, np.asarray(rpinv), rtol=1e-15)
+
+
+def test_the_product_never_touches_the_oracle_or_the_reference():
+    """The oracle (and the shim that runs the reference) are test infrastructure: nothing under probdiffeq_b200/ may
+    import them, read the fixtures, or look for the reference's sources -- statically (no such import or path in any
+    product source file) and dynamically (importing the product and building a solver pulls in no `oracle` module)."""
+    import subprocess
+    import sys
+
+    root = pathlib.Path(__file__).resolve().parents[1]
+    pattern = re.compile(r"^\s*(from|import)\s+oracle\b|/root/reference|tests/golden|refshim", re.MULTILINE)
+    for path in sorted((root / "probdiffeq_b200").rglob("*")):
+        if path.suffix in (".py", ".cu", ".cuh", ".cc", ".h") and "lib" not in path.relative_to(root).parts[1:2]:
+            text = path.read_text(errors="ignore")
+            hits = [m.group(0) for m in pattern.finditer(text)]
+            # comments may cite reference file:line, never an absolute path to it
+            assert not hits, (str(path), hits)
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from probdiffeq_b200 import ivpsolve, probdiffeq, sharding, plugins\n"
+        "vf = probdiffeq.ode('lotka_volterra', params=[0.5, 0.05, 0.5, 0.05])\n"
+        "ssm = probdiffeq.state_space_model_isotropic(); c = ssm.constraint_ode_ts0(vf)\n"
+        "s = probdiffeq.solver(strategy=probdiffeq.strategy_filter(), constraint=c)\n"
+        "ivpsolve.solve_adaptive_terminal_values(solver=s, error=probdiffeq.error_state_std(constraint=c))\n"
+        "bad = [m for m in sys.modules if m == 'oracle' or m.startswith('oracle.')]\n"
+        "assert not bad, bad\n" % str(root)
+    )
+    run = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stderr[-2000:]
