@@ -10,7 +10,7 @@ reproduced is XLA's arithmetic (operation fusion, its LAPACK calls) and JAX's au
 rounding level, not bit for bit.
 
 The backend is validated by the reference's OWN test-suite: `python -m oracle.refshim.run_reference_tests` runs the
-modules of `/root/reference/tests` that concern this path on it (204 pass, none fails; tests/test_refshim_backend.py).
+modules of `/root/reference/tests` that concern this path on it (224 pass, none fails; tests/test_refshim_backend.py).
 
 Used by `tests/golden/make_reference_golden.py` (which only runs where `/root/reference` exists, i.e. in the build
 container) to write `tests/golden/reference_numpy_backend.npz`: outputs of the reference's own step loop that pin the

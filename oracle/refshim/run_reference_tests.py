@@ -43,6 +43,9 @@ MODULES = (
     "test_probdiffeq/test_priors/test_output_scales.py",
     "test_probdiffeq/test_priors/test_diffuse_derivatives.py",
     "test_probdiffeq/test_sample.py",
+    "test_probdiffeq/test_jacobian_handling.py",
+    "test_probdiffeq/test_constraints/test_ts1_vs_residual.py",
+    "test_probdiffeq/test_jetexpand/test_ode.py",  # (its three-body cases need diffeqzoo and skip)
 )
 
 
